@@ -1,0 +1,23 @@
+"""imcoalhmm_b200 -- B200-native drop-in for IMCoalHMM's likelihood hot path.
+
+Public surface (mirrors /root/reference/src/IMCoalHMM for this path only):
+    Forwarder(input_filename, NSYM).forward(pi, T, E) -> float            hmm.py:10-21
+    Forwarder.fromSequence / Forwarder.fromDirectory                      legacy pyZipHMM constructors
+    ForwarderSet(forwarders).forward / .forward_batch                     likelihood.py:33, batched
+    Likelihood(model, forwarders)(theta) / .batched(thetas)               likelihood.py:8-33
+    ziphmm.preprocess_raw_observations / ziphmm.zip_forward               hmm.py:16,20-21
+
+Importing the package needs the in-tree shared library (python -m imcoalhmm_b200.build); there is no
+CPU fallback.  CUDA itself is initialised lazily by the first forward call.
+"""
+from . import _lib
+
+_lib.load()   # fail loudly at import time if the CUDA library is missing
+
+from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel  # noqa: E402
+from .hmm import Forwarder, ForwarderSet  # noqa: E402
+from .likelihood import Likelihood  # noqa: E402
+from . import ziphmm  # noqa: E402
+
+__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm",
+           "set_option", "get_option", "kernel_launches", "last_forward_kernel"]

@@ -1,0 +1,96 @@
+"""ctypes binding of libimcoalhmm_b200.so (include/imcoalhmm_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every
+forward call fails loudly when no B200 is usable.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libimcoalhmm_b200.so")
+
+
+class IMCError(RuntimeError):
+    """Raised for every non-zero return code of the C ABI."""
+
+    def __init__(self, code, message):
+        super().__init__("imcoalhmm_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "imc_last_error": (ctypes.c_char_p, []),
+    "imc_version": (ctypes.c_int, []),
+    "imc_init": (ctypes.c_int, [ctypes.c_int]),
+    "imc_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "imc_seq_create": (ctypes.c_int, [c_i32p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seq_create_u8": (ctypes.c_int, [c_u8p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seq_from_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seq_length": (ctypes.c_int, [c_vp, c_i64p]),
+    "imc_seq_nsym": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "imc_seq_symbol_counts": (ctypes.c_int, [c_vp, c_i64p]),
+    "imc_seq_symbols": (ctypes.c_int, [c_vp, c_u8p, ctypes.c_int64]),
+    "imc_seq_destroy": (ctypes.c_int, [c_vp]),
+    "imc_seqset_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seqset_destroy": (ctypes.c_int, [c_vp]),
+    "imc_seqset_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), c_i64p, c_i64p]),
+    "imc_forward": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "imc_forward_batch": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f64p, c_f64p, c_f64p,
+                                         c_f64p]),
+    "imc_forward_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
+                                             c_vp]),
+    "imc_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
+    "imc_get_option": (ctypes.c_int, [ctypes.c_char_p, c_i64p]),
+    "imc_kernel_launches": (ctypes.c_int64, []),
+    "imc_last_forward_kernel": (ctypes.c_char_p, []),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError with the build hint when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not found: build it with `python -m imcoalhmm_b200.build` "
+                              "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError here == header/library mismatch
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise IMCError(rc, load().imc_last_error().decode("utf-8", "replace"))
+
+
+def set_option(key, value):
+    check(load().imc_set_option(key.encode(), int(value)))
+
+
+def get_option(key):
+    v = ctypes.c_int64()
+    check(load().imc_get_option(key.encode(), ctypes.byref(v)))
+    return v.value
+
+
+def kernel_launches():
+    return int(load().imc_kernel_launches())
+
+
+def last_forward_kernel():
+    return load().imc_last_forward_kernel().decode()

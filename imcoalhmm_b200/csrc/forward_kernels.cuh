@@ -1,0 +1,470 @@
+// Forward log-likelihood kernels for sm_100a (B200).
+//
+// What they compute (reference semantics: /root/reference/src/IMCoalHMM/hmm.py:19-21 -> ziphmm.zip_forward,
+// summed over forwarders at likelihood.py:33):
+//     alpha_0 = pi o E[:,o_0];  alpha_t = (T^T alpha_{t-1}) o E[:,o_t];  logL = log sum_j alpha_L-1[j]
+// for every chain = (parameter point n, sequence stream s).  Scaling is by exact powers of two (the
+// exponent of sum(alpha) is moved into an integer accumulator), so no rounding is introduced by the
+// rescale and logL = ln2 * sum(exponents) + log(sum(alpha_final)).
+//
+// Measured on this pool's B200 (tools/microbench/fp64_micro.cu, profiles/r01_fp64_micro.txt):
+//   DFMA 34.2 TFLOP/s, DMMA.8x8x4 37.1 TFLOP/s, broadcast LDS only 8 B/clk/SM.  Hence T lives in REGISTERS:
+//   * fwd_pair_kernel<K>   (small even K, e.g. 10): two lanes per chain, each owns K/2 output states and the
+//                          matching K x K/2 slice of T in registers; 10 SHFL per step exchange the halves.
+//   * fwd_dmma_kernel<K,MT> (K = 16..64): chains are rows of an m8n8k4 FP64 MMA, T is held as B fragments
+//                          (K*K/32 doubles per lane); the C fragment of step t is the A fragment of step t+1
+//                          under a fixed permutation of the state order, so no data moves between steps.
+//   * fwd_generic_kernel   any K <= 128: state in shared memory, rescale every step.  Correctness baseline
+//                          and the path for parameter points whose per-step decay could underflow 16 steps.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace imc {
+
+struct StreamInfo {
+    long long base;  // index of word 0 of this stream in the packed word array; word w is at base + 32*w
+    int nwords;      // ceil(len / 16)
+    int len;         // symbols
+};
+
+struct FwdArgs {
+    const uint32_t* words;
+    const StreamInfo* streams;
+    int nstreams;
+    int N, K, S;
+    const double* pi;  // [N][K]
+    const double* T;   // [N][K][K]
+    const double* E;   // [N][K][S]
+    double* chain_out; // [N][nstreams]
+    long long nchains; // N * nstreams
+};
+
+constexpr double LN2 = 0.693147180559945309417232121458;
+
+__device__ __forceinline__ int exponent_of(double x) {
+    return ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+}
+__device__ __forceinline__ double pow2_neg(int e) {  // 2^-e for e in [-1023, 1023]
+    return __hiloint2double((1023 - e) << 20, 0);
+}
+// result of a finished chain: log(sum) + scale*ln2; -inf when the sequence is impossible under the model
+__device__ __forceinline__ double finish_logl(double sum, int scale) {
+    if (sum == 0.0) return -INFINITY;
+    return log(sum) + (double)scale * LN2;
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: one thread per chain, one parameter point per CTA (blockIdx.y), state in shared memory
+// ------------------------------------------------------------------------------------------------
+__global__ void fwd_generic_kernel(FwdArgs a) {
+    extern __shared__ double sm[];
+    const int K = a.K, S = a.S, nt = blockDim.x, tid = threadIdx.x;
+    const int theta = blockIdx.y;
+    double* Ts = sm;               // [K][K]
+    double* Es = Ts + K * K;       // [4][K], row 3 (padding code) = 1
+    double* A = Es + 4 * K;        // [K][nt]
+    double* B = A + (size_t)K * nt;
+    const double* Tg = a.T + (size_t)theta * K * K;
+    const double* Eg = a.E + (size_t)theta * K * S;
+    const double* pig = a.pi + (size_t)theta * K;
+    for (int x = tid; x < K * K; x += nt) Ts[x] = Tg[x];
+    for (int x = tid; x < 4 * K; x += nt) {
+        const int s = x / K, j = x % K;
+        Es[x] = s < S ? Eg[j * S + s] : 1.0;
+    }
+    __syncthreads();
+    const int stream = blockIdx.x * nt + tid;
+    if (stream >= a.nstreams) return;
+    const StreamInfo si = a.streams[stream];
+    const uint32_t* wp = a.words + si.base;
+    int scale = 0;
+    bool dead = false;
+    for (int w = 0; w < si.nwords; ++w) {
+        uint32_t word = wp[(long long)w * 32];
+        const int hi = min(16, si.len - 16 * w);
+        for (int t = 0; t < hi; ++t) {
+            const int o = word & 3u;
+            word >>= 2;
+            double sum = 0.0;
+            if (w == 0 && t == 0) {
+                for (int j = 0; j < K; ++j) {
+                    const double v = pig[j] * Es[o * K + j];
+                    A[j * nt + tid] = v;
+                    sum += v;
+                }
+            } else {
+                for (int j = 0; j < K; ++j) {
+                    double acc = 0.0;
+                    for (int i = 0; i < K; ++i) acc = fma(A[i * nt + tid], Ts[i * K + j], acc);
+                    acc *= Es[o * K + j];
+                    B[j * nt + tid] = acc;
+                    sum += acc;
+                }
+                double* tmp = A; A = B; B = tmp;
+            }
+            if (!(sum > 0.0)) { dead = dead || (sum == 0.0); continue; }
+            const int e = exponent_of(sum);
+            const double f = pow2_neg(e);
+            for (int j = 0; j < K; ++j) A[j * nt + tid] *= f;
+            scale += e;
+        }
+    }
+    double sum = 0.0;
+    for (int j = 0; j < K; ++j) sum += A[j * nt + tid];
+    a.chain_out[(size_t)theta * a.nstreams + stream] = dead ? -INFINITY : finish_logl(sum, scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane-pair DFMA kernel: 16 chains per warp, T slice in registers
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct PairCfg {
+    static constexpr int H = K / 2;
+    static constexpr int Hp = (H + 1) & ~1;        // padded to an even count (16-byte rows)
+    static constexpr int ROW = 4 * Hp;             // doubles of E table per lane: [4 symbols][Hp]
+    static constexpr int THREADS = 128;
+    static constexpr size_t smem_bytes() { return (size_t)THREADS * ROW * sizeof(double); }
+};
+
+template <int K>
+__device__ __forceinline__ void pair_step(double (&al)[K], const double (&To)[K / 2][K / 2],
+                                          const double (&Tx)[K / 2][K / 2], const double* erow) {
+    constexpr int H = K / 2;
+    double b[H];
+#pragma unroll
+    for (int jj = 0; jj < H; ++jj) b[jj] = al[0] * To[0][jj];
+#pragma unroll
+    for (int ii = 1; ii < H; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) b[jj] = fma(al[ii], To[ii][jj], b[jj]);
+#pragma unroll
+    for (int ii = 0; ii < H; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) b[jj] = fma(al[H + ii], Tx[ii][jj], b[jj]);
+#pragma unroll
+    for (int jj = 0; jj < H; ++jj) {
+        const double v = b[jj] * erow[jj];
+        al[jj] = v;
+        al[H + jj] = shfl_xor_f64(v, 1);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(PairCfg<K>::THREADS) fwd_pair_kernel(FwdArgs a) {
+    using C = PairCfg<K>;
+    constexpr int H = C::H, Hp = C::Hp;
+    extern __shared__ __align__(16) double esm_all[];
+    const int lane = threadIdx.x & 31, h = lane & 1, wib = threadIdx.x >> 5;
+    double* esm = esm_all + (size_t)(wib * 32 + lane) * C::ROW;
+    long long chain = ((long long)blockIdx.x * (C::THREADS / 32) + wib) * 16 + (lane >> 1);
+    const bool valid = chain < a.nchains;
+    if (!valid) chain = a.nchains - 1;
+    const int theta = (int)(chain / a.nstreams), s = (int)(chain % a.nstreams);
+    const StreamInfo si = a.streams[s];
+    const double* Tg = a.T + (size_t)theta * K * K;
+    const double* Eg = a.E + (size_t)theta * K * a.S;
+    const double* pig = a.pi + (size_t)theta * K;
+
+    // T slice: this lane produces output states h*H .. h*H+H-1.  To: inputs from its own half, Tx: from the partner's.
+    double To[H][H], Tx[H][H];
+#pragma unroll
+    for (int ii = 0; ii < H; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) {
+            To[ii][jj] = Tg[(h * H + ii) * K + h * H + jj];
+            Tx[ii][jj] = Tg[((1 - h) * H + ii) * K + h * H + jj];
+        }
+#pragma unroll
+    for (int sym = 0; sym < 4; ++sym)
+#pragma unroll
+        for (int jj = 0; jj < Hp; ++jj)
+            esm[sym * Hp + jj] = (sym < a.S && jj < H) ? Eg[(h * H + jj) * a.S + sym] : 1.0;
+    __syncwarp();
+
+    const uint32_t* wp = a.words + si.base;
+    const int nw = si.nwords;
+    int maxnw = nw;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) maxnw = max(maxnw, __shfl_xor_sync(0xffffffffu, maxnw, m));
+
+    double al[K];  // [own half | partner half]
+    int scale = 0;
+    bool dead = false;
+    double result = 0.0;
+    uint32_t word = wp[0];
+    {   // position 0: alpha = pi o E[:, o_0]
+        const int o = word & 3u;
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) {
+            const double v = pig[h * H + jj] * esm[o * Hp + jj];
+            al[jj] = v;
+            al[H + jj] = shfl_xor_f64(v, 1);
+        }
+    }
+    for (int w = 0; w < maxnw; ++w) {
+        const uint32_t next = wp[(long long)min(w + 1, nw - 1) * 32];
+        const int lo = (w == 0) ? 1 : 0;
+        const int hi = max(0, min(16, si.len - 16 * w));
+        const bool full = (lo == 0) && (hi == 16);
+        if (__all_sync(0xffffffffu, full)) {
+            uint32_t ww = word;
+#pragma unroll 4
+            for (int t = 0; t < 16; ++t) {
+                const int o = ww & 3u;
+                ww >>= 2;
+                pair_step<K>(al, To, Tx, esm + o * Hp);
+            }
+        } else {
+            uint32_t ww = word >> (2 * lo);
+#pragma unroll 1
+            for (int t = lo; t < 16; ++t) {
+                const int o = ww & 3u;
+                ww >>= 2;
+                double old[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) old[k] = al[k];
+                pair_step<K>(al, To, Tx, esm + o * Hp);
+                const bool act = t < hi;
+#pragma unroll
+                for (int k = 0; k < K; ++k) al[k] = act ? al[k] : old[k];
+            }
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) sum += al[k];
+        if (sum > 0.0) {
+            const int e = exponent_of(sum);
+            const double f = pow2_neg(e);
+#pragma unroll
+            for (int k = 0; k < K; ++k) al[k] *= f;
+            scale += e;
+            sum *= f;
+        } else if (w < nw) {
+            dead = true;   // sum == 0 (impossible observation) or NaN input
+            if (sum != sum) result = sum;
+        }
+        if (w == nw - 1) result = dead ? (result != result ? result : -INFINITY) : finish_logl(sum, scale);
+        word = next;
+    }
+    if (valid && h == 0) a.chain_out[chain] = result;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA kernel: chains are rows of m8n8k4 tiles; T as B fragments in registers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int K>
+struct DmmaCfg {
+    static constexpr int NT = (K + 7) / 8;                 // output tiles of 8 states
+    static constexpr int REM = K - 8 * (NT - 1);           // valid states in the last tile (1..8)
+    static constexpr bool LAST_ONE = REM <= 4;             // last tile packed into its r=0 registers only
+    static constexpr int KS = 2 * (NT - 1) + (LAST_ONE ? 1 : 2);  // k-slices of 4 states
+    // state held at column n (0..7) of C tile t; -1 = padding
+    __host__ __device__ static constexpr int state_of(int t, int n) {
+        if (t < NT - 1 || !LAST_ONE) { return (8 * t + n < K) ? 8 * t + n : -1; }
+        return ((n & 1) == 0 && (n >> 1) < REM) ? 8 * t + (n >> 1) : -1;
+    }
+};
+
+template <int K, int MT>
+struct DmmaState {
+    double c[MT][DmmaCfg<K>::NT][2];
+};
+
+// one forward step for MT tiles of 8 chains; o[mt] = symbol of this lane's chain in tile mt
+template <int K, int MT>
+__device__ __forceinline__ void dmma_step(DmmaState<K, MT>& st, const double (&Bf)[DmmaCfg<K>::KS][DmmaCfg<K>::NT],
+                                          const double* esm, const int (&o)[MT], int q) {
+    using C = DmmaCfg<K>;
+    constexpr int NT = C::NT, KS = C::KS;
+    double n[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { n[mt][t][0] = 0.0; n[mt][t][1] = 0.0; }
+#pragma unroll
+    for (int sl = 0; sl < KS; ++sl)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) dmma884(n[mt][t][0], n[mt][t][1], st.c[mt][sl >> 1][sl & 1], Bf[sl][t]);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double2 e = *reinterpret_cast<const double2*>(esm + ((o[mt] * NT + t) * 4 + q) * 2);
+            st.c[mt][t][0] = n[mt][t][0] * e.x;
+            st.c[mt][t][1] = n[mt][t][1] * e.y;
+        }
+}
+
+template <int K, int MT>
+__global__ void __launch_bounds__(128) fwd_dmma_kernel(FwdArgs a) {
+    using C = DmmaCfg<K>;
+    constexpr int NT = C::NT, KS = C::KS;
+    __shared__ __align__(16) double esm[4 * NT * 8];   // [sym][tile][q][r], sym 3 (padding) = 1
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, wib = threadIdx.x >> 5;
+    const int theta = blockIdx.y;
+    const double* Tg = a.T + (size_t)theta * K * K;
+    const double* Eg = a.E + (size_t)theta * K * a.S;
+    const double* pig = a.pi + (size_t)theta * K;
+    for (int x = threadIdx.x; x < 4 * NT * 8; x += blockDim.x) {
+        const int r = x & 1, qq = (x >> 1) & 3, t = (x >> 3) % NT, sym = (x >> 3) / NT;
+        const int stt = C::state_of(t, 2 * qq + r);
+        esm[x] = (stt >= 0 && sym < a.S) ? Eg[stt * a.S + sym] : (stt >= 0 ? 1.0 : 0.0);
+    }
+    // B fragments: lane holds row kq = lane&3 (input state) and column n = lane>>2 (output state)
+    double Bf[KS][NT];
+#pragma unroll
+    for (int sl = 0; sl < KS; ++sl) {
+        const int sin = C::state_of(sl >> 1, 2 * q + (sl & 1));
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int sout = C::state_of(t, g);
+            Bf[sl][t] = (sin >= 0 && sout >= 0) ? Tg[sin * K + sout] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const int tile0 = (blockIdx.x * (blockDim.x >> 5) + wib) * MT;     // first M-tile of this warp
+    const uint32_t* wp[MT];
+    int nw[MT], len[MT];
+    bool valid[MT];
+    int maxnw = 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        int s = (tile0 + mt) * 8 + g;
+        valid[mt] = s < a.nstreams;
+        if (!valid[mt]) s = a.nstreams - 1;
+        const StreamInfo si = a.streams[s];
+        wp[mt] = a.words + si.base;
+        nw[mt] = si.nwords;
+        len[mt] = si.len;
+        maxnw = max(maxnw, nw[mt]);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) maxnw = max(maxnw, __shfl_xor_sync(0xffffffffu, maxnw, m));
+    if (tile0 * 8 >= a.nstreams) return;   // whole warp past the end (warp-uniform)
+
+    DmmaState<K, MT> st;
+    int scale[MT];
+    bool dead[MT];
+    double result[MT];
+    uint32_t word[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        scale[mt] = 0; dead[mt] = false; result[mt] = 0.0;
+        word[mt] = wp[mt][0];
+        const int o = word[mt] & 3u;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int stt = C::state_of(t, 2 * q + r);
+                st.c[mt][t][r] = stt >= 0 ? pig[stt] * esm[((o * NT + t) * 4 + q) * 2 + r] : 0.0;
+            }
+    }
+    for (int w = 0; w < maxnw; ++w) {
+        uint32_t next[MT];
+        int hi[MT];
+        bool full = true;
+        const int lo = (w == 0) ? 1 : 0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            next[mt] = wp[mt][(long long)min(w + 1, nw[mt] - 1) * 32];
+            hi[mt] = max(0, min(16, len[mt] - 16 * w));
+            full = full && (lo == 0) && (hi[mt] == 16);
+        }
+        if (__all_sync(0xffffffffu, full)) {
+            uint32_t ww[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) ww[mt] = word[mt];
+#pragma unroll 2
+            for (int t = 0; t < 16; ++t) {
+                int o[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { o[mt] = ww[mt] & 3u; ww[mt] >>= 2; }
+                dmma_step<K, MT>(st, Bf, esm, o, q);
+            }
+        } else {
+            uint32_t ww[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) ww[mt] = word[mt] >> (2 * lo);
+#pragma unroll 1
+            for (int t = lo; t < 16; ++t) {
+                int o[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { o[mt] = ww[mt] & 3u; ww[mt] >>= 2; }
+                DmmaState<K, MT> old = st;
+                dmma_step<K, MT>(st, Bf, esm, o, q);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const bool act = t < hi[mt];
+#pragma unroll
+                    for (int tt = 0; tt < NT; ++tt) {
+                        st.c[mt][tt][0] = act ? st.c[mt][tt][0] : old.c[mt][tt][0];
+                        st.c[mt][tt][1] = act ? st.c[mt][tt][1] : old.c[mt][tt][1];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            double sum = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) sum += st.c[mt][t][0] + st.c[mt][t][1];
+            sum += shfl_xor_f64(sum, 1);
+            sum += shfl_xor_f64(sum, 2);
+            if (sum > 0.0) {
+                const int e = exponent_of(sum);
+                const double f = pow2_neg(e);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { st.c[mt][t][0] *= f; st.c[mt][t][1] *= f; }
+                scale[mt] += e;
+                sum *= f;
+            } else if (w < nw[mt]) {
+                dead[mt] = true;
+                if (sum != sum) result[mt] = sum;
+            }
+            if (w == nw[mt] - 1)
+                result[mt] = dead[mt] ? (result[mt] != result[mt] ? result[mt] : -INFINITY) : finish_logl(sum, scale[mt]);
+            word[mt] = next[mt];
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int s = (tile0 + mt) * 8 + g;
+        if (valid[mt] && q == 0) a.chain_out[(size_t)theta * a.nstreams + s] = result[mt];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[n] = sum_s chain_out[n][s] with a fixed-shape tree (bitwise reproducible run to run)
+// ------------------------------------------------------------------------------------------------
+__global__ void reduce_chains_kernel(const double* chain_out, int nstreams, double* out) {
+    __shared__ double sh[256];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const double* src = chain_out + (size_t)n * nstreams;
+    double acc = 0.0;
+    for (int s = tid; s < nstreams; s += 256) acc += src[s];
+    sh[tid] = acc;
+    __syncthreads();
+    for (int m = 128; m >= 1; m >>= 1) {
+        if (tid < m) sh[tid] += sh[tid + m];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = sh[0];
+}
+
+}  // namespace imc

@@ -1,0 +1,522 @@
+// libimcoalhmm_b200.so -- host side: sequences, packed sequence sets, launchers and the C ABI
+// declared in include/imcoalhmm_b200.h.  No CPU fallback: every forward entry point needs the GPU.
+#include "../../include/imcoalhmm_b200.h"
+#include "forward_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+using namespace imc;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static thread_local const char* g_last_kernel = "none";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) return fail(IMC_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ context
+struct Context {
+    std::mutex mu;
+    int device = -1;          // requested device (-1 = default 0)
+    bool ready = false;
+    pid_t pid = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    long long opt_forward_kernel = 0;
+    long long opt_dmma_mtiles = 0;
+};
+static Context g_ctx;
+
+static int ensure_device() {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (g_ctx.ready) {
+        if (g_ctx.pid != getpid())
+            return fail(IMC_ERR_CUDA, "CUDA was initialised in the parent before fork(); create the context in the "
+                                      "child (construct Forwarders before forking, call forward only in children, "
+                                      "or use the 'spawn' start method)");
+        return IMC_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(IMC_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    const int dev = g_ctx.device < 0 ? 0 : g_ctx.device;
+    if (dev >= count) return fail(IMC_ERR_INVALID, "device %d requested but only %d present", dev, count);
+    CUDA_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(IMC_ERR_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", dev, prop.major, prop.minor);
+    g_ctx.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.device = dev;
+    g_ctx.pid = getpid();
+    g_ctx.ready = true;
+    return IMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sequences
+struct imc_seq {
+    std::vector<uint8_t> sym;
+    int nsym = 0;
+};
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return IMC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CUDA_TRY(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return IMC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct imc_seqset {
+    int n_chunks = 0;
+    int nsym = 0;
+    long long total_sites = 0;
+    // host-side packed layout
+    std::vector<uint32_t> words;          // bundles of 32 streams, word-interleaved, 16 two-bit symbols per word
+    std::vector<StreamInfo> streams;      // non-empty chunks only, sorted by length (descending)
+    // device side (lazy)
+    bool uploaded = false;
+    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out;
+};
+
+static int seq_finish(imc_seq* s, imc_seq** out) {
+    *out = s;
+    return IMC_OK;
+}
+
+extern "C" const char* imc_last_error(void) { return g_err.c_str(); }
+extern "C" int imc_version(void) { return 100; }
+
+extern "C" int imc_init(int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        if (g_ctx.ready && g_ctx.device != device && g_ctx.pid == getpid())
+            return fail(IMC_ERR_INVALID, "context already bound to device %d", g_ctx.device);
+        if (!g_ctx.ready) g_ctx.device = device;
+    }
+    return ensure_device();
+}
+
+extern "C" int imc_device_count(int* count_out) {
+    if (!count_out) return fail(IMC_ERR_INVALID, "count_out is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    *count_out = (e == cudaSuccess) ? c : 0;
+    return IMC_OK;
+}
+
+template <typename Tin>
+static int seq_create_impl(const Tin* obs, int64_t L, int nsym, imc_seq** out) {
+    if (!out) return fail(IMC_ERR_INVALID, "out is NULL");
+    if (L < 0 || (L > 0 && !obs)) return fail(IMC_ERR_INVALID, "bad observation buffer");
+    if (nsym < 1 || nsym > 255) return fail(IMC_ERR_INVALID, "nsym must be in [1, 255], got %d", nsym);
+    imc_seq* s = new (std::nothrow) imc_seq;
+    if (!s) return fail(IMC_ERR_NOMEM, "out of memory");
+    s->nsym = nsym;
+    try { s->sym.resize((size_t)L); } catch (...) { delete s; return fail(IMC_ERR_NOMEM, "out of memory for %lld symbols", (long long)L); }
+    for (int64_t t = 0; t < L; ++t) {
+        const long long v = (long long)obs[t];
+        if (v < 0 || v >= nsym) {
+            delete s;
+            return fail(IMC_ERR_INVALID, "symbol %lld at position %lld is outside [0, %d)", v, (long long)t, nsym);
+        }
+        s->sym[(size_t)t] = (uint8_t)v;
+    }
+    return seq_finish(s, out);
+}
+
+extern "C" int imc_seq_create(const int32_t* obs, int64_t L, int nsym, imc_seq** out) {
+    return seq_create_impl(obs, L, nsym, out);
+}
+extern "C" int imc_seq_create_u8(const uint8_t* obs, int64_t L, int nsym, imc_seq** out) {
+    return seq_create_impl(obs, L, nsym, out);
+}
+
+extern "C" int imc_seq_from_file(const char* path, int nsym, imc_seq** out) {
+    if (!path || !out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (nsym < 1 || nsym > 255) return fail(IMC_ERR_INVALID, "nsym must be in [1, 255], got %d", nsym);
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
+    imc_seq* s = new (std::nothrow) imc_seq;
+    if (!s) { fclose(f); return fail(IMC_ERR_NOMEM, "out of memory"); }
+    s->nsym = nsym;
+    // whitespace-separated base-10 integers (python: map(int, text.split()), hmm.py:13-14)
+    std::vector<char> buf(1 << 20);
+    long long cur = 0;
+    bool in_num = false, neg = false;
+    int rc = IMC_OK;
+    size_t got;
+    long long pos = 0;
+    auto flush = [&]() -> int {
+        if (!in_num) return IMC_OK;
+        const long long v = neg ? -cur : cur;
+        if (v < 0 || v >= nsym) return fail(IMC_ERR_INVALID, "symbol %lld (token %zu) in '%s' is outside [0, %d)", v, s->sym.size(), path, nsym);
+        s->sym.push_back((uint8_t)v);
+        in_num = false; neg = false; cur = 0;
+        return IMC_OK;
+    };
+    while (rc == IMC_OK && (got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        for (size_t i = 0; i < got && rc == IMC_OK; ++i, ++pos) {
+            const char ch = buf[i];
+            if (ch >= '0' && ch <= '9') {
+                cur = cur * 10 + (ch - '0');
+                if (cur > 1000000) cur = 1000000;  // saturate; rejected by the range check
+                in_num = true;
+            } else if (ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\f' || ch == '\v') {
+                rc = flush();
+            } else if ((ch == '-' || ch == '+') && !in_num) {
+                neg = (ch == '-'); in_num = true;
+            } else {
+                rc = fail(IMC_ERR_IO, "unexpected character 0x%02x at byte %lld of '%s'", (unsigned char)ch, pos, path);
+            }
+        }
+    }
+    if (rc == IMC_OK) rc = flush();
+    fclose(f);
+    if (rc != IMC_OK) { delete s; return rc; }
+    return seq_finish(s, out);
+}
+
+extern "C" int imc_seq_length(const imc_seq* seq, int64_t* L_out) {
+    if (!seq || !L_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    *L_out = (int64_t)seq->sym.size();
+    return IMC_OK;
+}
+extern "C" int imc_seq_nsym(const imc_seq* seq, int* nsym_out) {
+    if (!seq || !nsym_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    *nsym_out = seq->nsym;
+    return IMC_OK;
+}
+extern "C" int imc_seq_symbol_counts(const imc_seq* seq, int64_t* counts) {
+    if (!seq || !counts) return fail(IMC_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < seq->nsym; ++i) counts[i] = 0;
+    for (uint8_t v : seq->sym) counts[v]++;
+    return IMC_OK;
+}
+extern "C" int imc_seq_symbols(const imc_seq* seq, uint8_t* out, int64_t capacity) {
+    if (!seq || !out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (capacity < (int64_t)seq->sym.size()) return fail(IMC_ERR_INVALID, "capacity %lld < length %zu", (long long)capacity, seq->sym.size());
+    memcpy(out, seq->sym.data(), seq->sym.size());
+    return IMC_OK;
+}
+extern "C" int imc_seq_destroy(imc_seq* seq) {
+    delete seq;
+    return IMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sequence sets
+extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset** out) {
+    if (!out || C < 0 || (C > 0 && !seqs)) return fail(IMC_ERR_INVALID, "bad arguments");
+    imc_seqset* set = new (std::nothrow) imc_seqset;
+    if (!set) return fail(IMC_ERR_NOMEM, "out of memory");
+    set->n_chunks = C;
+    std::vector<int> order;
+    for (int c = 0; c < C; ++c) {
+        if (!seqs[c]) { delete set; return fail(IMC_ERR_INVALID, "seqs[%d] is NULL", c); }
+        if (c == 0) set->nsym = seqs[c]->nsym;
+        if (seqs[c]->nsym != set->nsym) { delete set; return fail(IMC_ERR_INVALID, "chunks disagree on nsym (%d vs %d)", seqs[c]->nsym, set->nsym); }
+        if (seqs[c]->sym.size() > 0x7fffffffULL) { delete set; return fail(IMC_ERR_UNSUPPORTED, "chunk %d has more than 2^31-1 sites; split it", c); }
+        set->total_sites += (long long)seqs[c]->sym.size();
+        if (!seqs[c]->sym.empty()) order.push_back(c);   // an empty chunk contributes logL = 0
+    }
+    if (set->nsym > 3 && !order.empty()) {
+        delete set;
+        return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols are not packed yet (nsym = %d)", set->nsym);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seqs[x]->sym.size() > seqs[y]->sym.size(); });
+    const int ns = (int)order.size();
+    set->streams.resize(ns);
+    long long word_off = 0;   // in words
+    try {
+        for (int b0 = 0; b0 < ns; b0 += 32) {
+            const int nb = std::min(32, ns - b0);
+            const long long maxlen = (long long)seqs[order[b0]]->sym.size();
+            const long long nwords = (maxlen + 15) / 16;
+            set->words.resize((size_t)(word_off + nwords * 32), 0xffffffffu);   // code 3 everywhere = padding
+            for (int k = 0; k < nb; ++k) {
+                const imc_seq* sq = seqs[order[b0 + k]];
+                const long long len = (long long)sq->sym.size();
+                StreamInfo& si = set->streams[b0 + k];
+                si.base = word_off + k;
+                si.len = (int)len;
+                si.nwords = (int)((len + 15) / 16);
+                for (long long w = 0; w < si.nwords; ++w) {
+                    uint32_t v = 0xffffffffu;
+                    const long long t0 = w * 16, t1 = std::min(len, t0 + 16);
+                    for (long long t = t0; t < t1; ++t) {
+                        const int sh = 2 * (int)(t - t0);
+                        v = (v & ~(3u << sh)) | ((uint32_t)sq->sym[(size_t)t] << sh);
+                    }
+                    set->words[(size_t)(word_off + w * 32 + k)] = v;
+                }
+            }
+            word_off += nwords * 32;
+        }
+    } catch (...) { delete set; return fail(IMC_ERR_NOMEM, "out of host memory while packing"); }
+    *out = set;
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_destroy(imc_seqset* set) {
+    if (!set) return IMC_OK;
+    if (set->uploaded && g_ctx.pid == getpid()) {
+        set->d_words.release(); set->d_streams.release(); set->d_chain.release();
+        set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
+    }
+    delete set;
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_info(const imc_seqset* set, int* n_chunks, int64_t* total_sites, int64_t* packed_bytes) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (n_chunks) *n_chunks = set->n_chunks;
+    if (total_sites) *total_sites = set->total_sites;
+    if (packed_bytes) *packed_bytes = (int64_t)(set->words.size() * sizeof(uint32_t));
+    return IMC_OK;
+}
+
+static int seqset_upload(imc_seqset* set) {
+    if (set->uploaded) return IMC_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!set->streams.empty()) {
+        if ((rc = set->d_words.reserve(set->words.size() * sizeof(uint32_t)))) return rc;
+        if ((rc = set->d_streams.reserve(set->streams.size() * sizeof(StreamInfo)))) return rc;
+        CUDA_TRY(cudaMemcpy(set->d_words.p, set->words.data(), set->words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(set->d_streams.p, set->streams.data(), set->streams.size() * sizeof(StreamInfo), cudaMemcpyHostToDevice));
+    }
+    set->uploaded = true;
+    return IMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3 };
+
+static bool pair_supported(int K) { return K == 2 || K == 4 || K == 6 || K == 8 || K == 10 || K == 12; }
+static bool dmma_supported(int K) {
+    switch (K) { case 10: case 12: case 16: case 20: case 24: case 28: case 32: case 36: case 40: case 48: case 64: return true; }
+    return false;
+}
+
+template <int K>
+static int launch_pair(const FwdArgs& a, cudaStream_t st) {
+    using C = PairCfg<K>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(fwd_pair_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes()));
+        attr_set = true;
+    }
+    const long long warps = (a.nchains + 15) / 16;
+    const int wpb = C::THREADS / 32;
+    const long long blocks = (warps + wpb - 1) / wpb;
+    fwd_pair_kernel<K><<<(unsigned)blocks, C::THREADS, C::smem_bytes(), st>>>(a);
+    return IMC_OK;
+}
+
+template <int K, int MT>
+static int launch_dmma_mt(const FwdArgs& a, cudaStream_t st) {
+    const int tiles = (a.nstreams + 7) / 8;
+    const int warps = (tiles + MT - 1) / MT;
+    const int wpb = 4;
+    dim3 grid((warps + wpb - 1) / wpb, a.N);
+    fwd_dmma_kernel<K, MT><<<grid, wpb * 32, 0, st>>>(a);
+    return IMC_OK;
+}
+
+template <int K>
+static int launch_dmma(const FwdArgs& a, cudaStream_t st, int mt_opt) {
+    constexpr int NT = DmmaCfg<K>::NT;
+    constexpr int MAXMT = NT <= 3 ? 4 : (NT <= 5 ? 2 : 1);   // keep 2*MT*NT*2 state doubles + K*K/32 fragment doubles in registers
+    int mt = mt_opt;
+    if (mt == 0) {
+        // enough warps to give every SM sub-partition at least two; otherwise fewer chains per warp
+        const long long tiles = (long long)((a.nstreams + 7) / 8) * a.N;
+        const long long want = 2LL * 4 * (g_ctx.sm_count > 0 ? g_ctx.sm_count : 148);
+        mt = MAXMT;
+        while (mt > 1 && tiles / mt < want) mt >>= 1;
+    }
+    if (mt > MAXMT) mt = MAXMT;
+    if constexpr (MAXMT >= 4) { if (mt == 4) return launch_dmma_mt<K, 4>(a, st); }
+    if constexpr (MAXMT >= 2) { if (mt >= 2) return launch_dmma_mt<K, 2>(a, st); }
+    return launch_dmma_mt<K, 1>(a, st);
+}
+
+static int launch_generic(const FwdArgs& a, cudaStream_t st) {
+    const int K = a.K;
+    int threads = K <= 64 ? 128 : (K <= 100 ? 64 : 32);
+    if (a.nstreams <= 32) threads = 32; else if (a.nstreams <= 64 && threads > 64) threads = 64;
+    const size_t smem = ((size_t)K * K + 4 * (size_t)K + 2 * (size_t)K * threads) * sizeof(double);
+    if (smem > 227 * 1024) return fail(IMC_ERR_UNSUPPORTED, "K = %d needs %zu bytes of shared memory (max 232448)", K, smem);
+    static size_t attr_max = 0;
+    if (smem > attr_max) {
+        CUDA_TRY(cudaFuncSetAttribute(fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_max = smem;
+    }
+    dim3 grid((a.nstreams + threads - 1) / threads, a.N);
+    fwd_generic_kernel<<<grid, threads, smem, st>>>(a);
+    return IMC_OK;
+}
+
+static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
+                       double* d_out, cudaStream_t st) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (N < 0 || K < 1 || S < 1) return fail(IMC_ERR_INVALID, "bad sizes N=%d K=%d S=%d", N, K, S);
+    if (N == 0) return IMC_OK;
+    if (!set->streams.empty() && S != set->nsym)
+        return fail(IMC_ERR_INVALID, "emission matrix has %d symbols but the sequences were created with nsym = %d", S, set->nsym);
+    if (K > 128) return fail(IMC_ERR_UNSUPPORTED, "K = %d > 128 is not supported", K);
+    int rc = seqset_upload(set);
+    if (rc) return rc;
+    const int ns = (int)set->streams.size();
+    if (ns == 0) {   // only empty chunks: logL = 0 for every point
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)N, st));
+        return IMC_OK;
+    }
+    if ((rc = set->d_chain.reserve(sizeof(double) * (size_t)N * ns))) return rc;
+    FwdArgs a;
+    a.words = (const uint32_t*)set->d_words.p;
+    a.streams = (const StreamInfo*)set->d_streams.p;
+    a.nstreams = ns;
+    a.N = N; a.K = K; a.S = S;
+    a.pi = d_pi; a.T = d_T; a.E = d_E;
+    a.chain_out = (double*)set->d_chain.p;
+    a.nchains = (long long)N * ns;
+
+    int which = (int)g_ctx.opt_forward_kernel;
+    if (which == KERNEL_AUTO) which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
+    if (which == KERNEL_PAIR) {
+        if (!pair_supported(K)) return fail(IMC_ERR_UNSUPPORTED, "lane-pair kernel covers even K <= 12, not K = %d", K);
+        g_last_kernel = "pair";
+        switch (K) {
+            case 2: rc = launch_pair<2>(a, st); break;
+            case 4: rc = launch_pair<4>(a, st); break;
+            case 6: rc = launch_pair<6>(a, st); break;
+            case 8: rc = launch_pair<8>(a, st); break;
+            case 10: rc = launch_pair<10>(a, st); break;
+            case 12: rc = launch_pair<12>(a, st); break;
+        }
+    } else if (which == KERNEL_DMMA) {
+        if (!dmma_supported(K)) return fail(IMC_ERR_UNSUPPORTED, "DMMA kernel is not instantiated for K = %d", K);
+        g_last_kernel = "dmma";
+        const int mt = (int)g_ctx.opt_dmma_mtiles;
+        switch (K) {
+            case 10: rc = launch_dmma<10>(a, st, mt); break;
+            case 12: rc = launch_dmma<12>(a, st, mt); break;
+            case 16: rc = launch_dmma<16>(a, st, mt); break;
+            case 20: rc = launch_dmma<20>(a, st, mt); break;
+            case 24: rc = launch_dmma<24>(a, st, mt); break;
+            case 28: rc = launch_dmma<28>(a, st, mt); break;
+            case 32: rc = launch_dmma<32>(a, st, mt); break;
+            case 36: rc = launch_dmma<36>(a, st, mt); break;
+            case 40: rc = launch_dmma<40>(a, st, mt); break;
+            case 48: rc = launch_dmma<48>(a, st, mt); break;
+            case 64: rc = launch_dmma<64>(a, st, mt); break;
+        }
+    } else if (which == KERNEL_GENERIC) {
+        g_last_kernel = "generic";
+        rc = launch_generic(a, st);
+    } else {
+        return fail(IMC_ERR_INVALID, "unknown forward_kernel option %d", which);
+    }
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    reduce_chains_kernel<<<N, 256, 0, st>>>(a.chain_out, ns, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 2;
+    return IMC_OK;
+}
+
+extern "C" int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T,
+                                     const double* d_E, double* d_out, void* stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (N > 0 && (!d_pi || !d_T || !d_E || !d_out)) return fail(IMC_ERR_INVALID, "NULL device pointer");
+    return forward_dev(set, N, K, S, d_pi, d_T, d_E, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int imc_forward_batch(imc_seqset* set, int N, int K, int S, const double* pi, const double* T,
+                                 const double* E, double* out) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (N < 0 || K < 1 || S < 1) return fail(IMC_ERR_INVALID, "bad sizes N=%d K=%d S=%d", N, K, S);
+    if (N == 0) return IMC_OK;
+    if (!pi || !T || !E || !out) return fail(IMC_ERR_INVALID, "NULL host pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const size_t npi = (size_t)N * K, nT = (size_t)N * K * K, nE = (size_t)N * K * S;
+    if ((rc = set->d_pi.reserve(npi * sizeof(double)))) return rc;
+    if ((rc = set->d_T.reserve(nT * sizeof(double)))) return rc;
+    if ((rc = set->d_E.reserve(nE * sizeof(double)))) return rc;
+    if ((rc = set->d_out.reserve((size_t)N * sizeof(double)))) return rc;
+    cudaStream_t st = g_ctx.stream;
+    CUDA_TRY(cudaMemcpyAsync(set->d_pi.p, pi, npi * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(set->d_T.p, T, nT * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(set->d_E.p, E, nE * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = forward_dev(set, N, K, S, (const double*)set->d_pi.p, (const double*)set->d_T.p, (const double*)set->d_E.p,
+                     (double*)set->d_out.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, set->d_out.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IMC_OK;
+}
+
+extern "C" int imc_forward(imc_seqset* set, int K, int S, const double* pi, const double* T, const double* E,
+                           double* logL_out) {
+    return imc_forward_batch(set, 1, K, S, pi, T, E, logL_out);
+}
+
+// ------------------------------------------------------------------------------------------ options
+extern "C" int imc_set_option(const char* key, int64_t value) {
+    if (!key) return fail(IMC_ERR_INVALID, "NULL key");
+    if (!strcmp(key, "forward_kernel")) {
+        if (value < 0 || value > 3) return fail(IMC_ERR_INVALID, "forward_kernel must be 0..3");
+        g_ctx.opt_forward_kernel = value;
+        return IMC_OK;
+    }
+    if (!strcmp(key, "dmma_mtiles")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return fail(IMC_ERR_INVALID, "dmma_mtiles must be 0, 1, 2 or 4");
+        g_ctx.opt_dmma_mtiles = value;
+        return IMC_OK;
+    }
+    return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
+}
+extern "C" int imc_get_option(const char* key, int64_t* value_out) {
+    if (!key || !value_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "forward_kernel")) { *value_out = g_ctx.opt_forward_kernel; return IMC_OK; }
+    if (!strcmp(key, "dmma_mtiles")) { *value_out = g_ctx.opt_dmma_mtiles; return IMC_OK; }
+    return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
+}
+extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }
+extern "C" const char* imc_last_forward_kernel(void) { return g_last_kernel; }

@@ -1,0 +1,227 @@
+"""Drop-in for the reference's Forwarder boundary (/root/reference/src/IMCoalHMM/hmm.py:10-21).
+
+`Forwarder(input_filename, NSYM)` and `.forward(init_probs, trans_probs, emission_probs) -> float`
+keep the reference's names, argument meaning and error behaviour; the arithmetic runs in the
+hand-written sm_100a kernels of libimcoalhmm_b200.so through its C ABI.  New on top of the
+reference: `forward_batch` (N parameter points per call) and `ForwarderSet` (all the chunks a
+Likelihood sums over, likelihood.py:33, scored in one launch).
+
+The legacy pyZipHMM constructors used by the reference's ILS scripts are mirrored as
+`Forwarder.fromSequence` (scripts/prepare-alignments.py:201) and `Forwarder.fromDirectory`
+(scripts/ils-isolation-model.py:112).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import IMCError, check  # noqa: F401  (re-exported)
+
+
+def _as_f64(a, shape_tail, what):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if a.shape[-len(shape_tail):] != tuple(shape_tail):
+        raise ValueError("%s has shape %s, expected (..., %s)" % (what, a.shape, ", ".join(map(str, shape_tail))))
+    return a
+
+
+def _hmm_arrays(pis, Ts, Es, batched):
+    """Normalise (pi, T, E) to contiguous float64 arrays [N,K], [N,K,K], [N,K,S]."""
+    Ts = np.ascontiguousarray(np.asarray(Ts, dtype=np.float64))
+    if not batched:
+        Ts = Ts[None]
+    if Ts.ndim != 3 or Ts.shape[1] != Ts.shape[2]:
+        raise ValueError("transition matrix must be square, got shape %s" % (Ts.shape[1:],))
+    N, K = Ts.shape[0], Ts.shape[1]
+    pis = np.ascontiguousarray(np.asarray(pis, dtype=np.float64)).reshape(N, -1)   # accepts (K,), (K,1), (1,K)
+    if pis.shape[1] != K:
+        raise ValueError("initial probabilities have %d entries for %d states" % (pis.shape[1], K))
+    Es = np.ascontiguousarray(np.asarray(Es, dtype=np.float64))
+    if not batched:
+        Es = Es[None]
+    if Es.ndim != 3 or Es.shape[0] != N or Es.shape[1] != K:
+        raise ValueError("emission matrix has shape %s, expected (%d, S)" % (Es.shape[1:], K))
+    return pis, Ts, Es, N, K, Es.shape[2]
+
+
+class _Seq(object):
+    """Owner of one imc_seq handle."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().imc_seq_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def length(self):
+        n = ctypes.c_int64()
+        check(_lib.load().imc_seq_length(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def symbols(self):
+        out = np.empty(self.length, dtype=np.uint8)
+        check(_lib.load().imc_seq_symbols(self.handle, out.ctypes.data_as(_lib.c_u8p), out.size))
+        return out
+
+
+class ForwarderSet(object):
+    """The chunks a Likelihood sums over, packed once and resident on the GPU.
+
+    forward(pi, T, E) == sum(f.forward(pi, T, E) for f in forwarders)   (likelihood.py:33)
+    """
+
+    def __init__(self, forwarders):
+        if isinstance(forwarders, Forwarder):
+            forwarders = [forwarders]
+        self.forwarders = list(forwarders)
+        self._seqs = [f._seq for f in self.forwarders]   # keep the handles alive
+        lib = _lib.load()
+        arr = (_lib.c_vp * max(1, len(self._seqs)))(*[s.handle for s in self._seqs])
+        h = _lib.c_vp()
+        check(lib.imc_seqset_create(arr, len(self._seqs), ctypes.byref(h)))
+        self._handle = h
+        n, sites, nbytes = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib.imc_seqset_info(h, ctypes.byref(n), ctypes.byref(sites), ctypes.byref(nbytes)))
+        self.n_chunks, self.total_sites, self.packed_bytes = n.value, sites.value, nbytes.value
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                _lib.load().imc_seqset_destroy(h)
+            except Exception:
+                pass
+
+    def __len__(self):
+        return self.n_chunks
+
+    def forward(self, init_probs, trans_probs, emission_probs):
+        pis, Ts, Es, _, K, S = _hmm_arrays(init_probs, trans_probs, emission_probs, batched=False)
+        out = ctypes.c_double()
+        check(_lib.load().imc_forward(self._handle, K, S, pis.ctypes.data_as(_lib.c_f64p),
+                                      Ts.ctypes.data_as(_lib.c_f64p), Es.ctypes.data_as(_lib.c_f64p),
+                                      ctypes.byref(out)))
+        return out.value
+
+    def forward_batch(self, pis, Ts, Es, out=None):
+        """logL for N parameter points: pis [N,K], Ts [N,K,K], Es [N,K,S] (host arrays) -> float64[N]."""
+        pis, Ts, Es, N, K, S = _hmm_arrays(pis, Ts, Es, batched=True)
+        if out is None:
+            out = np.empty(N, dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == N and out.flags.c_contiguous
+        check(_lib.load().imc_forward_batch(self._handle, N, K, S, pis.ctypes.data_as(_lib.c_f64p),
+                                            Ts.ctypes.data_as(_lib.c_f64p), Es.ctypes.data_as(_lib.c_f64p),
+                                            out.ctypes.data_as(_lib.c_f64p)))
+        return out
+
+    def forward_batch_device(self, d_pi, d_T, d_E, d_out, N, K, S, stream=0):
+        """Device-resident variant: arguments are raw device pointers (ints); enqueued on `stream`."""
+        check(_lib.load().imc_forward_batch_dev(self._handle, int(N), int(K), int(S), int(d_pi), int(d_T), int(d_E),
+                                                int(d_out), int(stream)))
+
+
+class Forwarder(object):
+    """One alignment chunk (reference: hmm.py:10-21)."""
+
+    def __init__(self, input_filename, NSYM):
+        lib = _lib.load()
+        h = _lib.c_vp()
+        rc = lib.imc_seq_from_file(os.fsencode(input_filename), int(NSYM), ctypes.byref(h))
+        if rc == -5 and not os.path.exists(input_filename):
+            raise IOError(lib.imc_last_error().decode())     # the reference's open() raises IOError
+        if rc == -5 or rc == -1:
+            raise ValueError(lib.imc_last_error().decode())  # int('x') / out-of-range symbol
+        check(rc)
+        self._finish(_Seq(h), NSYM)
+
+    def _finish(self, seq, NSYM):
+        self._seq = seq
+        self.NSYM = int(NSYM)
+        self._set = None
+
+    @classmethod
+    def from_symbols(cls, obs, NSYM):
+        """Build from an in-memory array of symbols in [0, NSYM) (what hmm.py:14 parses from the file)."""
+        self = cls.__new__(cls)
+        lib = _lib.load()
+        h = _lib.c_vp()
+        obs = np.asarray(obs)
+        if obs.dtype == np.uint8:
+            obs = np.ascontiguousarray(obs)
+            check(lib.imc_seq_create_u8(obs.ctypes.data_as(_lib.c_u8p), obs.size, int(NSYM), ctypes.byref(h)))
+        else:
+            obs = np.ascontiguousarray(obs, dtype=np.int32)
+            check(lib.imc_seq_create(obs.ctypes.data_as(_lib.c_i32p), obs.size, int(NSYM), ctypes.byref(h)))
+        self._finish(_Seq(h), NSYM)
+        return self
+
+    # -- legacy pyZipHMM constructors -------------------------------------------------------------
+    @classmethod
+    def fromSequence(cls, seqFilename, alphabetSize, minNoEvals=500):
+        """pyZipHMM.Forwarder.fromSequence (scripts/prepare-alignments.py:201).  minNoEvals tuned zipHMM's
+        CPU compression and has no meaning here; it is accepted and ignored."""
+        return cls(seqFilename, alphabetSize)
+
+    @classmethod
+    def fromDirectory(cls, directory):
+        """pyZipHMM.Forwarder.fromDirectory (scripts/ils-isolation-model.py:112).  The legacy directory
+        schema is not in the reference; only the file names are evidenced (.gitignore:2-4,38-40):
+        read `original_sequence` (same integer text format) and take the alphabet size from the first
+        integer of `data_structure` when it parses, else max symbol + 1."""
+        seq_file = os.path.join(directory, "original_sequence")
+        if not os.path.exists(seq_file):
+            raise IOError("no 'original_sequence' in zipHMM directory %r" % (directory,))
+        nsym = None
+        ds = os.path.join(directory, "data_structure")
+        if os.path.exists(ds):
+            try:
+                with open(ds) as f:
+                    for tok in f.read().split():
+                        if tok.lstrip("-").isdigit():
+                            nsym = int(tok)
+                            break
+            except (IOError, OSError):
+                nsym = None
+        with open(seq_file) as f:
+            obs = np.array(f.read().split(), dtype=np.int64)
+        if nsym is None or nsym <= int(obs.max(initial=0)):
+            nsym = int(obs.max(initial=0)) + 1
+        return cls.from_symbols(obs.astype(np.int32), nsym)
+
+    # -- reference attributes (hmm.py:15-16).  No pair compression is applied on the host: the identity
+    # re-encoding is exact, and ziphmm.zip_forward accepts it. ---------------------------------------
+    @property
+    def new_obs(self):
+        from .ziphmm import _tag
+        return _tag(self._seq.symbols().astype(np.int32), self)
+
+    @property
+    def sym2pair(self):
+        return np.zeros((0, 2), dtype=np.int32)
+
+    @property
+    def new_nsyms(self):
+        return self.NSYM
+
+    def __len__(self):
+        return self._seq.length
+
+    def _as_set(self):
+        if self._set is None:
+            self._set = ForwarderSet([self])
+        return self._set
+
+    def forward(self, init_probs, trans_probs, emission_probs):
+        """log P(sequence | pi, T, E) as a python float (hmm.py:19-21)."""
+        return self._as_set().forward(init_probs, trans_probs, emission_probs)
+
+    def forward_batch(self, pis, Ts, Es):
+        """The same for N parameter points at once -> float64[N]."""
+        return self._as_set().forward_batch(pis, Ts, Es)

@@ -1,0 +1,48 @@
+"""Likelihood glue (reference: /root/reference/src/IMCoalHMM/likelihood.py:8-33) + the batched entry.
+
+`Likelihood(model, forwarders)(theta)` keeps the reference's contract: invalid parameters give -inf
+(likelihood.py:29-30), otherwise the model's (pi, T, E) is scored on every forwarder and the
+log-likelihoods are added (likelihood.py:33).  All forwarders are packed into one ForwarderSet so the
+sum is one launch.  `batched(thetas)` scores N parameter points per call.
+"""
+import numpy as np
+
+from .hmm import Forwarder, ForwarderSet
+
+
+class Likelihood(object):
+    def __init__(self, model, forwarders):
+        self.model = model
+        if isinstance(forwarders, ForwarderSet):
+            self.forwarder_set = forwarders
+            self.forwarders = forwarders.forwarders
+        else:
+            if isinstance(forwarders, Forwarder) or not hasattr(forwarders, "__iter__"):
+                forwarders = [forwarders]     # likelihood.py:22-25
+            self.forwarders = list(forwarders)
+            if all(isinstance(f, Forwarder) for f in self.forwarders):
+                self.forwarder_set = ForwarderSet(self.forwarders)
+            else:
+                self.forwarder_set = None     # foreign forwarder objects: fall back to the reference's loop
+
+    def __call__(self, *parameters):
+        if not self.model.valid_parameters(*parameters):
+            return -float("inf")
+        pi, T, E = self.model.build_hidden_markov_model(*parameters)
+        if self.forwarder_set is not None:
+            return self.forwarder_set.forward(pi, T, E)
+        return sum(f.forward(pi, T, E) for f in self.forwarders)
+
+    def batched(self, thetas):
+        """float64[N] of log-likelihoods for thetas[N, P]; invalid rows give -inf."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        out = np.full(thetas.shape[0], -np.inf)
+        if hasattr(self.model, "batched_log_likelihood"):
+            return self.model.batched_log_likelihood(thetas, self.forwarder_set)
+        ok = np.array([bool(self.model.valid_parameters(th)) for th in thetas])
+        if ok.any():
+            hmms = [self.model.build_hidden_markov_model(th) for th in thetas[ok]]
+            out[ok] = self.forwarder_set.forward_batch(np.stack([h[0] for h in hmms]),
+                                                       np.stack([h[1] for h in hmms]),
+                                                       np.stack([h[2] for h in hmms]))
+        return out

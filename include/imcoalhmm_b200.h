@@ -1,0 +1,100 @@
+/*
+ * imcoalhmm_b200.h -- C ABI of the B200-native IMCoalHMM likelihood hot path.
+ *
+ * The reference (harvardinformatics/IMCoalHMM) has no C ABI of its own: its forward arithmetic lives in
+ * the external CPython extension `ziphmm`, reached at exactly two call sites
+ *     /root/reference/src/IMCoalHMM/hmm.py:16      ziphmm.preprocess_raw_observations(obs, NSYM)
+ *     /root/reference/src/IMCoalHMM/hmm.py:20-21   ziphmm.zip_forward(pi, T, E, sym2pair, new_obs, NSYM, new_nsyms)
+ * and its model build is Python (model.py:44-49).  The entry points below are what a ctypes / cffi binding
+ * for that path binds instead (see INTEGRATION.md for the stub).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns IMC_OK (0) or a negative IMC_ERR_* code; imc_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - all floating point is IEEE binary64.  pi is [K], T is [K][K] row-major with T[i][j] = P(next=j | cur=i)
+ *     (transitions.py:243-246), E is [K][S] with E[state][symbol] (emissions.py:95-99).
+ *   - batched arrays are [N][...] contiguous: pi [N][K], T [N][K][K], E [N][K][S], out [N].
+ *   - caller owns every host buffer; the library copies in/out and keeps no host pointer past return.
+ *   - there is NO CPU fallback: calls that need the GPU fail with IMC_ERR_CUDA when no device is usable.
+ *   - CUDA is initialised lazily by the first call that needs the device (imc_init or a forward call),
+ *     so a process may create sequences, fork (mcmc.py:113-122), and only then touch the GPU in the child.
+ */
+#ifndef IMCOALHMM_B200_H
+#define IMCOALHMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMC_OK 0
+#define IMC_ERR_INVALID (-1)     /* bad argument (shape, NULL, symbol out of range, ...) */
+#define IMC_ERR_CUDA (-2)        /* CUDA runtime failure or no usable device */
+#define IMC_ERR_NOMEM (-3)
+#define IMC_ERR_UNSUPPORTED (-4) /* valid request outside what the kernels cover (e.g. K > 128) */
+#define IMC_ERR_IO (-5)          /* file could not be read / parsed */
+
+const char* imc_last_error(void);
+int imc_version(void);
+
+/* Select the device for the calling process (default 0) and create the context.  Optional: the first
+ * forward call does it implicitly on device 0 (or the device given by an earlier imc_init). */
+int imc_init(int device);
+int imc_device_count(int* count_out);
+
+/* ---- sequences: one alignment chunk == one reference Forwarder (hmm.py:12-16) --------------------- */
+typedef struct imc_seq imc_seq;
+
+/* obs[L] symbols in [0, nsym).  Replaces np.array(map(int, ...), dtype=np.int32) + preprocess (hmm.py:14-16). */
+int imc_seq_create(const int32_t* obs, int64_t L, int nsym, imc_seq** out);
+int imc_seq_create_u8(const uint8_t* obs, int64_t L, int nsym, imc_seq** out);
+/* Text file of whitespace-separated integers (hmm.py:13-14; written by scripts/prepare-alignments.py:93-105). */
+int imc_seq_from_file(const char* path, int nsym, imc_seq** out);
+int imc_seq_length(const imc_seq* seq, int64_t* L_out);
+int imc_seq_nsym(const imc_seq* seq, int* nsym_out);
+/* counts[nsym] <- number of occurrences of each symbol */
+int imc_seq_symbol_counts(const imc_seq* seq, int64_t* counts);
+/* copy the symbols back (uint8), e.g. to check the encoding byte-for-byte */
+int imc_seq_symbols(const imc_seq* seq, uint8_t* out, int64_t capacity);
+int imc_seq_destroy(imc_seq* seq);
+
+/* ---- sequence sets: the list of forwarders a Likelihood sums over (likelihood.py:22-25,33), packed into
+ * the interleaved 2-bit layout the kernels stream from HBM.  Host-only until the first forward call. */
+typedef struct imc_seqset imc_seqset;
+
+int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset** out);
+int imc_seqset_destroy(imc_seqset* set);
+/* any output may be NULL */
+int imc_seqset_info(const imc_seqset* set, int* n_chunks, int64_t* total_sites, int64_t* packed_bytes);
+
+/* ---- forward log-likelihood ------------------------------------------------------------------------ */
+/* logL_out[0] = sum over the set's chunks of log P(chunk | pi, T, E).  Replaces
+ * sum(f.forward(pi, T, E) for f in forwarders)  (hmm.py:19-21, likelihood.py:33). */
+int imc_forward(imc_seqset* set, int K, int S, const double* pi, const double* T, const double* E,
+                double* logL_out);
+
+/* The same for N parameter points in one call (new; the reference evaluates one point per call). */
+int imc_forward_batch(imc_seqset* set, int N, int K, int S, const double* pi, const double* T,
+                      const double* E, double* out);
+
+/* Device-resident variant: all four pointers are device memory on the set's device; work is enqueued on
+ * `stream` (a cudaStream_t, NULL = legacy default stream) and NOT synchronised. */
+int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T,
+                          const double* d_E, double* d_out, void* stream);
+
+/* ---- knobs and introspection (tests, bench) ---------------------------------------------------------- */
+/* key "forward_kernel": 0 auto, 1 generic (shared-memory state, per-step rescale), 2 lane-pair DFMA,
+ *                       3 DMMA tiles.  Forcing a kernel that does not cover (K, S) returns IMC_ERR_UNSUPPORTED.
+ * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto). */
+int imc_set_option(const char* key, int64_t value);
+int imc_get_option(const char* key, int64_t* value_out);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+int64_t imc_kernel_launches(void);
+/* name of the forward kernel chosen by the last forward call on this thread ("generic", "pair", "dmma") */
+const char* imc_last_forward_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMCOALHMM_B200_H */

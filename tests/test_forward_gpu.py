@@ -1,0 +1,178 @@
+"""Parity of the CUDA forward kernels with the CPU oracle, through the C ABI.
+
+Tolerance: north_star asks for 1e-9 relative; the kernels are held to 1e-11 here (expected ~1e-13).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_model, example_symbols, random_hmm, synthetic_sequence
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-11
+
+KERNELS = {"generic": 1, "pair": 2, "dmma": 3}
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    import imcoalhmm_b200 as m
+    yield
+    m.set_option("forward_kernel", 0)
+    m.set_option("dmma_mtiles", 0)
+
+
+def oracle_batch(chunks, pis, Ts, Es):
+    from oracle import forward as F
+    out, _ = F.forward_batch([np.asarray(c, dtype=np.int32) for c in chunks], pis, Ts, Es)
+    return out
+
+
+def make_set(chunks, nsym=3):
+    import imcoalhmm_b200 as m
+    return m.ForwarderSet([m.Forwarder.from_symbols(np.asarray(c), nsym) for c in chunks])
+
+
+def test_example_alignment_reference_models():
+    """config 1: hg18 vs pantro2, reference-built (pi,T,E), single evaluation (SURVEY 7.1c probe values)."""
+    import imcoalhmm_b200 as m
+    obs = example_symbols()
+    f = m.Forwarder.from_symbols(obs, 3)
+    _, pi, T, E = golden_model("isolation_k10")
+    assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3729.5586472699, rel=1e-11)
+    assert m.last_forward_kernel() == "pair"
+    _, pi, T, E = golden_model("im_k10_10")
+    assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
+    assert m.last_forward_kernel() == "dmma"
+
+
+@pytest.mark.parametrize("model,kernels", [
+    ("isolation_k4", ["generic", "pair"]),
+    ("isolation_k10", ["generic", "pair", "dmma"]),
+    ("im_k3_4", ["generic"]),
+    ("im_epochs_2_3_3", ["generic", "pair", "dmma"]),
+    ("im_k10_10", ["generic", "dmma"]),
+    ("psmc_iso_split_4x10", ["generic", "dmma"]),
+    ("varmig_i12_4x10", ["generic", "dmma"]),
+])
+def test_batch_parity_on_reference_models(model, kernels):
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(20261018)
+    _, pis, Ts, Es = golden_model(model)
+    obs = example_symbols()
+    # ragged chunks: includes a length-1 chunk, a chunk that ends mid-word, an empty chunk
+    cuts = [0, 1, 18, 5000, 5000, 21017, 40000, len(obs)]
+    chunks = [obs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    chunks += [rng.choice(3, size=n, p=[0.9, 0.05, 0.05]).astype(np.uint8) for n in (33, 64, 777, 4096, 15, 16, 17)]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    for k in kernels:
+        m.set_option("forward_kernel", KERNELS[k])
+        got = s.forward_batch(pis, Ts, Es)
+        assert m.last_forward_kernel() == k
+        np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="%s / %s" % (model, k))
+        one = s.forward(pis[-1], Ts[-1], Es[-1])
+        assert one == pytest.approx(want[-1], rel=RTOL)
+
+
+@pytest.mark.parametrize("K", [2, 6, 8, 12, 16, 24, 28, 32, 36, 48, 64])
+def test_random_hmms_all_instantiated_sizes(K):
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(K)
+    N = 5
+    hmms = [random_hmm(rng, K) for _ in range(N)]
+    pis, Ts, Es = (np.stack([h[i] for h in hmms]) for i in range(3))
+    chunks = [rng.integers(0, 3, size=n).astype(np.uint8) for n in (1, 2, 31, 32, 33, 500, 1000, 1000, 999, 47, 2048)]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    for k, code in KERNELS.items():
+        if k == "pair" and (K % 2 or K > 12):
+            continue
+        if k == "dmma" and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
+            continue
+        m.set_option("forward_kernel", code)
+        np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d %s" % (K, k))
+
+
+@pytest.mark.parametrize("K", [3, 5, 7, 9, 11, 13, 20, 40, 65, 100, 128])
+def test_generic_kernel_any_K(K):
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(100 + K)
+    pi, T, E = random_hmm(rng, K)
+    chunks = [rng.integers(0, 3, size=n).astype(np.uint8) for n in (300, 17, 64)]
+    want = oracle_batch(chunks, pi[None], T[None], E[None])[0]
+    m.set_option("forward_kernel", 1)
+    assert make_set(chunks).forward(pi, T, E) == pytest.approx(want, rel=RTOL)
+
+
+@pytest.mark.parametrize("mt", [1, 2, 4])
+def test_dmma_mtile_variants(mt):
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(mt)
+    _, pis, Ts, Es = golden_model("im_k10_10")
+    chunks = [rng.choice(3, size=int(n), p=[0.95, 0.01, 0.04]).astype(np.uint8) for n in rng.integers(900, 1100, size=70)]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    m.set_option("forward_kernel", 3)
+    m.set_option("dmma_mtiles", mt)
+    np.testing.assert_allclose(make_set(chunks).forward_batch(pis, Ts, Es), want, rtol=RTOL)
+
+
+def test_edge_cases():
+    import imcoalhmm_b200 as m
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    # all-missing: logL = log(sum(pi)) = 0 (emissions.py:99); empty set / empty chunks: 0
+    s = make_set([np.full(1000, 2, dtype=np.uint8)])
+    assert abs(s.forward(pis[0], Ts[0], Es[0])) < 1e-11
+    assert make_set([np.zeros(0, dtype=np.uint8)]).forward(pis[0], Ts[0], Es[0]) == 0.0
+    assert m.ForwarderSet([]).forward(pis[0], Ts[0], Es[0]) == 0.0
+    # single site
+    for o in range(3):
+        got = make_set([np.array([o], dtype=np.uint8)]).forward(pis[0], Ts[0], Es[0])
+        assert got == pytest.approx(np.log(pis[0] @ Es[0][:, o]), rel=1e-13)
+    # an impossible observation gives -inf, not NaN
+    E0 = Es[0].copy()
+    E0[:, 1] = 0.0
+    for code in (1, 2):
+        m.set_option("forward_kernel", code)
+        assert make_set([np.array([0, 0, 1, 0] * 10, dtype=np.uint8)]).forward(pis[0], Ts[0], E0) == -np.inf
+    m.set_option("forward_kernel", 0)
+    # shape errors are loud
+    with pytest.raises(ValueError):
+        s.forward(pis[0][:5], Ts[0], Es[0])
+    with pytest.raises(m.IMCError):
+        s.forward(pis[0], Ts[0], Es[0][:, :2])       # S != NSYM of the sequences
+    # (K,1) column vector for pi as pyZipHMM.Matrix users pass it
+    assert s.forward(pis[0].reshape(-1, 1), Ts[0], Es[0]) == pytest.approx(s.forward(pis[0], Ts[0], Es[0]))
+
+
+def test_properties_at_scale():
+    """Size-independent properties on inputs too large for a quick oracle pass: chunk additivity,
+    time-reversal invariance (reversible reference models), kernel-vs-kernel agreement."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(7)
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    obs = synthetic_sequence(rng, pis[0], Ts[0], Es[0], 400_000)
+    whole = make_set([obs]).forward_batch(pis[:8], Ts[:8], Es[:8])
+    rev = make_set([obs[::-1].copy()]).forward_batch(pis[:8], Ts[:8], Es[:8])
+    np.testing.assert_allclose(rev, whole, rtol=1e-11)
+    m.set_option("forward_kernel", 1)
+    np.testing.assert_allclose(make_set([obs]).forward_batch(pis[:8], Ts[:8], Es[:8]), whole, rtol=1e-11)
+    m.set_option("forward_kernel", 3)
+    np.testing.assert_allclose(make_set([obs]).forward_batch(pis[:8], Ts[:8], Es[:8]), whole, rtol=1e-11)
+    m.set_option("forward_kernel", 0)
+    # the oracle on the same input (0.4 Mbp x 8 points: ~1 s of CPU)
+    np.testing.assert_allclose(whole, oracle_batch([obs], pis[:8], Ts[:8], Es[:8]), rtol=RTOL)
+
+
+def test_ziphmm_module_contract():
+    """The two calls the reference's hmm.py makes (hmm.py:16, :20-21)."""
+    from imcoalhmm_b200 import ziphmm
+    from oracle import forward as F
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    obs = example_symbols().astype(np.int32)[:10000]
+    new_obs, sym2pair, new_nsyms = ziphmm.preprocess_raw_observations(obs, 3)
+    got = ziphmm.zip_forward(pis[0], Ts[0], Es[0], sym2pair, new_obs, 3, new_nsyms)
+    want = F.forward_plain(obs, pis[0], Ts[0], Es[0])
+    assert got == pytest.approx(want, rel=RTOL)
+    # a genuinely pair-compressed encoding produced elsewhere is accepted too
+    z_obs, z_pairs, z_n = F.zip_preprocess(obs, 3)
+    assert ziphmm.zip_forward(pis[0], Ts[0], Es[0], z_pairs, z_obs, 3, z_n) == pytest.approx(want, rel=RTOL)

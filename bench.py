@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- forward sites x parameter-points / second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2_small|c3_1gpu]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one batched log-likelihood evaluation: N_theta parameter points scored on every alignment
+chunk of the (per-rank) shard, logL[N_theta] out.  Rank 0 prints ONE JSON line.
+
+  value      device-timed (CUDA events on the launching stream, max over ranks) with the packed sequences and
+             the parameter batch resident in HBM; an L2 flush (256 MiB write) separates timed steps.
+  e2e        the same metric through the public host API (ForwarderSet.forward_batch -> imc_forward_batch):
+             (pi,T,E) copied from pinned host memory, logL copied back, every step, wall clock around the calls.
+             The sequences stay resident (uploaded once when the Forwarders are built, exactly like the
+             reference preprocesses once in Forwarder.__init__, hmm.py:12-16).
+  roofline   dominant kernel against the FP64 peak MEASURED IN THIS RUN (imc_measure_fp64_peak: DFMA and DMMA
+             loops; MEASURED_PEAKS.json has no FP64 entry).  achieved = sites*points*(2K^2+3K) / kernel time.
+  cpu_baseline  the CPU oracle's zipHMM-style forward (oracle/forward_oracle.c, OpenMP over all host cores) on a
+             bounded sample of the same workload -- a reported baseline, not the target.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED0 = 20261018
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: isolation model, 10 intervals, synthetic 100 Mbp, 256 parameter points, 1 B200
+    "c2": dict(model="isolation_k10", K=10, chunks=100, chunk_len=1_000_000, points=256,
+               desc="configs[1]: isolation model K=10, synthetic 100 Mbp (100 x 1 Mbp chunks), 256 parameter points"),
+    "c2_small": dict(model="isolation_k10", K=10, chunks=100, chunk_len=50_000, points=256,
+                     desc="reduced configs[1] for smoke runs: 100 x 50 kbp, 256 points"),
+    # per-GPU slice of configs[2] (IM model, K=20, 1 Gbp, 1024 points on 8 GPUs = 125 chunks/GPU)
+    "c3_1gpu": dict(model="im_k10_10", K=20, chunks=125, chunk_len=1_000_000, points=1024,
+                    desc="configs[2] per-GPU shard: IM model K=10+10, 125 x 1 Mbp chunks, 1024 parameter points"),
+}
+
+
+def flops_per_site_point(K):
+    return 2 * K * K + 3 * K
+
+
+# ---------------------------------------------------------------------------------------- synthetic data
+def simulate_chunk(rng, pi, T, E, L, missing=0.04, mean_run=100):
+    """Exact sample from the HMM (hidden path from (pi,T), symbols from E[:, :2]) + missing-data runs of
+    symbol 2 (geometric length, mean 100, ~4% coverage) -- SURVEY 8(d).  Jump-chain simulation: O(#jumps)."""
+    K = pi.size
+    stay = np.clip(np.diag(T), 0.0, 1.0 - 1e-15)
+    jump = T.copy()
+    np.fill_diagonal(jump, 0.0)
+    jump /= jump.sum(axis=1, keepdims=True)
+    cum = np.cumsum(jump, axis=1)
+    states, holds = [], []
+    s = int(rng.choice(K, p=pi / pi.sum()))
+    total = 0
+    while total < L:
+        h = int(rng.geometric(1.0 - stay[s]))
+        states.append(s)
+        holds.append(h)
+        total += h
+        s = min(int(np.searchsorted(cum[s], rng.random())), K - 1)
+    path = np.repeat(np.asarray(states), np.asarray(holds))[:L]
+    p1 = (E[:, 1] / (E[:, 0] + E[:, 1]))[path]
+    obs = (rng.random(L) < p1).astype(np.uint8)
+    n_runs = int(L * missing / mean_run * 1.5) + 8
+    gaps = rng.geometric(missing / (mean_run * (1.0 - missing)), size=n_runs)
+    runs = rng.geometric(1.0 / mean_run, size=n_runs)
+    ends = np.cumsum(gaps + runs)
+    starts = ends - runs
+    keep = starts < L
+    delta = np.zeros(L + 1, dtype=np.int32)
+    np.add.at(delta, starts[keep], 1)
+    np.add.at(delta, np.minimum(ends[keep], L), -1)
+    obs[np.cumsum(delta[:L]) > 0] = 2
+    return obs
+
+
+def load_points(model, n_points):
+    """(pi, T, E) for the parameter batch.  INTERIM (round 1): the committed reference-derived fixture
+    tests/golden/model_<name>.npz holds 16 points theta_b = default * exp(0.1 N(0,1)); they are tiled to
+    n_points.  Model build is therefore outside the timed region in this revision."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_%s.npz" % model))
+    reps = (n_points + g["pi"].shape[0] - 1) // g["pi"].shape[0]
+    pis = np.ascontiguousarray(np.tile(g["pi"], (reps, 1))[:n_points])
+    Ts = np.ascontiguousarray(np.tile(g["T"], (reps, 1, 1))[:n_points])
+    Es = np.ascontiguousarray(np.tile(g["E"], (reps, 1, 1))[:n_points])
+    return pis, Ts, Es
+
+
+def make_chunks(wl, pis, Ts, Es, chunk_ids):
+    out = []
+    for cid in chunk_ids:
+        rng = np.random.Generator(np.random.PCG64(SEED0 + int(cid)))
+        out.append(simulate_chunk(rng, pis[0], Ts[0], Es[0], wl["chunk_len"]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
+    """The reference's CPU path restated (oracle, zipHMM-style pair compression + forward, OpenMP over
+    (point, chunk) tasks on all host cores).  Each step scores a bounded sample of the workload."""
+    from oracle import forward as F
+    F.build()
+    ncores = os.cpu_count() or 1
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    # bounded sample: n_c chunks x n_p points sized from a calibration run
+    n_c = min(wl["chunks"], max(ncores, 8))
+    n_p = min(wl["points"], 16)
+    chunks = make_chunks(wl, pis, Ts, Es, range(n_c))
+    t0 = time.perf_counter()
+    zipped = [F.zip_preprocess(c.astype(np.int32), 3) for c in chunks]
+    t_prep = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped)
+    t_cal = time.perf_counter() - t0
+    per_step = budget_s / max(1, steps + warmup)
+    scale = max(1, min(wl["points"] // n_p, int(per_step / max(t_cal, 1e-4))))
+    n_p = min(wl["points"], n_p * scale)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, used = F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sites = sum(len(c) for c in chunks)
+    t = float(np.sum(times))
+    value = sites * n_p * len(times) / t
+    ratio = float(np.mean([len(c) / max(1, len(z[0])) for c, z in zip(chunks, zipped)]))
+    return {"value": value, "unit": "sites*points/s", "cores": int(used), "kind": "port",
+            "sample": "%d chunks x %d bp x %d points per step, zipHMM-style compressed forward (%.0fx fewer symbols, "
+                      "preprocess %.1fs excluded like hmm.py:16), OpenMP, %d steps" %
+                      (n_c, wl["chunk_len"], n_p, ratio, t_prep, len(times)),
+            "ms_per_step": 1e3 * t / len(times)}
+
+
+# ---------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K = wl["K"]
+    pis, Ts, Es = load_points(wl["model"], wl["points"])
+    config = {"workload": wl["desc"], "chunks_per_gpu": wl["chunks"], "chunk_len": wl["chunk_len"],
+              "points": wl["points"], "K": K, "sharding": "chunks across ranks, no data-path collective except one "
+              "all-reduce of float64[points]", "l2": "flushed between timed steps (256 MiB write)",
+              "model_build": "outside the timed region in this revision (fixture-derived pi,T,E)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = cpu_reference_run(wl, pis, Ts, Es, args.steps, max(args.warmup, 1))
+        line = {"metric": "forward sites*param-points/sec", "value": res["value"], "unit": "sites*points/s",
+                "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": 0,
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": "sites*points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import imcoalhmm_b200 as m
+    assert args.warmup >= 3 or args.steps <= 2, "timing rules: at least 3 warm-up steps"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    m._lib.check(m._lib.load().imc_init(local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # weak scaling: every rank owns wl["chunks"] chunks (distinct seeds), all ranks score the same points
+    chunk_ids = range(rank * wl["chunks"], (rank + 1) * wl["chunks"])
+    chunks = make_chunks(wl, pis, Ts, Es, chunk_ids)
+    fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
+    sites_rank = fset.total_sites
+    N, S = wl["points"], 3
+    d_pi, d_T, d_E = (torch.tensor(x, device=dev) for x in (pis, Ts, Es))
+    d_out = torch.empty(N, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        fset.forward_batch_device(d_pi.data_ptr(), d_T.data_ptr(), d_E.data_ptr(), d_out.data_ptr(), N, K, S,
+                                  stream.cuda_stream)
+        if dist is not None:
+            dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods
+
+    peak_dfma, peak_dmma = m.measure_fp64_peak()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    launches0 = m.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step()
+        b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = m.kernel_launches() - launches0
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    if dist is not None:
+        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+    logl_dev = d_out.cpu().numpy().copy()
+
+    # ---- kernel-only time of the dominant kernel (forward kernel without the reduce / all-reduce) ----
+    kt = []
+    for _ in range(min(3, args.steps)):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fset.forward_batch_device(d_pi.data_ptr(), d_T.data_ptr(), d_E.data_ptr(), d_out.data_ptr(), N, K, S,
+                                  stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b) * 1e-3)
+    t_kernel = float(np.mean(kt))
+
+    # ---- end to end through the host API: pinned host (pi,T,E) in, host logL out, every step ----
+    h_pi, h_T, h_E = (torch.tensor(x).pin_memory() for x in (pis, Ts, Es))
+    h_out = torch.empty(N, dtype=torch.float64).pin_memory()
+    np_pi, np_T, np_E, np_out = h_pi.numpy(), h_T.numpy(), h_E.numpy(), h_out.numpy()
+    for _ in range(2):
+        fset.forward_batch(np_pi, np_T, np_E, out=np_out)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fset.forward_batch(np_pi, np_T, np_E, out=np_out)      # synchronous: returns with logL on the host
+        if dist is not None:
+            tmp = torch.from_numpy(np_out).to(dev)
+            dist.all_reduce(tmp)
+            np_out[:] = tmp.cpu().numpy()
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    h2d = (pis.nbytes + Ts.nbytes + Es.nbytes)
+    d2h = N * 8
+    if world == 1:
+        assert np.allclose(np_out, logl_dev, rtol=1e-12), "host API and device API disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_site_points = float(sites_rank) * N * world
+    value = total_site_points * args.steps / t_dev
+    algo_flops = float(sites_rank) * N * flops_per_site_point(K)          # per launch (one rank)
+    peak = max(peak_dfma, peak_dmma)
+    achieved = algo_flops / t_kernel / 1e12
+    line = {
+        "metric": "forward sites*param-points/sec", "value": value, "unit": "sites*points/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config, "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": total_site_points * args.steps / t_e2e, "unit": "sites*points/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "roofline": {"bound": "fp64", "kernel": "imc::fwd_%s_kernel" % m.last_forward_kernel(),
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": "measured in this run (imc_measure_fp64_peak): DFMA %.1f, DMMA %.1f TFLOP/s; "
+                     "MEASURED_PEAKS.json has no FP64 entry" % (peak_dfma, peak_dmma),
+                     "algorithmic_flop_per_site_point": flops_per_site_point(K), "kernel_ms": 1e3 * t_kernel},
+        "logL_check": {"first": float(logl_dev[0]), "finite": bool(np.isfinite(logl_dev).all())},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, pis, Ts, Es, 3, 1).items() if k != "ms_per_step"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,17 +7,17 @@ Public surface (mirrors /root/reference/src/IMCoalHMM for this path only):
     Likelihood(model, forwarders)(theta) / .batched(thetas)               likelihood.py:8-33
     ziphmm.preprocess_raw_observations / ziphmm.zip_forward               hmm.py:16,20-21
 
-Importing the package needs the in-tree shared library (python -m imcoalhmm_b200.build); there is no
+Importing the package needs the in-tree shared library (python imcoalhmm_b200/build.py); there is no
 CPU fallback.  CUDA itself is initialised lazily by the first forward call.
 """
 from . import _lib
 
 _lib.load()   # fail loudly at import time if the CUDA library is missing
 
-from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel  # noqa: E402
+from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel, measure_fp64_peak  # noqa: E402
 from .hmm import Forwarder, ForwarderSet  # noqa: E402
 from .likelihood import Likelihood  # noqa: E402
 from . import ziphmm  # noqa: E402
 
 __all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm",
-           "set_option", "get_option", "kernel_launches", "last_forward_kernel"]
+           "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak"]

@@ -46,6 +46,7 @@ _SIGNATURES = {
                                          c_f64p]),
     "imc_forward_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                              c_vp]),
+    "imc_measure_fp64_peak": (ctypes.c_int, [c_f64p, c_f64p]),
     "imc_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "imc_get_option": (ctypes.c_int, [ctypes.c_char_p, c_i64p]),
     "imc_kernel_launches": (ctypes.c_int64, []),
@@ -62,7 +63,7 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError("%s not found: build it with `python -m imcoalhmm_b200.build` "
+            raise ImportError("%s not found: build it with `python imcoalhmm_b200/build.py` "
                               "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         lib = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in _SIGNATURES.items():
@@ -86,6 +87,13 @@ def get_option(key):
     v = ctypes.c_int64()
     check(load().imc_get_option(key.encode(), ctypes.byref(v)))
     return v.value
+
+
+def measure_fp64_peak():
+    """(dfma_tflops, dmma_tflops) measured on the bound device."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    check(load().imc_measure_fp64_peak(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 def kernel_launches():

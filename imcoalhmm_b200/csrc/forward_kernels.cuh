@@ -38,6 +38,7 @@ struct FwdArgs {
     const double* E;   // [N][K][S]
     double* chain_out; // [N][nstreams]
     long long nchains; // N * nstreams
+    int fold_sym;      // most frequent symbol of the set (its emission column is folded into T where possible)
 };
 
 constexpr double LN2 = 0.693147180559945309417232121458;
@@ -123,21 +124,31 @@ __global__ void fwd_generic_kernel(FwdArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // lane-pair DFMA kernel: 16 chains per warp, T slice in registers
+//
+// ncu (profiles/r01_pair10_v1.txt) showed the first version limited by the shared-memory data pipe:
+// 14 LDS wavefronts (per-lane emission rows) + 10 SHFL wavefronts per warp-step against 27.5 SM-cycles
+// of FP64 work.  This version folds the emission column of the most frequent symbol s0 into the register
+// copy of T (T0[i][j] = T[i][j] * E[j][s0]); a step whose symbol is s0 is then pure DFMA + the 10 SHFL, and
+// other symbols multiply by the ratio row E[:,o]/E[:,s0] (one LDS per lane that needs it, under a warp
+// vote).  Parameter points with E[j][s0] == 0 cannot be folded and take the unfolded loop.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct PairCfg {
     static constexpr int H = K / 2;
     static constexpr int Hp = (H + 1) & ~1;        // padded to an even count (16-byte rows)
-    static constexpr int ROW = 4 * Hp;             // doubles of E table per lane: [4 symbols][Hp]
+    // doubles of E table per lane: [4 symbols][Hp] + 2 of padding so that the per-lane stride is an ODD
+    // multiple of 16 bytes: the 8 lanes of a quarter-warp then fall into 8 different 16-byte bank groups
+    // (with a 192-byte stride they fell into 2 and every LDS.128 replayed 4x).
+    static constexpr int ROW = 4 * Hp + 2;
     static constexpr int THREADS = 128;
     static constexpr size_t smem_bytes() { return (size_t)THREADS * ROW * sizeof(double); }
 };
 
+// b = (T slice)^T alpha for this lane's H output states
 template <int K>
-__device__ __forceinline__ void pair_step(double (&al)[K], const double (&To)[K / 2][K / 2],
-                                          const double (&Tx)[K / 2][K / 2], const double* erow) {
+__device__ __forceinline__ void pair_matvec(const double (&al)[K], const double (&To)[K / 2][K / 2],
+                                            const double (&Tx)[K / 2][K / 2], double (&b)[K / 2]) {
     constexpr int H = K / 2;
-    double b[H];
 #pragma unroll
     for (int jj = 0; jj < H; ++jj) b[jj] = al[0] * To[0][jj];
 #pragma unroll
@@ -148,11 +159,98 @@ __device__ __forceinline__ void pair_step(double (&al)[K], const double (&To)[K 
     for (int ii = 0; ii < H; ++ii)
 #pragma unroll
         for (int jj = 0; jj < H; ++jj) b[jj] = fma(al[H + ii], Tx[ii][jj], b[jj]);
+}
+
+template <int K>
+__device__ __forceinline__ void pair_exchange(double (&al)[K], const double (&b)[K / 2]) {
+    constexpr int H = K / 2;
 #pragma unroll
     for (int jj = 0; jj < H; ++jj) {
-        const double v = b[jj] * erow[jj];
-        al[jj] = v;
-        al[H + jj] = shfl_xor_f64(v, 1);
+        al[jj] = b[jj];
+        al[H + jj] = shfl_xor_f64(b[jj], 1);
+    }
+}
+
+// FOLD: To/Tx already carry E[:,s0]; erow rows hold E[:,o]/E[:,s0] (row s0 is never read)
+template <int K, bool FOLD>
+__device__ __forceinline__ void pair_step(double (&al)[K], const double (&To)[K / 2][K / 2],
+                                          const double (&Tx)[K / 2][K / 2], const double* esm, int o, int s0) {
+    constexpr int H = K / 2, Hp = PairCfg<K>::Hp;
+    double b[H];
+    pair_matvec<K>(al, To, Tx, b);
+    if (FOLD) {
+        if (__any_sync(0xffffffffu, o != s0)) {
+            if (o != s0) {
+                const double* erow = esm + o * Hp;
+#pragma unroll
+                for (int jj = 0; jj < H; ++jj) b[jj] *= erow[jj];
+            }
+        }
+    } else {
+        const double* erow = esm + o * Hp;
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) b[jj] *= erow[jj];
+    }
+    pair_exchange<K>(al, b);
+}
+
+struct PairChain {
+    const uint32_t* wp;
+    int nw, len, maxnw;
+    int scale;
+    bool dead, isnan;
+    double result;
+};
+
+template <int K, bool FOLD>
+__device__ __forceinline__ void pair_main_loop(double (&al)[K], const double (&To)[K / 2][K / 2],
+                                               const double (&Tx)[K / 2][K / 2], const double* esm, int s0,
+                                               PairChain& c, uint32_t word) {
+    for (int w = 0; w < c.maxnw; ++w) {
+        const uint32_t next = c.wp[(long long)min(w + 1, c.nw - 1) * 32];
+        const int lo = (w == 0) ? 1 : 0;
+        const int hi = max(0, min(16, c.len - 16 * w));
+        const bool full = (lo == 0) && (hi == 16);
+        if (__all_sync(0xffffffffu, full)) {
+            uint32_t ww = word;
+#pragma unroll 4
+            for (int t = 0; t < 16; ++t) {
+                const int o = ww & 3u;
+                ww >>= 2;
+                pair_step<K, FOLD>(al, To, Tx, esm, o, s0);
+            }
+        } else {
+            uint32_t ww = word >> (2 * lo);
+#pragma unroll 1
+            for (int t = lo; t < 16; ++t) {
+                const int o = ww & 3u;
+                ww >>= 2;
+                double old[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) old[k] = al[k];
+                pair_step<K, FOLD>(al, To, Tx, esm, o, s0);
+                const bool act = t < hi;
+#pragma unroll
+                for (int k = 0; k < K; ++k) al[k] = act ? al[k] : old[k];
+            }
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) sum += al[k];
+        if (sum > 0.0) {
+            const int e = exponent_of(sum);
+            const double f = pow2_neg(e);
+#pragma unroll
+            for (int k = 0; k < K; ++k) al[k] *= f;
+            c.scale += e;
+            sum *= f;
+        } else if (w < c.nw) {
+            c.dead = true;                     // sum == 0: impossible observation; NaN: bad input
+            c.isnan = c.isnan || (sum != sum);
+        }
+        if (w == c.nw - 1)
+            c.result = c.dead ? (c.isnan ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY) : finish_logl(sum, c.scale);
+        word = next;
     }
 }
 
@@ -171,6 +269,22 @@ __global__ void __launch_bounds__(PairCfg<K>::THREADS) fwd_pair_kernel(FwdArgs a
     const double* Tg = a.T + (size_t)theta * K * K;
     const double* Eg = a.E + (size_t)theta * K * a.S;
     const double* pig = a.pi + (size_t)theta * K;
+    const int s0 = a.fold_sym;
+
+    // can the emission of symbol s0 be folded into T for this parameter point?  (needs E[j][s0] > 0 and finite ratios)
+    bool fold_ok = s0 >= 0 && s0 < a.S;
+    if (fold_ok) {
+#pragma unroll
+        for (int jj = 0; jj < H; ++jj) {
+            const double e0 = Eg[(h * H + jj) * a.S + s0];
+            fold_ok = fold_ok && (e0 > 0.0);
+            for (int sym = 0; sym < a.S; ++sym) {
+                const double r = Eg[(h * H + jj) * a.S + sym] / e0;
+                fold_ok = fold_ok && (r == r) && (r < 1e300);
+            }
+        }
+    }
+    const bool fold = __all_sync(0xffffffffu, fold_ok);
 
     // T slice: this lane produces output states h*H .. h*H+H-1.  To: inputs from its own half, Tx: from the partner's.
     double To[H][H], Tx[H][H];
@@ -178,82 +292,44 @@ __global__ void __launch_bounds__(PairCfg<K>::THREADS) fwd_pair_kernel(FwdArgs a
     for (int ii = 0; ii < H; ++ii)
 #pragma unroll
         for (int jj = 0; jj < H; ++jj) {
-            To[ii][jj] = Tg[(h * H + ii) * K + h * H + jj];
-            Tx[ii][jj] = Tg[((1 - h) * H + ii) * K + h * H + jj];
+            const double e0 = fold ? Eg[(h * H + jj) * a.S + s0] : 1.0;
+            To[ii][jj] = Tg[(h * H + ii) * K + h * H + jj] * e0;
+            Tx[ii][jj] = Tg[((1 - h) * H + ii) * K + h * H + jj] * e0;
         }
 #pragma unroll
     for (int sym = 0; sym < 4; ++sym)
 #pragma unroll
-        for (int jj = 0; jj < Hp; ++jj)
-            esm[sym * Hp + jj] = (sym < a.S && jj < H) ? Eg[(h * H + jj) * a.S + sym] : 1.0;
+        for (int jj = 0; jj < Hp; ++jj) {
+            double v = 1.0;                                   // padding code 3 and padded columns
+            if (sym < a.S && jj < H) {
+                v = Eg[(h * H + jj) * a.S + sym];
+                if (fold) v /= Eg[(h * H + jj) * a.S + s0];
+            }
+            esm[sym * Hp + jj] = v;
+        }
     __syncwarp();
 
-    const uint32_t* wp = a.words + si.base;
-    const int nw = si.nwords;
-    int maxnw = nw;
+    PairChain c;
+    c.wp = a.words + si.base;
+    c.nw = si.nwords;
+    c.len = si.len;
+    c.maxnw = c.nw;
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) maxnw = max(maxnw, __shfl_xor_sync(0xffffffffu, maxnw, m));
+    for (int m = 16; m >= 1; m >>= 1) c.maxnw = max(c.maxnw, __shfl_xor_sync(0xffffffffu, c.maxnw, m));
+    c.scale = 0; c.dead = false; c.isnan = false; c.result = 0.0;
 
     double al[K];  // [own half | partner half]
-    int scale = 0;
-    bool dead = false;
-    double result = 0.0;
-    uint32_t word = wp[0];
-    {   // position 0: alpha = pi o E[:, o_0]
+    const uint32_t word = c.wp[0];
+    {   // position 0: alpha = pi o E[:, o_0]  (true emission, not the ratio)
         const int o = word & 3u;
+        double b[H];
 #pragma unroll
-        for (int jj = 0; jj < H; ++jj) {
-            const double v = pig[h * H + jj] * esm[o * Hp + jj];
-            al[jj] = v;
-            al[H + jj] = shfl_xor_f64(v, 1);
-        }
+        for (int jj = 0; jj < H; ++jj) b[jj] = pig[h * H + jj] * (o < a.S ? Eg[(h * H + jj) * a.S + o] : 1.0);
+        pair_exchange<K>(al, b);
     }
-    for (int w = 0; w < maxnw; ++w) {
-        const uint32_t next = wp[(long long)min(w + 1, nw - 1) * 32];
-        const int lo = (w == 0) ? 1 : 0;
-        const int hi = max(0, min(16, si.len - 16 * w));
-        const bool full = (lo == 0) && (hi == 16);
-        if (__all_sync(0xffffffffu, full)) {
-            uint32_t ww = word;
-#pragma unroll 4
-            for (int t = 0; t < 16; ++t) {
-                const int o = ww & 3u;
-                ww >>= 2;
-                pair_step<K>(al, To, Tx, esm + o * Hp);
-            }
-        } else {
-            uint32_t ww = word >> (2 * lo);
-#pragma unroll 1
-            for (int t = lo; t < 16; ++t) {
-                const int o = ww & 3u;
-                ww >>= 2;
-                double old[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) old[k] = al[k];
-                pair_step<K>(al, To, Tx, esm + o * Hp);
-                const bool act = t < hi;
-#pragma unroll
-                for (int k = 0; k < K; ++k) al[k] = act ? al[k] : old[k];
-            }
-        }
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) sum += al[k];
-        if (sum > 0.0) {
-            const int e = exponent_of(sum);
-            const double f = pow2_neg(e);
-#pragma unroll
-            for (int k = 0; k < K; ++k) al[k] *= f;
-            scale += e;
-            sum *= f;
-        } else if (w < nw) {
-            dead = true;   // sum == 0 (impossible observation) or NaN input
-            if (sum != sum) result = sum;
-        }
-        if (w == nw - 1) result = dead ? (result != result ? result : -INFINITY) : finish_logl(sum, scale);
-        word = next;
-    }
-    if (valid && h == 0) a.chain_out[chain] = result;
+    if (fold) pair_main_loop<K, true>(al, To, Tx, esm, s0, c, word);
+    else pair_main_loop<K, false>(al, To, Tx, esm, s0, c, word);
+    if (valid && h == 0) a.chain_out[chain] = c.result;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,6 +541,40 @@ __global__ void reduce_chains_kernel(const double* chain_out, int nstreams, doub
         __syncthreads();
     }
     if (tid == 0) out[n] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probes (the roofline denominator is measured in the same run: MEASURED_PEAKS.json has no FP64 entry)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) peak_dfma_kernel(double* out, int iters, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = threadIdx.x * 1e-9 + k;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fma(acc[k], a, b);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(512) peak_dmma_kernel(double* out, int iters) {
+    double d[4][2];
+    const double a = 1e-3 * threadIdx.x, b = 1e-3 * (threadIdx.x * 3 + 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { d[k][0] = k; d[k][1] = k + 0.5; }
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dmma884(d[k][0], d[k][1], a, b);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += d[k][0] + d[k][1];
+    if (s == 12345.678) out[0] = s;
 }
 
 }  // namespace imc

@@ -48,6 +48,7 @@ struct Context {
     int sm_count = 0;
     long long opt_forward_kernel = 0;
     long long opt_dmma_mtiles = 0;
+    long long opt_fold_emission = 0;   // measured slower than the emission-row multiply on B200 (profiles/r01_pair_micro2.txt)
 };
 static Context g_ctx;
 
@@ -104,6 +105,7 @@ struct imc_seqset {
     int n_chunks = 0;
     int nsym = 0;
     long long total_sites = 0;
+    int fold_sym = 0;                     // most frequent symbol over the whole set
     // host-side packed layout
     std::vector<uint32_t> words;          // bundles of 32 streams, word-interleaved, 16 two-bit symbols per word
     std::vector<StreamInfo> streams;      // non-empty chunks only, sorted by length (descending)
@@ -255,6 +257,11 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
     if (set->nsym > 3 && !order.empty()) {
         delete set;
         return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols are not packed yet (nsym = %d)", set->nsym);
+    }
+    {
+        long long counts[256] = {0};
+        for (int c : order) for (uint8_t v : seqs[c]->sym) counts[v]++;
+        set->fold_sym = (int)(std::max_element(counts, counts + set->nsym) - counts);
     }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seqs[x]->sym.size() > seqs[y]->sym.size(); });
     const int ns = (int)order.size();
@@ -414,6 +421,7 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
     a.pi = d_pi; a.T = d_T; a.E = d_E;
     a.chain_out = (double*)set->d_chain.p;
     a.nchains = (long long)N * ns;
+    a.fold_sym = g_ctx.opt_fold_emission ? set->fold_sym : -1;
 
     int which = (int)g_ctx.opt_forward_kernel;
     if (which == KERNEL_AUTO) which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
@@ -497,6 +505,41 @@ extern "C" int imc_forward(imc_seqset* set, int K, int S, const double* pi, cons
     return imc_forward_batch(set, 1, K, S, pi, T, E, logL_out);
 }
 
+// ------------------------------------------------------------------------------------------ FP64 peak probe
+extern "C" int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int sms = g_ctx.sm_count, threads = 512, iters = 20000;
+    cudaStream_t st = g_ctx.stream;
+    double best_fma = 0.0, best_mma = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventRecord(e0, st));
+        peak_dfma_kernel<<<sms, threads, 0, st>>>(d_out, iters, 1.0000001, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep) best_fma = std::max(best_fma, 2.0 * 64.0 * iters * (double)threads * sms / (ms * 1e9));
+        CUDA_TRY(cudaEventRecord(e0, st));
+        peak_dmma_kernel<<<sms, threads, 0, st>>>(d_out, iters / 4);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep) best_mma = std::max(best_mma, 512.0 * 32.0 * (iters / 4) * (double)(threads / 32) * sms / (ms * 1e9));
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    g_launches += 8;
+    if (dfma_tflops) *dfma_tflops = best_fma;
+    if (dmma_tflops) *dmma_tflops = best_mma;
+    return IMC_OK;
+}
+
 // ------------------------------------------------------------------------------------------ options
 extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!key) return fail(IMC_ERR_INVALID, "NULL key");
@@ -510,12 +553,14 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
         g_ctx.opt_dmma_mtiles = value;
         return IMC_OK;
     }
+    if (!strcmp(key, "fold_emission")) { g_ctx.opt_fold_emission = value ? 1 : 0; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!key || !value_out) return fail(IMC_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "forward_kernel")) { *value_out = g_ctx.opt_forward_kernel; return IMC_OK; }
     if (!strcmp(key, "dmma_mtiles")) { *value_out = g_ctx.opt_dmma_mtiles; return IMC_OK; }
+    if (!strcmp(key, "fold_emission")) { *value_out = g_ctx.opt_fold_emission; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }

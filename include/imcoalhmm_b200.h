@@ -86,9 +86,14 @@ int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_
 /* ---- knobs and introspection (tests, bench) ---------------------------------------------------------- */
 /* key "forward_kernel": 0 auto, 1 generic (shared-memory state, per-step rescale), 2 lane-pair DFMA,
  *                       3 DMMA tiles.  Forcing a kernel that does not cover (K, S) returns IMC_ERR_UNSUPPORTED.
- * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto). */
+ * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
+ * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
+ *                       of T where E[:,s0] > 0; 0 (default; measured faster on B200) = always multiply by the emission row. */
 int imc_set_option(const char* key, int64_t value);
 int imc_get_option(const char* key, int64_t* value_out);
+/* Measured FP64 peaks of the bound device in TFLOP/s: plain DFMA and DMMA.8x8x4 (mma.sync f64) loops,
+ * best of 3 after warm-up (~100 ms).  bench.py uses the larger as the roofline denominator. */
+int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t imc_kernel_launches(void);
 /* name of the forward kernel chosen by the last forward call on this thread ("generic", "pair", "dmma") */

@@ -19,6 +19,7 @@ def _reset_options():
     yield
     m.set_option("forward_kernel", 0)
     m.set_option("dmma_mtiles", 0)
+    m.set_option("fold_emission", 0)
 
 
 def oracle_batch(chunks, pis, Ts, Es):
@@ -114,6 +115,35 @@ def test_dmma_mtile_variants(mt):
     m.set_option("forward_kernel", 3)
     m.set_option("dmma_mtiles", mt)
     np.testing.assert_allclose(make_set(chunks).forward_batch(pis, Ts, Es), want, rtol=RTOL)
+
+
+def test_emission_folding_on_off_and_unfoldable():
+    """The pair kernel folds E[:,s0] of the most frequent symbol into T; results must not depend on it,
+    and parameter points with a zero in that column (cannot be folded) must take the unfolded loop."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(99)
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    chunks = [rng.choice(3, size=n, p=p).astype(np.uint8)
+              for n, p in ((3000, [0.95, 0.01, 0.04]), (2000, [0.1, 0.8, 0.1]), (1000, [0.3, 0.3, 0.4]), (17, [1, 0, 0]))]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    m.set_option("forward_kernel", 2)
+    for fold in (1, 0):
+        m.set_option("fold_emission", fold)
+        np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL)
+    # most frequent symbol is 1 here -> s0 = 1
+    s1 = make_set([chunks[1]])
+    m.set_option("fold_emission", 1)
+    np.testing.assert_allclose(s1.forward_batch(pis, Ts, Es), oracle_batch([chunks[1]], pis, Ts, Es), rtol=RTOL)
+    # unfoldable: some states cannot emit symbol 0 at all
+    E2 = Es.copy()
+    E2[:, 3, 0] = 0.0
+    E2[:, 7, 0] = 0.0
+    np.testing.assert_allclose(s.forward_batch(pis, Ts, E2), oracle_batch(chunks, pis, Ts, E2), rtol=RTOL)
+    # mixed batch: only some parameter points unfoldable (lanes of one warp disagree)
+    E3 = Es.copy()
+    E3[::2, 1, 0] = 0.0
+    np.testing.assert_allclose(s.forward_batch(pis, Ts, E3), oracle_batch(chunks, pis, Ts, E3), rtol=RTOL)
 
 
 def test_edge_cases():

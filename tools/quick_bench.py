@@ -53,13 +53,23 @@ def run(K, C, L, N, kernel, mt, reps, seed=0):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c2")
+    ap.add_argument("--custom", action="append", default=[], help="K,C,L,N,kernel,mt,fold")
     args = ap.parse_args()
+    for spec in args.custom:
+        K, C, L, N, kern, mt, fold = map(int, spec.split(","))
+        m.set_option("fold_emission", fold)
+        run(K, C, L, N, kern, mt, 2)
+    m.set_option("fold_emission", 1)
     if "c2" in args.cases:
         run(10, 100, 1_000_000, 256, 2, 0, 3)
     if "k10small" in args.cases:
         run(10, 100, 100_000, 256, 2, 0, 3)
         run(10, 100, 100_000, 256, 3, 0, 2)
         run(10, 100, 20_000, 256, 1, 0, 1)
+    if "ncu_pair" in args.cases:
+        run(10, 100, 50_000, 256, 2, 0, 1)
+    if "ncu_dmma20" in args.cases:
+        run(20, 128, 50_000, 128, 3, 1, 1)
     if "k20" in args.cases:
         for mt in (1, 2, 4):
             run(20, 128, 200_000, 128, 3, mt, 2)

@@ -17,7 +17,11 @@ _lib.load()   # fail loudly at import time if the CUDA library is missing
 from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel, measure_fp64_peak  # noqa: E402
 from .hmm import Forwarder, ForwarderSet  # noqa: E402
 from .likelihood import Likelihood  # noqa: E402
+from .models import (Model, IsolationModel, IsolationMigrationModel, VariableCoalescenceRateIsolationModel,  # noqa: E402
+                     VariableCoalAndMigrationRateModel, IsolationMigrationEpochsModel)
 from . import ziphmm  # noqa: E402
 
-__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm",
+__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm", "Model", "IsolationModel",
+           "IsolationMigrationModel", "VariableCoalescenceRateIsolationModel", "VariableCoalAndMigrationRateModel",
+           "IsolationMigrationEpochsModel",
            "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak"]

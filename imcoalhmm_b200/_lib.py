@@ -46,6 +46,16 @@ _SIGNATURES = {
                                          c_f64p]),
     "imc_forward_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                              c_vp]),
+    "imc_model_create": (ctypes.c_int, [ctypes.c_int, c_i32p, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_model_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "imc_model_destroy": (ctypes.c_int, [c_vp]),
+    "imc_model_build_batch": (ctypes.c_int, [c_vp, ctypes.c_int, c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]),
+    "imc_model_build_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "imc_loglik_batch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_f64p, c_f64p, c_i32p]),
+    "imc_loglik_batch_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "imc_statespace_describe": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                               ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), c_i32p, c_i32p,
+                                               c_u8p]),
     "imc_measure_fp64_peak": (ctypes.c_int, [c_f64p, c_f64p]),
     "imc_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "imc_get_option": (ctypes.c_int, [ctypes.c_char_p, c_i64p]),

@@ -2,6 +2,7 @@
 // declared in include/imcoalhmm_b200.h.  No CPU fallback: every forward entry point needs the GPU.
 #include "../../include/imcoalhmm_b200.h"
 #include "forward_kernels.cuh"
+#include "model_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -9,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -565,3 +567,6 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
 }
 extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }
 extern "C" const char* imc_last_forward_kernel(void) { return g_last_kernel; }
+
+// ------------------------------------------------------------------------------------------ model build
+#include "model_host.inl"

@@ -83,6 +83,39 @@ int imc_forward_batch(imc_seqset* set, int N, int K, int S, const double* pi, co
 int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T,
                           const double* d_E, double* d_out, void* stream);
 
+/* ---- batched model build: theta -> (pi, T, E) on the GPU ----------------------------------------------
+ * Replaces Model.build_hidden_markov_model (model.py:44-49) and everything under it (state_spaces.py, CTMC.py,
+ * transitions.py, emissions.py, break_points.py and the model files) for N parameter points per call.
+ *   kind 0  IsolationModel(no_hmm_states)                          iparams {K}             theta[3]   isolation_model.py:94-122
+ *   kind 1  IsolationMigrationModel(no_mig, no_anc)                iparams {n_mig, n_anc}  theta[5]   isolation_with_migration_model.py:116-164
+ *   kind 2  VariableCoalescenceRateIsolationModel(intervals, split) iparams {est_split, n_epochs, intervals...}
+ *                                                                   theta[n_epochs+1(+1)]  variable_coalescence_rate_isolation_model.py:90-178
+ *   kind 3  VariableCoalAndMigrationRateModel(initial, intervals)  iparams {initial 0|1|2, n_epochs, intervals...}
+ *                                                                   theta[4 n_epochs+1]    variable_migration_model.py:86-181
+ *   kind 4  IsolationMigrationEpochsModel(epochs, no_mig, no_anc)  iparams {e, n_mig, n_anc} theta[3+(2e+1)+e]
+ *                                                                   isolation_with_migration_model_epochs.py:133-211
+ * status[n]: 0 ok, 1 invalid parameters (some theta <= 0; model.py:32-42 -> logL = -inf, likelihood.py:29-30),
+ *            2 joint matrix does not sum to 1 within 7 decimals (the reference raises AssertionError, transitions.py:239). */
+typedef struct imc_model imc_model;
+int imc_model_create(int kind, const int32_t* iparams, int n_iparams, imc_model** out);
+int imc_model_info(const imc_model* model, int* K_out, int* P_out);
+int imc_model_destroy(imc_model* model);
+/* host arrays: theta [N][P] in; pi [N][K], T [N][K][K], E [N][K][3], status [N] (may be NULL) out */
+int imc_model_build_batch(imc_model* model, int N, const double* theta, double* pi, double* T, double* E,
+                          int32_t* status);
+int imc_model_build_batch_dev(imc_model* model, int N, const double* d_theta, double* d_pi, double* d_T,
+                              double* d_E, int32_t* d_status, void* stream);
+/* fused theta -> logL (model build and forward on the device, no host round trip in between; replaces
+ * Likelihood.__call__, likelihood.py:27-33, for N points).  out[n] = -inf where status[n] == 1, NaN where 2. */
+int imc_loglik_batch(imc_model* model, imc_seqset* set, int N, const double* theta, double* out, int32_t* status);
+int imc_loglik_batch_dev(imc_model* model, imc_seqset* set, int N, const double* d_theta, double* d_out,
+                         int32_t* d_status /* may be NULL */, void* stream);
+/* The two-locus ancestry state spaces (state_spaces.py:7-116): space 0 Isolation, 1 Single, 2 Migration.
+ * States are numbered in a canonical order; lineages[i][k] = (population << 4) | (left mask << 2) | right mask,
+ * 0xff = unused slot.  Any output may be NULL. */
+int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts, int* special, int32_t* edges,
+                            int32_t* classes, uint8_t* lineages);
+
 /* ---- knobs and introspection (tests, bench) ---------------------------------------------------------- */
 /* key "forward_kernel": 0 auto, 1 generic (shared-memory state, per-step rescale), 2 lane-pair DFMA,
  *                       3 DMMA tiles.  Forcing a kernel that does not cover (K, S) returns IMC_ERR_UNSUPPORTED.

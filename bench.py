@@ -9,10 +9,10 @@ chunk of the (per-rank) shard, logL[N_theta] out.  Rank 0 prints ONE JSON line.
 
   value      device-timed (CUDA events on the launching stream, max over ranks) with the packed sequences and
              the parameter batch resident in HBM; an L2 flush (256 MiB write) separates timed steps.
-  e2e        the same metric through the public host API (ForwarderSet.forward_batch -> imc_forward_batch):
-             (pi,T,E) copied from pinned host memory, logL copied back, every step, wall clock around the calls.
-             The sequences stay resident (uploaded once when the Forwarders are built, exactly like the
-             reference preprocesses once in Forwarder.__init__, hmm.py:12-16).
+  e2e        the same metric through the public host API (Model.batched_log_likelihood -> imc_loglik_batch):
+             theta[N,P] copied from pinned host memory, logL[N] + status[N] copied back, every step, wall clock
+             around the calls.  The sequences stay resident (uploaded once when the Forwarders are built, exactly
+             like the reference preprocesses once in Forwarder.__init__, hmm.py:12-16).
   roofline   dominant kernel against the FP64 peak MEASURED IN THIS RUN (imc_measure_fp64_peak: DFMA and DMMA
              loops; MEASURED_PEAKS.json has no FP64 entry).  achieved = sites*points*(2K^2+3K) / kernel time.
   cpu_baseline  the CPU oracle's zipHMM-style forward (oracle/forward_oracle.c, OpenMP over all host cores) on a
@@ -35,14 +35,26 @@ SEED0 = 20261018
 
 WORKLOADS = {
     # BASELINE.json configs[1]: isolation model, 10 intervals, synthetic 100 Mbp, 256 parameter points, 1 B200
-    "c2": dict(model="isolation_k10", K=10, chunks=100, chunk_len=1_000_000, points=256,
+    "c2": dict(model="isolation_k10", ctor=("IsolationModel", (10,)), default=[1e-3, 2000.0, 0.4], K=10,
+               chunks=100, chunk_len=1_000_000, points=256,
                desc="configs[1]: isolation model K=10, synthetic 100 Mbp (100 x 1 Mbp chunks), 256 parameter points"),
-    "c2_small": dict(model="isolation_k10", K=10, chunks=100, chunk_len=50_000, points=256,
+    "c2_small": dict(model="isolation_k10", ctor=("IsolationModel", (10,)), default=[1e-3, 2000.0, 0.4], K=10,
+                     chunks=100, chunk_len=50_000, points=256,
                      desc="reduced configs[1] for smoke runs: 100 x 50 kbp, 256 points"),
     # per-GPU slice of configs[2] (IM model, K=20, 1 Gbp, 1024 points on 8 GPUs = 125 chunks/GPU)
-    "c3_1gpu": dict(model="im_k10_10", K=20, chunks=125, chunk_len=1_000_000, points=1024,
+    "c3_1gpu": dict(model="im_k10_10", ctor=("IsolationMigrationModel", (10, 10)),
+                    default=[1e-3, 1e-3, 2000.0, 0.4, 200.0], K=20, chunks=125, chunk_len=1_000_000, points=1024,
                     desc="configs[2] per-GPU shard: IM model K=10+10, 125 x 1 Mbp chunks, 1024 parameter points"),
 }
+
+
+def thetas_around(default, n, seed=7, scale=0.1):
+    """theta_b = default * exp(0.1 N(0,1)), PCG64(seed=7): the MCMC proposal scale (mcmc.py:26,34-36)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    default = np.asarray(default, dtype=np.float64)
+    out = default[None, :] * np.exp(scale * rng.standard_normal((n, default.size)))
+    out[0] = default
+    return np.ascontiguousarray(out)
 
 
 def flops_per_site_point(K):
@@ -85,9 +97,9 @@ def simulate_chunk(rng, pi, T, E, L, missing=0.04, mean_run=100):
 
 
 def load_points(model, n_points):
-    """(pi, T, E) for the parameter batch.  INTERIM (round 1): the committed reference-derived fixture
-    tests/golden/model_<name>.npz holds 16 points theta_b = default * exp(0.1 N(0,1)); they are tiled to
-    n_points.  Model build is therefore outside the timed region in this revision."""
+    """(pi, T, E) for the CPU reference arm only: the committed reference-derived fixture
+    tests/golden/model_<name>.npz (16 points theta_b = default * exp(0.1 N(0,1)), built by the reference's own
+    build_hidden_markov_model) tiled to n_points, so that arm touches none of this repository's kernels."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "model_%s.npz" % model))
     reps = (n_points + g["pi"].shape[0] - 1) // g["pi"].shape[0]
     pis = np.ascontiguousarray(np.tile(g["pi"], (reps, 1))[:n_points])
@@ -201,12 +213,14 @@ def main():
     config = {"workload": wl["desc"], "chunks_per_gpu": wl["chunks"], "chunk_len": wl["chunk_len"],
               "points": wl["points"], "K": K, "sharding": "chunks across ranks, no data-path collective except one "
               "all-reduce of float64[points]", "l2": "flushed between timed steps (256 MiB write)",
-              "model_build": "outside the timed region in this revision (fixture-derived pi,T,E)"}
+              "model_build": "inside the timed region, on the GPU (theta -> pi,T,E -> logL fused on the device)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         res = cpu_reference_run(wl, pis, Ts, Es, args.steps, max(args.warmup, 1))
+        config = dict(config, model_build="not part of this arm: (pi,T,E) come from the committed fixture built by the "
+                      "reference's own Python build_hidden_markov_model (2.4 ms/theta for this model on one core, SURVEY 3.1)")
         line = {"metric": "forward sites*param-points/sec", "value": res["value"], "unit": "sites*points/s",
                 "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -227,20 +241,26 @@ def main():
     m._lib.check(m._lib.load().imc_init(local_rank))
     dev = torch.device("cuda", local_rank)
 
+    model = getattr(m, wl["ctor"][0])(*wl["ctor"][1])
+    thetas = thetas_around(wl["default"], wl["points"])
+    # the synthetic alignment is simulated from the model at the scripts' default parameters (thetas[0])
+    pis, Ts, Es, st = model.build_hidden_markov_models(thetas)
+    assert (st == 0).all()
     # weak scaling: every rank owns wl["chunks"] chunks (distinct seeds), all ranks score the same points
     chunk_ids = range(rank * wl["chunks"], (rank + 1) * wl["chunks"])
     chunks = make_chunks(wl, pis, Ts, Es, chunk_ids)
     fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
     sites_rank = fset.total_sites
     N, S = wl["points"], 3
+    d_theta = torch.tensor(thetas, device=dev)
     d_pi, d_T, d_E = (torch.tensor(x, device=dev) for x in (pis, Ts, Es))
     d_out = torch.empty(N, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
     def step():
-        fset.forward_batch_device(d_pi.data_ptr(), d_T.data_ptr(), d_E.data_ptr(), d_out.data_ptr(), N, K, S,
-                                  stream.cuda_stream)
+        # theta -> (pi,T,E) -> logL on the device: 3 model-build kernels, forward, chunk reduction, status fix-up
+        model.batched_log_likelihood_device(d_theta.data_ptr(), fset, d_out.data_ptr(), N, 0, stream.cuda_stream)
         if dist is not None:
             dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods
 
@@ -286,18 +306,19 @@ def main():
         kt.append(a.elapsed_time(b) * 1e-3)
     t_kernel = float(np.mean(kt))
 
-    # ---- end to end through the host API: pinned host (pi,T,E) in, host logL out, every step ----
-    h_pi, h_T, h_E = (torch.tensor(x).pin_memory() for x in (pis, Ts, Es))
-    h_out = torch.empty(N, dtype=torch.float64).pin_memory()
-    np_pi, np_T, np_E, np_out = h_pi.numpy(), h_T.numpy(), h_E.numpy(), h_out.numpy()
+    # ---- end to end through the host API (Model.batched_log_likelihood -> imc_loglik_batch): pinned host theta in,
+    # host logL + status out, every step; model build and forward on the device in between ----
+    h_theta = torch.tensor(thetas).pin_memory()
+    np_theta = h_theta.numpy()
+    np_out = np.empty(N)
     for _ in range(2):
-        fset.forward_batch(np_pi, np_T, np_E, out=np_out)
+        np_out = model.batched_log_likelihood(np_theta, fset)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fset.forward_batch(np_pi, np_T, np_E, out=np_out)      # synchronous: returns with logL on the host
+        np_out = model.batched_log_likelihood(np_theta, fset)   # synchronous: returns with logL on the host
         if dist is not None:
             tmp = torch.from_numpy(np_out).to(dev)
             dist.all_reduce(tmp)
@@ -307,8 +328,8 @@ def main():
         tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
-    h2d = (pis.nbytes + Ts.nbytes + Es.nbytes)
-    d2h = N * 8
+    h2d = thetas.nbytes
+    d2h = N * 8 + N * 4
     if world == 1:
         assert np.allclose(np_out, logl_dev, rtol=1e-12), "host API and device API disagree"
 

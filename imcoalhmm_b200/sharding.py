@@ -1,0 +1,64 @@
+"""Sharding of alignment chunks across the GPUs of one box.
+
+Chunks (= reference Forwarders, one per alignment file) are independent HMM runs whose log-likelihoods are
+added (likelihood.py:33), so the path shards by chunk with no data-path exchange: every rank owns a contiguous
+block of chunks balanced by total sites, scores the same parameter batch on it, and the partial logL[N] vectors
+are summed by ONE all-reduce (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def partition_chunks(lengths, world_size):
+    """Contiguous blocks [(start, end), ...] of chunk indices, one per rank, balanced by total sites.
+
+    Greedy prefix split at the ideal cumulative boundaries; every rank gets a (possibly empty) block and the
+    blocks tile range(len(lengths)) in order, so chunk order -- and therefore the summation order inside a rank --
+    is preserved."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = lengths.size
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    cum = np.concatenate([[0], np.cumsum(lengths)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        k = int(np.searchsorted(cum, target, side="left"))
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, n)] - target):
+            k -= 1
+        bounds.append(min(max(k, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+class ShardedLikelihood(object):
+    """Likelihood over chunks sharded across ranks.
+
+    local_scorer(thetas) -> tensor float64[N] of this rank's partial log-likelihoods, on the device the process
+    group communicates on (cuda for nccl, cpu for gloo).  `batched` all-reduces it (sum) and returns the tensor.
+    """
+
+    def __init__(self, local_scorer, process_group=None):
+        self.local_scorer = local_scorer
+        self.process_group = process_group
+
+    def batched(self, thetas):
+        import torch.distributed as dist
+        part = self.local_scorer(thetas)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.process_group)   # the only collective
+        return part
+
+
+def make_gpu_scorer(model, forwarder_set, device):
+    """local_scorer for ShardedLikelihood: fused theta -> logL on `device`, result left on the device."""
+    import torch
+
+    def scorer(thetas):
+        th = torch.as_tensor(np.ascontiguousarray(thetas, dtype=np.float64)).to(device, non_blocking=True)
+        out = torch.empty(th.shape[0], dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        model.batched_log_likelihood_device(th.data_ptr(), forwarder_set, out.data_ptr(), th.shape[0], 0, stream)
+        return out
+
+    return scorer

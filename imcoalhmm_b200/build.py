@@ -7,6 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "imc_lib.cu")
 OUT = os.path.join(HERE, "libimcoalhmm_b200.so")
 DEPS = [SRC, os.path.join(HERE, "csrc", "forward_kernels.cuh"),
+        os.path.join(HERE, "csrc", "zip_kernels.cuh"),
+        os.path.join(HERE, "csrc", "tokenizer.inl"),
+        os.path.join(HERE, "csrc", "model_host.inl"),
         os.path.join(HERE, "csrc", "model_kernels.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "imcoalhmm_b200.h")]
 

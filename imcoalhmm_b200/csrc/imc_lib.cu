@@ -2,6 +2,7 @@
 // declared in include/imcoalhmm_b200.h.  No CPU fallback: every forward entry point needs the GPU.
 #include "../../include/imcoalhmm_b200.h"
 #include "forward_kernels.cuh"
+#include "zip_kernels.cuh"
 #include "model_kernels.cuh"
 
 #include <algorithm>
@@ -14,9 +15,12 @@
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <sched.h>
 #include <string>
 #include <unistd.h>
 #include <vector>
+
+#include "tokenizer.inl"
 
 using namespace imc;
 
@@ -51,6 +55,9 @@ struct Context {
     long long opt_forward_kernel = 0;
     long long opt_dmma_mtiles = 0;
     long long opt_fold_emission = 0;   // measured slower than the emission-row multiply on B200 (profiles/r01_pair_micro2.txt)
+    long long opt_zip_split = 0;       // CTAs per parameter point for the zip kernel (0 = auto)
+    long long opt_zip_ctas_per_sm = 0; // 1 or 2 resident CTAs per SM for the zip kernel (0 = auto)
+    long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
 };
 static Context g_ctx;
 
@@ -103,17 +110,31 @@ struct DeviceBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// device copy of the token streams derived for one dictionary size M (see zip_device)
+struct ZipDevice {
+    int M = 0, nlevels = 0;
+    long long total_tokens = 0;
+    DeviceBuf tokens, chunks, pairs, levels;
+};
+
 struct imc_seqset {
     int n_chunks = 0;
     int nsym = 0;
     long long total_sites = 0;
     int fold_sym = 0;                     // most frequent symbol over the whole set
-    // host-side packed layout
+    // host-side packed layout (plain kernels)
+    bool packable = false;                // nsym <= 3
     std::vector<uint32_t> words;          // bundles of 32 streams, word-interleaved, 16 two-bit symbols per word
     std::vector<StreamInfo> streams;      // non-empty chunks only, sorted by length (descending)
+    // host-side compressed layout (zip kernel): one dictionary for the whole set, tokens per non-empty chunk
+    ZipMerges merges;
+    std::vector<std::vector<uint8_t>> tok_full;   // per stream, over all merges.size() ids, symbols 1..L-1
+    std::vector<uint8_t> first_sym;               // per stream
+    std::vector<int> stream_of_chunk;             // chunk index as given to imc_seqset_create -> stream (-1: empty chunk)
     // device side (lazy)
     bool uploaded = false;
     DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out;
+    std::vector<ZipDevice*> zip_dev;      // one per dictionary size in use
 };
 
 static int seq_finish(imc_seq* s, imc_seq** out) {
@@ -256,10 +277,7 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
         set->total_sites += (long long)seqs[c]->sym.size();
         if (!seqs[c]->sym.empty()) order.push_back(c);   // an empty chunk contributes logL = 0
     }
-    if (set->nsym > 3 && !order.empty()) {
-        delete set;
-        return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols are not packed yet (nsym = %d)", set->nsym);
-    }
+    set->packable = set->nsym <= 3;
     {
         long long counts[256] = {0};
         for (int c : order) for (uint8_t v : seqs[c]->sym) counts[v]++;
@@ -270,7 +288,29 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
     set->streams.resize(ns);
     long long word_off = 0;   // in words
     try {
-        for (int b0 = 0; b0 < ns; b0 += 32) {
+        // ---- zipHMM-style preprocessing (hmm.py:16): learn the merges on a bounded prefix sample, encode every chunk
+        {
+            std::vector<std::vector<uint8_t>> sample;
+            long long budget = 16LL << 20;
+            for (int c = 0; c < C && budget > 0; ++c) {
+                const auto& sy = seqs[c]->sym;
+                if (sy.size() < 2) continue;
+                const size_t take = (size_t)std::min<long long>((long long)sy.size() - 1, budget);
+                sample.emplace_back(sy.begin() + 1, sy.begin() + 1 + take);
+                budget -= (long long)take;
+            }
+            set->merges = zip_learn(sample, set->nsym, 256, 16);
+        }
+        set->tok_full.resize(ns);
+        set->first_sym.resize(ns);
+        set->stream_of_chunk.assign(C, -1);
+        for (int k = 0; k < ns; ++k) set->stream_of_chunk[order[k]] = k;
+        parallel_for(ns, [&](int k) {
+            const auto& sy = seqs[order[k]]->sym;
+            set->first_sym[k] = sy[0];
+            zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
+        });
+        for (int b0 = 0; set->packable && b0 < ns; b0 += 32) {
             const int nb = std::min(32, ns - b0);
             const long long maxlen = (long long)seqs[order[b0]]->sym.size();
             const long long nwords = (maxlen + 15) / 16;
@@ -301,9 +341,14 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
 
 extern "C" int imc_seqset_destroy(imc_seqset* set) {
     if (!set) return IMC_OK;
-    if (set->uploaded && g_ctx.pid == getpid()) {
+    const bool mine = g_ctx.pid == getpid();
+    if (mine) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
         set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
+    }
+    for (ZipDevice* z : set->zip_dev) {
+        if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
+        delete z;
     }
     delete set;
     return IMC_OK;
@@ -331,8 +376,180 @@ static int seqset_upload(imc_seqset* set) {
     return IMC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ zip (compressed) path
+enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3, KERNEL_ZIP = 4 };
+
+#define ZIP_K_LIST(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(32) X(40)
+static bool zip_supported(int K) {
+    switch (K) {
+#define X(k) case k:
+        ZIP_K_LIST(X)
+#undef X
+        return true;
+    }
+    return false;
+}
+
+struct ZipPlan { int threads, ctas_per_sm, M; size_t smem; };
+static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
+
+template <int K>
+static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas) {
+    using C = ZipCfg<K>;
+    ZipPlan p;
+    p.threads = 256;
+    const int m2 = C::max_entries((ZIP_SMEM_SM - 1024) / 2, S, p.threads);
+    const int m1 = C::max_entries(ZIP_SMEM_SM, S, p.threads);
+    // two resident CTAs per SM overlap one CTA's dictionary build / tail with the other's chains; take that
+    // whenever half the shared memory still holds the whole dictionary or at least 48 entries
+    int ctas = want_ctas;
+    if (ctas == 0) ctas = (m2 >= avail_ids || m2 >= 48) ? 2 : 1;
+    p.ctas_per_sm = ctas;
+    p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
+    if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
+    p.M = std::max(p.M, S);
+    p.smem = C::smem_bytes(p.M, S, p.threads);
+    return p;
+}
+
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out) {
+    const int want = (int)g_ctx.opt_zip_ctas_per_sm;
+    switch (K) {
+#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want); break;
+        ZIP_K_LIST(X)
+#undef X
+        default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
+    }
+    if (out->smem > ZIP_SMEM_SM) return fail(IMC_ERR_UNSUPPORTED, "zip kernel: %d symbols x K = %d do not fit in shared memory", S, K);
+    return IMC_OK;
+}
+
+// token streams over the first M dictionary ids, level-ordered, on the device (cached per M)
+static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
+    for (ZipDevice* z : set->zip_dev) if (z->M == M) { *out = z; return IMC_OK; }
+    const int ns = (int)set->streams.size();
+    ZipLevels zl = zip_levels(set->merges, M);
+    std::vector<std::vector<uint8_t>> tok(ns);
+    parallel_for(ns, [&](int k) {
+        zip_expand(set->merges, set->tok_full[k], M, tok[k]);
+        for (auto& t : tok[k]) t = zl.perm[t];
+    });
+    std::vector<int> order(ns);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tok[x].size() > tok[y].size(); });
+    std::vector<ZipChunk> chunks(ns);
+    long long off = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int k = order[i];
+        if (tok[k].size() > 0x7fffffffULL) return fail(IMC_ERR_UNSUPPORTED, "a chunk has more than 2^31-1 tokens");
+        chunks[i].tok_off = off;
+        chunks[i].ntok = (int)tok[k].size();
+        chunks[i].first_sym = set->first_sym[k];
+        chunks[i].out_index = k;
+        chunks[i].pad = 0;
+        off += (long long)((tok[k].size() + 15) / 16) * 16 + 16;
+    }
+    std::vector<uint8_t> flat((size_t)off, 0);
+    long long total = 0;
+    for (int i = 0; i < ns; ++i) {
+        const auto& t = tok[order[i]];
+        if (!t.empty()) memcpy(flat.data() + chunks[i].tok_off, t.data(), t.size());
+        total += (long long)t.size();
+    }
+    ZipDevice* z = new (std::nothrow) ZipDevice;
+    if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
+    z->M = M;
+    z->nlevels = (int)zl.level_start.size() - 1;
+    z->total_tokens = total;
+    int rc;
+    if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
+        (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
+        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
+        delete z;
+        return rc;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!flat.empty()) e = cudaMemcpy(z->tokens.p, flat.data(), flat.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ns) e = cudaMemcpy(z->chunks.p, chunks.data(), sizeof(ZipChunk) * ns, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !zl.pairs.empty()) e = cudaMemcpy(z->pairs.p, zl.pairs.data(), zl.pairs.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(z->levels.p, zl.level_start.data(), sizeof(int) * zl.level_start.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
+        delete z;
+        return fail(IMC_ERR_CUDA, "uploading token streams failed: %s", cudaGetErrorString(e));
+    }
+    set->zip_dev.push_back(z);
+    *out = z;
+    return IMC_OK;
+}
+
+template <int K, int MINB>
+static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
+    static size_t attr_max = 0;
+    if (p.smem > attr_max) {
+        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<K, 256, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        attr_max = p.smem;
+    }
+    zip_forward_kernel<K, 256, MINB><<<(unsigned)((long long)a.N * a.J), 256, p.smem, st>>>(a);
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_zip_info(imc_seqset* set, int K, int* ids_available, int* ids_used, int64_t* tokens, int* levels) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (ids_available) *ids_available = set->merges.size();
+    if (!ids_used && !tokens && !levels) return IMC_OK;
+    ZipPlan plan;
+    int rc = zip_plan(K, set->nsym, set->merges.size(), &plan);
+    if (rc) return rc;
+    if (ids_used) *ids_used = plan.M;
+    if (levels) *levels = (int)zip_levels(set->merges, plan.M).level_start.size() - 1;
+    if (tokens) {
+        std::vector<long long> len(set->merges.size(), 1);
+        for (int id = std::max(plan.M, set->nsym); id < set->merges.size(); ++id) {
+            const auto& pr = set->merges.pairs[id - set->nsym];
+            len[id] = len[pr[0]] + len[pr[1]];
+        }
+        long long total = 0;
+        for (const auto& t : set->tok_full) for (uint8_t x : t) total += len[x];
+        *tokens = total;
+    }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_zip_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs) {
+    if (!set || !pairs_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (capacity_pairs < (int)set->merges.pairs.size()) return fail(IMC_ERR_INVALID, "capacity %d < %zu pairs", capacity_pairs, set->merges.pairs.size());
+    for (size_t i = 0; i < set->merges.pairs.size(); ++i) { pairs_out[2 * i] = set->merges.pairs[i][0]; pairs_out[2 * i + 1] = set->merges.pairs[i][1]; }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_t* out, int64_t capacity, int64_t* ntokens) {
+    if (!set || !ntokens) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (chunk < 0 || chunk >= set->n_chunks) return fail(IMC_ERR_INVALID, "chunk %d out of range", chunk);
+    if (ids < set->nsym || ids > set->merges.size()) return fail(IMC_ERR_INVALID, "ids must be in [%d, %d]", set->nsym, set->merges.size());
+    const int k = set->stream_of_chunk[chunk];
+    if (k < 0) { *ntokens = 0; return IMC_OK; }
+    std::vector<uint8_t> tok;
+    zip_expand(set->merges, set->tok_full[k], ids, tok);
+    *ntokens = (int64_t)tok.size();
+    if (out) {
+        if (capacity < (int64_t)tok.size()) return fail(IMC_ERR_INVALID, "capacity %lld < %zu tokens", (long long)capacity, tok.size());
+        if (!tok.empty()) memcpy(out, tok.data(), tok.size());
+    }
+    return IMC_OK;
+}
+
+static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
+    switch (a.K) {
+#define X(k) case k: return p.ctas_per_sm == 2 ? launch_zip_k<k, 2>(a, p, st) : launch_zip_k<k, 1>(a, p, st);
+        ZIP_K_LIST(X)
+#undef X
+    }
+    return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", a.K);
+}
+
 // ------------------------------------------------------------------------------------------ launchers
-enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3 };
 
 static bool pair_supported(int K) { return K == 2 || K == 4 || K == 6 || K == 8 || K == 10 || K == 12; }
 static bool dmma_supported(int K) {
@@ -407,7 +624,7 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
     if (!set->streams.empty() && S != set->nsym)
         return fail(IMC_ERR_INVALID, "emission matrix has %d symbols but the sequences were created with nsym = %d", S, set->nsym);
     if (K > 128) return fail(IMC_ERR_UNSUPPORTED, "K = %d > 128 is not supported", K);
-    int rc = seqset_upload(set);
+    int rc = ensure_device();
     if (rc) return rc;
     const int ns = (int)set->streams.size();
     if (ns == 0) {   // only empty chunks: logL = 0 for every point
@@ -415,6 +632,42 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         return IMC_OK;
     }
     if ((rc = set->d_chain.reserve(sizeof(double) * (size_t)N * ns))) return rc;
+
+    int which = (int)g_ctx.opt_forward_kernel;
+    if (which == KERNEL_AUTO) {
+        if (zip_supported(K)) which = KERNEL_ZIP;
+        else which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
+    }
+    if (which == KERNEL_ZIP) {
+        ZipPlan plan;
+        if ((rc = zip_plan(K, S, set->merges.size(), &plan))) return rc;
+        ZipDevice* z = nullptr;
+        if ((rc = zip_device(set, plan.M, &z))) return rc;
+        ZipArgs za;
+        za.tokens = (const uint8_t*)z->tokens.p;
+        za.chunks = (const ZipChunk*)z->chunks.p;
+        za.nchunks = ns;
+        const int slots = plan.threads / 8;
+        za.J = g_ctx.opt_zip_split > 0 ? (int)std::min<long long>(g_ctx.opt_zip_split, ns) : (ns + slots - 1) / slots;
+        za.pairs = (const uint8_t*)z->pairs.p;
+        za.level_start = (const int*)z->levels.p;
+        za.nlevels = z->nlevels;
+        za.M = plan.M;
+        za.N = N; za.K = K; za.S = S;
+        za.pi = d_pi; za.T = d_T; za.E = d_E;
+        za.chain_out = (double*)set->d_chain.p;
+        za.out_stride = ns;
+        g_last_kernel = "zip";
+        if ((rc = launch_zip(za, plan, st))) return rc;
+        CUDA_TRY(cudaGetLastError());
+        reduce_chains_kernel<<<N, 256, 0, st>>>(za.chain_out, ns, d_out);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+        return IMC_OK;
+    }
+    if (!set->packable)
+        return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols run on the zip kernel only (nsym = %d, K = %d)", set->nsym, K);
+    if ((rc = seqset_upload(set))) return rc;
     FwdArgs a;
     a.words = (const uint32_t*)set->d_words.p;
     a.streams = (const StreamInfo*)set->d_streams.p;
@@ -425,8 +678,6 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
     a.nchains = (long long)N * ns;
     a.fold_sym = g_ctx.opt_fold_emission ? set->fold_sym : -1;
 
-    int which = (int)g_ctx.opt_forward_kernel;
-    if (which == KERNEL_AUTO) which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
     if (which == KERNEL_PAIR) {
         if (!pair_supported(K)) return fail(IMC_ERR_UNSUPPORTED, "lane-pair kernel covers even K <= 12, not K = %d", K);
         g_last_kernel = "pair";
@@ -546,7 +797,7 @@ extern "C" int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
 extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!key) return fail(IMC_ERR_INVALID, "NULL key");
     if (!strcmp(key, "forward_kernel")) {
-        if (value < 0 || value > 3) return fail(IMC_ERR_INVALID, "forward_kernel must be 0..3");
+        if (value < 0 || value > 4) return fail(IMC_ERR_INVALID, "forward_kernel must be 0..4");
         g_ctx.opt_forward_kernel = value;
         return IMC_OK;
     }
@@ -556,6 +807,9 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
         return IMC_OK;
     }
     if (!strcmp(key, "fold_emission")) { g_ctx.opt_fold_emission = value ? 1 : 0; return IMC_OK; }
+    if (!strcmp(key, "zip_split")) { if (value < 0) return fail(IMC_ERR_INVALID, "zip_split must be >= 0"); g_ctx.opt_zip_split = value; return IMC_OK; }
+    if (!strcmp(key, "zip_ctas_per_sm")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_ctas_per_sm must be 0, 1 or 2"); g_ctx.opt_zip_ctas_per_sm = value; return IMC_OK; }
+    if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int imc_get_option(const char* key, int64_t* value_out) {
@@ -563,6 +817,9 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "forward_kernel")) { *value_out = g_ctx.opt_forward_kernel; return IMC_OK; }
     if (!strcmp(key, "dmma_mtiles")) { *value_out = g_ctx.opt_dmma_mtiles; return IMC_OK; }
     if (!strcmp(key, "fold_emission")) { *value_out = g_ctx.opt_fold_emission; return IMC_OK; }
+    if (!strcmp(key, "zip_split")) { *value_out = g_ctx.opt_zip_split; return IMC_OK; }
+    if (!strcmp(key, "zip_ctas_per_sm")) { *value_out = g_ctx.opt_zip_ctas_per_sm; return IMC_OK; }
+    if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }

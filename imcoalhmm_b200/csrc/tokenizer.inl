@@ -1,0 +1,142 @@
+// Host-side zipHMM-style preprocessing for the compressed forward kernel (zip_kernels.cuh).
+//
+// Reference contract: /root/reference/src/IMCoalHMM/hmm.py:16  ziphmm.preprocess_raw_observations(obs, NSYM)
+// -> (new_obs, sym2pair, new_nsyms): the observation sequence re-encoded over an extended alphabet in which
+// every id >= NSYM stands for an adjacent pair (left, right) of earlier ids.  Any such re-encoding is exact
+// (the pair's matrix is the product of its parts), so the particular merges need not match mini-ziphmm's.
+//
+// Differences that come from the GPU, not from the algorithm:
+//   * ONE dictionary is shared by all chunks of a sequence set (the kernel keeps one copy of every
+//     dictionary matrix per parameter point in shared memory), learned on a bounded prefix sample;
+//   * at most 256 ids (one byte per token); a forward call with K states uses the first M(K) ids that fit
+//     in shared memory, tokens with larger ids being expanded back into their parts (zip_derive);
+//   * position 0 of every chunk is kept out of the token stream (alpha_0 = pi o E[:,o_0] has no T factor).
+#include <array>
+#include <thread>
+
+namespace imc {
+
+struct ZipMerges {
+    int nsym = 0;
+    std::vector<std::array<uint8_t, 2>> pairs;   // pairs[i] = (left, right) of id nsym + i, creation order
+    int size() const { return nsym + (int)pairs.size(); }
+};
+
+// one left-to-right pass: replace every (a, b) by id, in place; returns the new length
+static inline size_t zip_replace(uint8_t* s, size_t n, uint8_t a, uint8_t b, uint8_t id) {
+    size_t w = 0, t = 0;
+    // skip the untouched prefix quickly
+    while (t + 1 < n && !(s[t] == a && s[t + 1] == b)) ++t;
+    w = t;
+    while (t < n) {
+        if (t + 1 < n && s[t] == a && s[t + 1] == b) { s[w++] = id; t += 2; }
+        else { s[w++] = s[t++]; }
+    }
+    return w;
+}
+
+// Greedy most-frequent-adjacent-pair merges learned on `sample` (each entry one chunk without its first symbol;
+// the buffers are consumed).  Stops at max_ids or when the best pair occurs fewer than min_count times.
+static ZipMerges zip_learn(std::vector<std::vector<uint8_t>>& sample, int nsym, int max_ids, long long min_count) {
+    ZipMerges mg;
+    mg.nsym = nsym;
+    if (max_ids > 256) max_ids = 256;
+    std::vector<long long> counts;
+    int ns = nsym;
+    while (ns < max_ids) {
+        counts.assign((size_t)ns * ns, 0);
+        for (const auto& s : sample)
+            for (size_t t = 0; t + 1 < s.size(); ++t) counts[(size_t)s[t] * ns + s[t + 1]]++;
+        long long best = 0;
+        int ba = 0, bb = 0;
+        for (int a = 0; a < ns; ++a)
+            for (int b = 0; b < ns; ++b)
+                if (counts[(size_t)a * ns + b] > best) { best = counts[(size_t)a * ns + b]; ba = a; bb = b; }
+        if (best < min_count) break;
+        for (auto& s : sample) s.resize(zip_replace(s.data(), s.size(), (uint8_t)ba, (uint8_t)bb, (uint8_t)ns));
+        mg.pairs.push_back({(uint8_t)ba, (uint8_t)bb});
+        ++ns;
+    }
+    return mg;
+}
+
+// apply the merges in creation order to one chunk (symbols 1..L-1)
+static void zip_encode(const ZipMerges& mg, const uint8_t* sym, size_t n, std::vector<uint8_t>& out) {
+    out.assign(sym, sym + n);
+    size_t len = n;
+    for (size_t i = 0; i < mg.pairs.size() && len >= 2; ++i)
+        len = zip_replace(out.data(), len, mg.pairs[i][0], mg.pairs[i][1], (uint8_t)(mg.nsym + i));
+    out.resize(len);
+    out.shrink_to_fit();
+}
+
+// tokens over the first M ids only: larger ids are expanded into their parts (left first)
+static void zip_expand(const ZipMerges& mg, const std::vector<uint8_t>& in, int M, std::vector<uint8_t>& out) {
+    out.clear();
+    out.reserve(in.size());
+    uint8_t stack[512];
+    for (uint8_t tok : in) {
+        if (tok < M) { out.push_back(tok); continue; }
+        int sp = 0;
+        stack[sp++] = tok;
+        while (sp > 0) {
+            const uint8_t x = stack[--sp];
+            if (x < M) { out.push_back(x); continue; }
+            const auto& p = mg.pairs[x - mg.nsym];
+            stack[sp++] = p[1];   // right is applied after left
+            stack[sp++] = p[0];
+        }
+    }
+}
+
+// Dictionary of the first M ids renumbered by level (a pair's level = 1 + max level of its parts) so that the
+// kernel can build all entries of one level in parallel: perm[old id] = new id, pairs_new[new id] = (left, right)
+// in new ids (entries < nsym unused), level_start[l] .. level_start[l+1] = new ids of level l+1 (pairs only).
+struct ZipLevels {
+    std::vector<uint8_t> perm;
+    std::vector<uint8_t> pairs;        // [M][2]
+    std::vector<int> level_start;      // size nlevels + 1, level_start[0] = nsym
+};
+
+static ZipLevels zip_levels(const ZipMerges& mg, int M) {
+    ZipLevels zl;
+    std::vector<int> level(M, 0), order;
+    for (int id = mg.nsym; id < M; ++id) {
+        const auto& p = mg.pairs[id - mg.nsym];
+        level[id] = 1 + std::max(level[p[0]], level[p[1]]);
+        order.push_back(id);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
+    zl.perm.resize(M);
+    for (int s = 0; s < mg.nsym && s < M; ++s) zl.perm[s] = (uint8_t)s;
+    for (size_t i = 0; i < order.size(); ++i) zl.perm[order[i]] = (uint8_t)(mg.nsym + i);
+    zl.pairs.assign((size_t)M * 2, 0);
+    zl.level_start.push_back(mg.nsym);
+    int cur = 1;
+    for (size_t i = 0; i < order.size(); ++i) {
+        const int id = order[i];
+        while (level[id] > cur) { zl.level_start.push_back(mg.nsym + (int)i); ++cur; }
+        const auto& p = mg.pairs[id - mg.nsym];
+        zl.pairs[(size_t)(mg.nsym + i) * 2] = zl.perm[p[0]];
+        zl.pairs[(size_t)(mg.nsym + i) * 2 + 1] = zl.perm[p[1]];
+    }
+    zl.level_start.push_back(M);
+    return zl;
+}
+
+template <typename F>
+static void parallel_for(int n, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 4u, 32u);
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof cs, &cs) == 0) nt = std::min(nt, std::max(1, CPU_COUNT(&cs)));
+    nt = std::min(nt, n);
+    if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&]() { for (int i = next++; i < n; i = next++) fn(i); });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace imc

@@ -121,6 +121,39 @@ class ForwarderSet(object):
                                             out.ctypes.data_as(_lib.c_f64p)))
         return out
 
+    # -- the zipHMM-style preprocessing of the set (hmm.py:16: new_obs, sym2pair, new_nsyms), host only ----------
+    def zip_info(self, K=None):
+        """dict(ids_available=new_nsyms of the shared dictionary; with K: ids_used, tokens, levels for a K-state model)."""
+        lib = _lib.load()
+        avail, used, lev, tok = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        if K is None:
+            check(lib.imc_seqset_zip_info(self._handle, 0, ctypes.byref(avail), None, None, None))
+            return {"ids_available": avail.value}
+        check(lib.imc_seqset_zip_info(self._handle, int(K), ctypes.byref(avail), ctypes.byref(used), ctypes.byref(tok),
+                                      ctypes.byref(lev)))
+        return {"ids_available": avail.value, "ids_used": used.value, "tokens": tok.value, "levels": lev.value}
+
+    def zip_pairs(self):
+        """sym2pair[P,2] (uint8): row i = (left, right) of id NSYM + i, creation order."""
+        n = self.zip_info()["ids_available"] - (self.forwarders[0].NSYM if self.forwarders else 0)
+        out = np.zeros((max(n, 0), 2), dtype=np.uint8)
+        if n > 0:
+            check(_lib.load().imc_seqset_zip_pairs(self._handle, out.ctypes.data_as(_lib.c_u8p), n))
+        return out
+
+    def zip_tokens(self, chunk, ids=None):
+        """new_obs of chunk `chunk` (positions 1..L-1) over the first `ids` dictionary ids (default: all)."""
+        lib = _lib.load()
+        if ids is None:
+            ids = self.zip_info()["ids_available"]
+        n = ctypes.c_int64()
+        check(lib.imc_seqset_zip_tokens(self._handle, int(chunk), int(ids), None, 0, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=np.uint8)
+        if n.value:
+            check(lib.imc_seqset_zip_tokens(self._handle, int(chunk), int(ids), out.ctypes.data_as(_lib.c_u8p), out.size,
+                                            ctypes.byref(n)))
+        return out
+
     def forward_batch_device(self, d_pi, d_T, d_E, d_out, N, K, S, stream=0):
         """Device-resident variant: arguments are raw device pointers (ints); enqueued on `stream`."""
         check(_lib.load().imc_forward_batch_dev(self._handle, int(N), int(K), int(S), int(d_pi), int(d_T), int(d_E),

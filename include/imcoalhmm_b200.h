@@ -68,6 +68,19 @@ int imc_seqset_destroy(imc_seqset* set);
 /* any output may be NULL */
 int imc_seqset_info(const imc_seqset* set, int* n_chunks, int64_t* total_sites, int64_t* packed_bytes);
 
+/* The zipHMM-style preprocessing of the set (hmm.py:16 preprocess_raw_observations -> new_obs, sym2pair, new_nsyms):
+ * ids_available = new_nsyms of the set's shared dictionary (<= 256); for a K-state model the kernel keeps the
+ * first ids_used of them in shared memory; tokens = total length of the re-encoded chunks (positions 1..L-1)
+ * over those ids; levels = depth of the pair dictionary.  Host only; any output may be NULL. */
+int imc_seqset_zip_info(imc_seqset* set, int K, int* ids_available, int* ids_used, int64_t* tokens, int* levels);
+
+/* sym2pair of the set's dictionary in creation order: pairs_out[2*i], pairs_out[2*i+1] = (left, right) of id nsym + i. */
+int imc_seqset_zip_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs);
+/* new_obs of one chunk (index as given to imc_seqset_create) over the first `ids` dictionary ids, creation-order
+ * numbering.  Position 0 of the chunk is not part of the stream (alpha_0 = pi o E[:,o_0] carries no transition).
+ * out may be NULL to query the length. */
+int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_t* out, int64_t capacity, int64_t* ntokens);
+
 /* ---- forward log-likelihood ------------------------------------------------------------------------ */
 /* logL_out[0] = sum over the set's chunks of log P(chunk | pi, T, E).  Replaces
  * sum(f.forward(pi, T, E) for f in forwarders)  (hmm.py:19-21, likelihood.py:33). */
@@ -117,8 +130,13 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
                             int32_t* classes, uint8_t* lineages);
 
 /* ---- knobs and introspection (tests, bench) ---------------------------------------------------------- */
-/* key "forward_kernel": 0 auto, 1 generic (shared-memory state, per-step rescale), 2 lane-pair DFMA,
- *                       3 DMMA tiles.  Forcing a kernel that does not cover (K, S) returns IMC_ERR_UNSUPPORTED.
+/* key "forward_kernel": 0 auto (zip where instantiated), 1 generic (shared-memory state, per-step rescale),
+ *                       2 lane-pair DFMA, 3 DMMA tiles (1-3 walk every site), 4 zip (compressed token streams,
+ *                       dictionary matrices in shared memory).  Forcing a kernel that does not cover (K, S)
+ *                       returns IMC_ERR_UNSUPPORTED.
+ * key "zip_split":      CTAs per parameter point for the zip kernel (0 = auto: one per 32 chunks).
+ * key "zip_ctas_per_sm": 1 or 2 resident CTAs per SM (0 = auto); 2 halves the shared memory for the dictionary.
+ * key "zip_max_entries": cap on the dictionary ids used (0 = as many as fit).
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
  *                       of T where E[:,s0] > 0; 0 (default; measured faster on B200) = always multiply by the emission row. */

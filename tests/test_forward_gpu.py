@@ -10,7 +10,8 @@ from conftest import golden_model, example_symbols, random_hmm, synthetic_sequen
 pytestmark = pytest.mark.gpu
 RTOL = 1e-11
 
-KERNELS = {"generic": 1, "pair": 2, "dmma": 3}
+KERNELS = {"generic": 1, "pair": 2, "dmma": 3, "zip": 4}
+ZIP_K = (2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40)
 
 
 @pytest.fixture(autouse=True)
@@ -20,6 +21,9 @@ def _reset_options():
     m.set_option("forward_kernel", 0)
     m.set_option("dmma_mtiles", 0)
     m.set_option("fold_emission", 0)
+    m.set_option("zip_split", 0)
+    m.set_option("zip_ctas_per_sm", 0)
+    m.set_option("zip_max_entries", 0)
 
 
 def oracle_batch(chunks, pis, Ts, Es):
@@ -40,20 +44,25 @@ def test_example_alignment_reference_models():
     f = m.Forwarder.from_symbols(obs, 3)
     _, pi, T, E = golden_model("isolation_k10")
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3729.5586472699, rel=1e-11)
-    assert m.last_forward_kernel() == "pair"
+    assert m.last_forward_kernel() == "zip"
     _, pi, T, E = golden_model("im_k10_10")
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
-    assert m.last_forward_kernel() == "dmma"
+    assert m.last_forward_kernel() == "zip"
+    for code, name in ((2, "pair"), (3, "dmma")):
+        m.set_option("forward_kernel", code)
+        _, pi, T, E = golden_model("isolation_k10")
+        assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3729.5586472699, rel=1e-11)
+        assert m.last_forward_kernel() == name
 
 
 @pytest.mark.parametrize("model,kernels", [
-    ("isolation_k4", ["generic", "pair"]),
-    ("isolation_k10", ["generic", "pair", "dmma"]),
+    ("isolation_k4", ["generic", "pair", "zip"]),
+    ("isolation_k10", ["generic", "pair", "dmma", "zip"]),
     ("im_k3_4", ["generic"]),
-    ("im_epochs_2_3_3", ["generic", "pair", "dmma"]),
-    ("im_k10_10", ["generic", "dmma"]),
-    ("psmc_iso_split_4x10", ["generic", "dmma"]),
-    ("varmig_i12_4x10", ["generic", "dmma"]),
+    ("im_epochs_2_3_3", ["generic", "pair", "dmma", "zip"]),
+    ("im_k10_10", ["generic", "dmma", "zip"]),
+    ("psmc_iso_split_4x10", ["generic", "dmma", "zip"]),
+    ("varmig_i12_4x10", ["generic", "dmma", "zip"]),
 ])
 def test_batch_parity_on_reference_models(model, kernels):
     import imcoalhmm_b200 as m
@@ -89,6 +98,8 @@ def test_random_hmms_all_instantiated_sizes(K):
         if k == "pair" and (K % 2 or K > 12):
             continue
         if k == "dmma" and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
+            continue
+        if k == "zip" and K not in ZIP_K:
             continue
         m.set_option("forward_kernel", code)
         np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d %s" % (K, k))
@@ -161,7 +172,7 @@ def test_edge_cases():
     # an impossible observation gives -inf, not NaN
     E0 = Es[0].copy()
     E0[:, 1] = 0.0
-    for code in (1, 2):
+    for code in (1, 2, 4):
         m.set_option("forward_kernel", code)
         assert make_set([np.array([0, 0, 1, 0] * 10, dtype=np.uint8)]).forward(pis[0], Ts[0], E0) == -np.inf
     m.set_option("forward_kernel", 0)
@@ -191,6 +202,46 @@ def test_properties_at_scale():
     m.set_option("forward_kernel", 0)
     # the oracle on the same input (0.4 Mbp x 8 points: ~1 s of CPU)
     np.testing.assert_allclose(whole, oracle_batch([obs], pis[:8], Ts[:8], Es[:8]), rtol=RTOL)
+
+
+@pytest.mark.parametrize("K", [3, 5, 10, 20, 40])
+def test_zip_kernel_configurations(K):
+    """The compressed kernel under every launch shape: CTAs per point, resident CTAs per SM, dictionary caps
+    (3 = base symbols only, i.e. no compression), on compressible and on incompressible data."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(500 + K)
+    N = 3
+    hmms = [random_hmm(rng, K) for _ in range(N)]
+    pis, Ts, Es = (np.stack([h[i] for h in hmms]) for i in range(3))
+    # keep transitions sticky so that long compressed runs stay well conditioned
+    Ts = 0.9 * np.eye(K)[None] + 0.1 * Ts
+    chunks = [rng.choice(3, size=int(n), p=[0.95, 0.01, 0.04]).astype(np.uint8) for n in rng.integers(2000, 6000, size=37)]
+    chunks += [rng.integers(0, 3, size=n).astype(np.uint8) for n in (1, 2, 3, 16, 17, 18, 300)]
+    chunks += [np.zeros(70000, dtype=np.uint8), np.zeros(0, dtype=np.uint8)]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    m.set_option("forward_kernel", 4)
+    for split, ctas, cap in ((0, 0, 0), (1, 1, 0), (2, 2, 16), (5, 1, 3), (1000, 2, 4), (3, 0, 64)):
+        m.set_option("zip_split", split)
+        m.set_option("zip_ctas_per_sm", ctas)
+        m.set_option("zip_max_entries", cap)
+        got = s.forward_batch(pis, Ts, Es)
+        assert m.last_forward_kernel() == "zip"
+        np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="K=%d split=%d ctas=%d cap=%d" % (K, split, ctas, cap))
+
+
+@pytest.mark.parametrize("nsym", [1, 2, 4, 9])
+def test_zip_kernel_other_alphabets(nsym):
+    """NSYM other than 3 (the ILS scripts use alphabetSize=9, scripts/prepare-alignments.py:201) runs on the zip kernel."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(nsym)
+    K = 6
+    pi, T, E = random_hmm(rng, K, S=nsym, missing_col=False)
+    chunks = [rng.integers(0, nsym, size=n).astype(np.int32) for n in (1, 50, 1000, 4097)]
+    want = oracle_batch(chunks, pi[None], T[None], E[None])[0]
+    got = make_set(chunks, nsym).forward(pi, T, E)
+    assert m.last_forward_kernel() == "zip"
+    assert got == pytest.approx(want, rel=RTOL)
 
 
 def test_ziphmm_module_contract():

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimcoalhmm_b200.so")
+LIB_PATH = os.environ.get("IMC_LIB_PATH") or os.path.join(_HERE, "libimcoalhmm_b200.so")   # IMC_LIB_PATH: experiment builds
 
 
 class IMCError(RuntimeError):

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "imc_lib.cu")
-OUT = os.path.join(HERE, "libimcoalhmm_b200.so")
+OUT = os.environ.get("IMC_LIB_PATH") or os.path.join(HERE, "libimcoalhmm_b200.so")   # IMC_LIB_PATH: experiment builds
 DEPS = [SRC, os.path.join(HERE, "csrc", "forward_kernels.cuh"),
         os.path.join(HERE, "csrc", "zip_kernels.cuh"),
         os.path.join(HERE, "csrc", "tokenizer.inl"),
@@ -28,7 +28,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = ([nvcc] + NVCC_FLAGS + os.environ.get("IMC_EXTRA_NVCC_FLAGS", "").split() +
+           (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC])
     subprocess.check_call(cmd)
     return OUT
 

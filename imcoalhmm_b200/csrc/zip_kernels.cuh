@@ -50,12 +50,30 @@ struct ZipCfg {
     static constexpr int CP = KP / 2;                  // units per row
     static constexpr int RPL = (K + 7) / 8;            // rows per lane
     static constexpr int STRIDE_D = RPL * CP * 16;     // doubles per dictionary matrix
-    static constexpr int GS = 2 * KP + 2;              // doubles of exchange buffer per chain (2 buffers; odd multiple of 16 B)
+    // Exchange buffer per chain: 2 x KP doubles (+2 of skew room), stride = 64 (mod 128) bytes, chains 2,3 of a warp
+    // skewed by 16 bytes: in 16-byte bank groups the four chains then start at 0,4,1,5 (mod 8), so the two chains of
+    // each half-warp store their 64-byte row blocks into disjoint bank halves (STS.64: 2 wavefronts instead of 4,
+    // tools/microbench/smem_patterns.cu) AND the quarter-broadcast read-back touches four different bank groups.
+    static constexpr int GS = ((2 * KP * 8 + 16 + 63) / 128 * 128 + 64) / 8;
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
+    static constexpr int FULL = K / 8;                 // slots in which all 8 lanes own a row
+    static constexpr int REM = K % 8;                  // rows of the last, partial slot
+    // The partial slot is stored REP times side by side (lane positions f*REM .. f*REM+REM-1 hold rows 8*FULL ..):
+    // chain slot g of a warp lets lanes of copy g % REP own the remainder rows, so that the four quarter-warps
+    // of one LDS.128 touch different bank groups instead of all hitting groups 0..REM-1.
+    static constexpr int REP = REM ? 8 / REM : 1;
     __host__ __device__ static constexpr int se_doubles(int S) { return (K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
-    // element (row r, column c): slot r/8, unit (slot*CP + c/2)*8 + r%8
+    // element (row r, column c): slot r/8, unit (slot*CP + c/2)*8 + r%8 (first copy of the partial slot)
     __host__ __device__ static constexpr int off(int r, int c) {
         return (((r >> 3) * CP + (c >> 1)) * 8 + (r & 7)) * 2 + (c & 1);
+    }
+    __device__ static __forceinline__ void store(double* D, int r, int c, double v) {
+        const int o = off(r, c);
+        D[o] = v;
+        if (REM && r >= 8 * FULL) {
+#pragma unroll
+            for (int f = 1; f < REP; ++f) D[o + 2 * f * REM] = v;
+        }
     }
     static size_t smem_bytes(int M, int S, int threads) {
         size_t d = (size_t)M * STRIDE_D + (size_t)se_doubles(S) + KP + (size_t)(threads / 8) * GS;
@@ -72,13 +90,13 @@ struct ZipCfg {
 // one token for one chain: acc = (rows of C_id owned by lane q) . al ; exchange ; al = new state
 template <int K, bool PRED>
 __device__ __forceinline__ void zip_step(double (&al)[ZipCfg<K>::KP], const double* dict, const int* dexp, int id,
-                                         double* sb, int q, long long& scale, bool active) {
+                                         double* sb, int q, int rem_row, long long& scale, bool active) {
     using C = ZipCfg<K>;
     if (!PRED || active) {
         const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * C::STRIDE_D) + q;
 #pragma unroll
         for (int k = 0; k < C::RPL; ++k) {
-            if (8 * k + 8 <= K || q + 8 * k < K) {
+            if (k < C::FULL || rem_row >= 0) {     // rem_row: row of the partial slot owned by this lane, or -1
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int cp = 0; cp < C::CP; ++cp) {
@@ -86,19 +104,24 @@ __device__ __forceinline__ void zip_step(double (&al)[ZipCfg<K>::KP], const doub
                     s0 = fma(m.x, al[2 * cp], s0);
                     s1 = fma(m.y, al[2 * cp + 1], s1);
                 }
-                sb[q + 8 * k] = s0 + s1;
+                sb[k < C::FULL ? q + 8 * k : rem_row] = s0 + s1;
             }
         }
         scale += dexp[id];
     }
     __syncwarp();
     if (!PRED || active) {
+#ifdef IMC_ZIP_READBACK64
+#pragma unroll
+        for (int k = 0; k < C::KP; ++k) al[k] = sb[k];
+#else
 #pragma unroll
         for (int cp = 0; cp < C::CP; ++cp) {
             const double2 v = reinterpret_cast<const double2*>(sb)[cp];
             al[2 * cp] = v.x;
             al[2 * cp + 1] = v.y;
         }
+#endif
     }
 }
 
@@ -156,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                 for (int x = lane; x < K * K; x += 32) {
                     const int r = x / K, c = x % K;
                     const double v = sE[r * S + e] * Tg[c * K + r];
-                    D[C::off(r, c)] = v;
+                    C::store(D, r, c, v);
                     mx = fmax(mx, fabs(v));
                     bad = bad || !(fabs(v) < 1.7e308);
                 }
@@ -170,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                     double acc = 0.0;
 #pragma unroll 4
                     for (int k = 0; k < K; ++k) acc = fma(B[C::off(r, k)], A[C::off(k, c)], acc);
-                    D[C::off(r, c)] = acc;
+                    C::store(D, r, c, acc);
                     mx = fmax(mx, fabs(acc));
                     bad = bad || !(fabs(acc) < 1.7e308);
                 }
@@ -183,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                 ex = exponent_of(mx);
                 if (ex < -1000) ex = -1000;
                 const double f = pow2_neg(ex);
-                for (int x = lane; x < K * K; x += 32) D[C::off(x / K, x % K)] *= f;
+                for (int x = lane; x < K * K; x += 32) C::store(D, x / K, x % K, D[C::off(x / K, x % K)] * f);
             }
             if (lane == 0) dexp[e] = ebase + ex;
         }
@@ -192,7 +215,12 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
 
     // ---- phase 2: chains ----------------------------------------------------------------------------
     const int q = lane & 7, grp = lane >> 3;
-    double* sb0 = sbuf + (size_t)(warp * 4 + grp) * C::GS;
+    int rem_row = -1;
+    if (C::REM) {
+        const int p = q - (grp % C::REP) * C::REM;
+        if (p >= 0 && p < C::REM) rem_row = 8 * C::FULL + p;
+    }
+    double* sb0 = sbuf + (size_t)(warp * 4 + grp) * C::GS + (grp >> 1) * 2;
     const int cnt = (a.nchunks - j + a.J - 1) / a.J;       // chunks owned by this CTA
     for (;;) {
         int base = 0;
@@ -229,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                     for (int b = 0; b < 4; ++b) {
                         const int id = wv & 0xffu;
                         wv >>= 8;
-                        zip_step<K, false>(al, dict, dexp, id, sb0 + buf * KP, q, scale, true);
+                        zip_step<K, false>(al, dict, dexp, id, sb0 + buf * KP, q, rem_row, scale, true);
                         buf ^= 1;
                     }
                     if (wi & 1) zip_rescale<K>(al, scale, dead, isnan);
@@ -242,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                     for (int b = 0; b < 4; ++b) {
                         const int id = wv & 0xffu;
                         wv >>= 8;
-                        zip_step<K, true>(al, dict, dexp, id, sb0 + buf * KP, q, scale, wi * 4 + b < rem);
+                        zip_step<K, true>(al, dict, dexp, id, sb0 + buf * KP, q, rem_row, scale, wi * 4 + b < rem);
                         buf ^= 1;
                     }
                     if (wi & 1) zip_rescale<K>(al, scale, dead, isnan);

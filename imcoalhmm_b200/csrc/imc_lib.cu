@@ -55,8 +55,8 @@ struct Context {
     long long opt_forward_kernel = 0;
     long long opt_dmma_mtiles = 0;
     long long opt_fold_emission = 0;   // measured slower than the emission-row multiply on B200 (profiles/r01_pair_micro2.txt)
-    long long opt_zip_split = 0;       // CTAs per parameter point for the zip kernel (0 = auto)
     long long opt_zip_ctas_per_sm = 0; // 1 or 2 resident CTAs per SM for the zip kernel (0 = auto)
+    long long opt_zip_lanes = 0;       // lanes per chain in the zip kernel: 8, 4 or 0 = auto
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
 };
 static Context g_ctx;
@@ -133,7 +133,7 @@ struct imc_seqset {
     std::vector<int> stream_of_chunk;             // chunk index as given to imc_seqset_create -> stream (-1: empty chunk)
     // device side (lazy)
     bool uploaded = false;
-    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out;
+    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext;
     std::vector<ZipDevice*> zip_dev;      // one per dictionary size in use
 };
 
@@ -344,7 +344,7 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
     const bool mine = g_ctx.pid == getpid();
     if (mine) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
-        set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
+        set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release(); set->d_pnext.release();
     }
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
@@ -391,32 +391,50 @@ static bool zip_supported(int K) {
     return false;
 }
 
-struct ZipPlan { int threads, ctas_per_sm, M; size_t smem; };
+struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
 static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
 
+// Launch shapes (all persistent, see zip_forward_kernel):
+//   lanes per chain 8: two CTAs of 256 threads per SM (K <= 24), or one CTA with all the shared memory for the
+//                      dictionary -- 512 threads where the register file allows (K <= 24), else 256;
+//   lanes per chain 4: one or (K <= 24) two CTAs of 256 threads (64 chains per CTA), K >= 8 only.
+// measured on B200 (gpurun_out/zip_bench_*.log, round 1): K=10 8.3 ms (8 lanes) vs 9.7 ms (4, padded to 12);
+// K=20 58.9 vs 43.7 ms; K=40 175 vs 190 ms (4 lanes need twice the exchange buffers, which costs dictionary entries)
+static int zip_default_lanes(int K) { return (K >= 12 && K <= 24) ? 4 : 8; }
+
 template <int K>
-static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas) {
-    using C = ZipCfg<K>;
+static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
     ZipPlan p;
-    p.threads = 256;
-    const int m2 = C::max_entries((ZIP_SMEM_SM - 1024) / 2, S, p.threads);
-    const int m1 = C::max_entries(ZIP_SMEM_SM, S, p.threads);
-    // two resident CTAs per SM overlap one CTA's dictionary build / tail with the other's chains; take that
-    // whenever half the shared memory still holds the whole dictionary or at least 48 entries
+    p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
+    if (K < 8) p.lanes = 8;
+    int m1, m2, t1;
+    if (p.lanes == 8) {
+        using C = ZipCfg8<K>;
+        t1 = K <= 24 ? 512 : 256;
+        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+    } else {
+        using C = ZipCfg4<K>;
+        t1 = 256;
+        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+    }
     int ctas = want_ctas;
-    if (ctas == 0) ctas = (m2 >= avail_ids || m2 >= 48) ? 2 : 1;
+    if (ctas == 2 && K > 24) ctas = 1;
+    if (ctas == 0) ctas = (K <= 24 && m2 >= avail_ids) ? 2 : 1;   // the bigger dictionary wins unless everything fits in half
     p.ctas_per_sm = ctas;
+    p.threads = ctas == 2 ? 256 : t1;
     p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
     if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
     p.M = std::max(p.M, S);
-    p.smem = C::smem_bytes(p.M, S, p.threads);
+    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads);
     return p;
 }
 
 static int zip_plan(int K, int S, int avail_ids, ZipPlan* out) {
-    const int want = (int)g_ctx.opt_zip_ctas_per_sm;
+    const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = (int)g_ctx.opt_zip_lanes;
     switch (K) {
-#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want); break;
+#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
         ZIP_K_LIST(X)
 #undef X
         default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
@@ -484,15 +502,45 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     return IMC_OK;
 }
 
-template <int K, int MINB>
-static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
+template <class C, int THREADS, int MINB>
+static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
     static size_t attr_max = 0;
     if (p.smem > attr_max) {
-        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<K, 256, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<C, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         attr_max = p.smem;
     }
-    zip_forward_kernel<K, 256, MINB><<<(unsigned)((long long)a.N * a.J), 256, p.smem, st>>>(a);
+    zip_forward_kernel<C, THREADS, MINB><<<grid, THREADS, p.smem, st>>>(a);
     return IMC_OK;
+}
+
+template <int K>
+static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
+    if constexpr (K >= 8) {
+        if (p.lanes == 4) {
+            if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2>(a, p, grid, st); }
+            return launch_zip_k<ZipCfg4<K>, 256, 1>(a, p, grid, st);
+        }
+    }
+    if constexpr (K <= 24) {
+        if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2>(a, p, grid, st);
+        return launch_zip_k<ZipCfg8<K>, 512, 1>(a, p, grid, st);
+    } else {
+        return launch_zip_k<ZipCfg8<K>, 256, 1>(a, p, grid, st);
+    }
+}
+
+static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
+    // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
+    const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
+    const long long units = (long long)a.N * ((nunits + nw - 1) / nw);
+    const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+    const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
+    switch (a.K) {
+#define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
+        ZIP_K_LIST(X)
+#undef X
+    }
+    return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", a.K);
 }
 
 extern "C" int imc_seqset_zip_info(imc_seqset* set, int K, int* ids_available, int* ids_used, int64_t* tokens, int* levels) {
@@ -538,15 +586,6 @@ extern "C" int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_
         if (!tok.empty()) memcpy(out, tok.data(), tok.size());
     }
     return IMC_OK;
-}
-
-static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
-    switch (a.K) {
-#define X(k) case k: return p.ctas_per_sm == 2 ? launch_zip_k<k, 2>(a, p, st) : launch_zip_k<k, 1>(a, p, st);
-        ZIP_K_LIST(X)
-#undef X
-    }
-    return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", a.K);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -647,8 +686,9 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         za.tokens = (const uint8_t*)z->tokens.p;
         za.chunks = (const ZipChunk*)z->chunks.p;
         za.nchunks = ns;
-        const int slots = plan.threads / 8;
-        za.J = g_ctx.opt_zip_split > 0 ? (int)std::min<long long>(g_ctx.opt_zip_split, ns) : (ns + slots - 1) / slots;
+        if ((rc = set->d_pnext.reserve(sizeof(int) * (size_t)N))) return rc;
+        CUDA_TRY(cudaMemsetAsync(set->d_pnext.p, 0, sizeof(int) * (size_t)N, st));
+        za.point_next = (int*)set->d_pnext.p;
         za.pairs = (const uint8_t*)z->pairs.p;
         za.level_start = (const int*)z->levels.p;
         za.nlevels = z->nlevels;
@@ -807,8 +847,8 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
         return IMC_OK;
     }
     if (!strcmp(key, "fold_emission")) { g_ctx.opt_fold_emission = value ? 1 : 0; return IMC_OK; }
-    if (!strcmp(key, "zip_split")) { if (value < 0) return fail(IMC_ERR_INVALID, "zip_split must be >= 0"); g_ctx.opt_zip_split = value; return IMC_OK; }
     if (!strcmp(key, "zip_ctas_per_sm")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_ctas_per_sm must be 0, 1 or 2"); g_ctx.opt_zip_ctas_per_sm = value; return IMC_OK; }
+    if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4 or 8"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
@@ -817,8 +857,8 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "forward_kernel")) { *value_out = g_ctx.opt_forward_kernel; return IMC_OK; }
     if (!strcmp(key, "dmma_mtiles")) { *value_out = g_ctx.opt_dmma_mtiles; return IMC_OK; }
     if (!strcmp(key, "fold_emission")) { *value_out = g_ctx.opt_fold_emission; return IMC_OK; }
-    if (!strcmp(key, "zip_split")) { *value_out = g_ctx.opt_zip_split; return IMC_OK; }
     if (!strcmp(key, "zip_ctas_per_sm")) { *value_out = g_ctx.opt_zip_ctas_per_sm; return IMC_OK; }
+    if (!strcmp(key, "zip_lanes")) { *value_out = g_ctx.opt_zip_lanes; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }

@@ -31,7 +31,7 @@ struct ZipArgs {
     const uint8_t* tokens;
     const ZipChunk* chunks;      // sorted by ntok, descending
     int nchunks;
-    int J;                       // CTAs per parameter point; CTA j owns chunks j, j+J, j+2J, ...
+    int* point_next;             // [N] warp-loads of chunks already claimed per parameter point (zeroed before the launch)
     const uint8_t* pairs;        // [M][2] (left, right) in level order; entries < S unused
     const int* level_start;      // [nlevels + 1]
     int nlevels;
@@ -44,16 +44,28 @@ struct ZipArgs {
     int out_stride;
 };
 
-template <int K>
-struct ZipCfg {
+// ------------------------------------------------------------------------------------------------
+// Lane decompositions.  A config class C describes how one chain's mat-vec is spread over G lanes:
+//   C::K, C::KP (state registers per lane), C::G, C::CPW = 32 / G chains per warp,
+//   C::STRIDE_D doubles per dictionary matrix, C::off / C::store (matrix layout), C::GS (exchange buffer stride),
+//   C::Lane (per-lane constants), C::step (one token), C::state_of (which state register k of a lane holds).
+// Costs measured on B200 (tools/microbench/smem_patterns.cu): LDS.128 with 512 distinct bytes 4.2 clk, sparse or
+// quarter-broadcast LDS.128 ~3 clk, STS.64 2 clk when bank-disjoint per half-warp.
+// ------------------------------------------------------------------------------------------------
+
+// G = 8: lane q owns rows q, q+8, ...; every LDS.128 of a quarter-warp reads 8 consecutive units of ONE matrix.
+template <int K_>
+struct ZipCfg8 {
+    static constexpr int K = K_;
+    static constexpr int G = 8, CPW = 4;
     static constexpr int KP = (K + 1) & ~1;            // columns padded to an even count (16-byte units)
     static constexpr int CP = KP / 2;                  // units per row
     static constexpr int RPL = (K + 7) / 8;            // rows per lane
     static constexpr int STRIDE_D = RPL * CP * 16;     // doubles per dictionary matrix
     // Exchange buffer per chain: 2 x KP doubles (+2 of skew room), stride = 64 (mod 128) bytes, chains 2,3 of a warp
     // skewed by 16 bytes: in 16-byte bank groups the four chains then start at 0,4,1,5 (mod 8), so the two chains of
-    // each half-warp store their 64-byte row blocks into disjoint bank halves (STS.64: 2 wavefronts instead of 4,
-    // tools/microbench/smem_patterns.cu) AND the quarter-broadcast read-back touches four different bank groups.
+    // each half-warp store their 64-byte row blocks into disjoint bank halves (STS.64: 2 wavefronts instead of 4)
+    // AND the quarter-broadcast read-back touches four different bank groups.
     static constexpr int GS = ((2 * KP * 8 + 16 + 63) / 128 * 128 + 64) / 8;
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
     static constexpr int FULL = K / 8;                 // slots in which all 8 lanes own a row
@@ -62,7 +74,6 @@ struct ZipCfg {
     // chain slot g of a warp lets lanes of copy g % REP own the remainder rows, so that the four quarter-warps
     // of one LDS.128 touch different bank groups instead of all hitting groups 0..REM-1.
     static constexpr int REP = REM ? 8 / REM : 1;
-    __host__ __device__ static constexpr int se_doubles(int S) { return (K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
     // element (row r, column c): slot r/8, unit (slot*CP + c/2)*8 + r%8 (first copy of the partial slot)
     __host__ __device__ static constexpr int off(int r, int c) {
         return (((r >> 3) * CP + (c >> 1)) * 8 + (r & 7)) * 2 + (c & 1);
@@ -75,66 +86,152 @@ struct ZipCfg {
             for (int f = 1; f < REP; ++f) D[o + 2 * f * REM] = v;
         }
     }
-    static size_t smem_bytes(int M, int S, int threads) {
-        size_t d = (size_t)M * STRIDE_D + (size_t)se_doubles(S) + KP + (size_t)(threads / 8) * GS;
-        return d * sizeof(double) + ((size_t)M + 4) * sizeof(int);
+    struct Lane {
+        int q, grp, rem_row;
+        double* sb0;
+        __device__ __forceinline__ Lane(int lane, int warp, double* sbuf) {
+            q = lane & 7; grp = lane >> 3;
+            rem_row = -1;
+            if (REM) {
+                const int p = q - (grp % REP) * REM;
+                if (p >= 0 && p < REM) rem_row = 8 * FULL + p;
+            }
+            sb0 = sbuf + (size_t)(warp * 4 + grp) * GS + (grp >> 1) * 2;
+        }
+        __device__ __forceinline__ bool writer() const { return q == 0; }
+    };
+    __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
+    template <bool PRED>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const int* dexp, int id,
+                                                const Lane& L, int buf, long long& scale, bool active) {
+        double* sb = L.sb0 + buf * KP;
+        if (!PRED || active) {
+            const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                if (k < FULL || L.rem_row >= 0) {     // rem_row: row of the partial slot owned by this lane, or -1
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int cp = 0; cp < CP; ++cp) {
+                        const double2 m = mp[(k * CP + cp) * 8];
+                        s0 = fma(m.x, al[2 * cp], s0);
+                        s1 = fma(m.y, al[2 * cp + 1], s1);
+                    }
+                    sb[k < FULL ? L.q + 8 * k : L.rem_row] = s0 + s1;
+                }
+            }
+            scale += dexp[id];
+        }
+        __syncwarp();
+        if (!PRED || active) {
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp) {
+                const double2 v = reinterpret_cast<const double2*>(sb)[cp];
+                al[2 * cp] = v.x;
+                al[2 * cp + 1] = v.y;
+            }
+        }
+    }
+};
+
+// G = 4: the state count is padded to a multiple of 4, lane g owns rows g, g+4, ...  A quarter-warp holds TWO chains
+// (slots c = 0, 1) that use different matrices, so the layout splits every 128-byte line into an even half (bank
+// groups 0-3) and an odd half (groups 4-7): line l holds pieces 2l and 2l+1 of each lane's row data (piece p =
+// row g + 4*(p / CP), column pair p % CP).  Slot 0 reads piece t at instruction t, slot 1 reads piece t^1, so the
+// two chains of a quarter-warp always sit in opposite halves -- conflict free whatever the two matrices are.
+// CP is even, so t^1 is the neighbouring column pair of the same row: slot-1 lanes simply keep their state registers
+// with neighbouring pairs swapped (they read the exchange buffer at cp^1).  Half as many lanes per chain halves the
+// cost of the state exchange per chain-step and leaves no partially filled loads.
+template <int K_>
+struct ZipCfg4 {
+    static constexpr int K = K_;
+    static constexpr int G = 4, CPW = 8;
+    static constexpr int KP = (K + 3) & ~3;            // states padded to a multiple of 4
+    static constexpr int CP = KP / 2;                  // column pairs per row (even)
+    static constexpr int RPL = KP / 4;                 // rows per lane
+    static constexpr int STRIDE_D = KP * KP;           // dense
+    // exchange buffer per chain: 2 x KP doubles, stride = 32 (mod 128) bytes: the four chains of a half-warp store
+    // their 32-byte row blocks into four different bank quarters (STS.64 in 2 wavefronts)
+    static constexpr int GS = ((2 * KP * 8 + 95) / 128 * 128 + 32) / 8;
+    static constexpr int UNROLL = K <= 12 ? 4 : 1;
+    __host__ __device__ static constexpr int off(int r, int c) {
+        const int p = (r >> 2) * CP + (c >> 1);
+        return (((p >> 1) * 8 + (p & 1) * 4 + (r & 3)) * 2) + (c & 1);
+    }
+    __device__ static __forceinline__ void store(double* D, int r, int c, double v) { D[off(r, c)] = v; }
+    struct Lane {
+        int g, c, grp;
+        int off_even, off_odd;     // byte offsets of this lane's even / odd pieces inside a matrix
+        double* sb0;
+        __device__ __forceinline__ Lane(int lane, int warp, double* sbuf) {
+            g = lane & 3; grp = lane >> 2; c = grp & 1;
+            off_even = (c * 4 + g) * 16;
+            off_odd = ((1 - c) * 4 + g) * 16;
+            sb0 = sbuf + (size_t)(warp * 8 + grp) * GS;
+        }
+        __device__ __forceinline__ bool writer() const { return g == 0; }
+    };
+    // register k of a slot-c lane holds state 2*((k/2)^c) + k%2
+    __device__ static __forceinline__ int state_of(const Lane& L, int k) { return 2 * ((k >> 1) ^ L.c) + (k & 1); }
+    template <bool PRED>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const int* dexp, int id,
+                                                const Lane& L, int buf, long long& scale, bool active) {
+        double* sb = L.sb0 + buf * KP;
+        if (!PRED || active) {
+            const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
+            const char* me = mb + L.off_even;
+            const char* mo = mb + L.off_odd;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp) {
+                    const int t = k * CP + cp;
+                    const double2 m = *reinterpret_cast<const double2*>(((t & 1) ? mo : me) + (t >> 1) * 128);
+                    s0 = fma(m.x, al[2 * cp], s0);
+                    s1 = fma(m.y, al[2 * cp + 1], s1);
+                }
+                sb[L.g + 4 * k] = s0 + s1;
+            }
+            scale += dexp[id];
+        }
+        __syncwarp();
+        if (!PRED || active) {
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp) {
+                const double2 v = reinterpret_cast<const double2*>(sb)[cp ^ L.c];
+                al[2 * cp] = v.x;
+                al[2 * cp + 1] = v.y;
+            }
+        }
+    }
+};
+
+template <class C>
+struct ZipSmem {
+    __host__ __device__ static constexpr int se_doubles(int S) { return (C::K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
+    static size_t bytes(int M, int S, int threads) {
+        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / C::G) * C::GS;
+        return d * sizeof(double) + ((size_t)M + 4) * sizeof(int);   // dexp[M], s_point[2]
     }
     static int max_entries(size_t budget, int S, int threads) {
-        const size_t fixed = smem_bytes(0, S, threads);
+        const size_t fixed = bytes(0, S, threads);
         if (budget <= fixed) return 0;
-        const size_t m = (budget - fixed) / (STRIDE_D * sizeof(double) + sizeof(int));
+        const size_t m = (budget - fixed) / (C::STRIDE_D * sizeof(double) + sizeof(int));
         return (int)(m > 256 ? 256 : m);
     }
 };
 
-// one token for one chain: acc = (rows of C_id owned by lane q) . al ; exchange ; al = new state
-template <int K, bool PRED>
-__device__ __forceinline__ void zip_step(double (&al)[ZipCfg<K>::KP], const double* dict, const int* dexp, int id,
-                                         double* sb, int q, int rem_row, long long& scale, bool active) {
-    using C = ZipCfg<K>;
-    if (!PRED || active) {
-        const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * C::STRIDE_D) + q;
-#pragma unroll
-        for (int k = 0; k < C::RPL; ++k) {
-            if (k < C::FULL || rem_row >= 0) {     // rem_row: row of the partial slot owned by this lane, or -1
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int cp = 0; cp < C::CP; ++cp) {
-                    const double2 m = mp[(k * C::CP + cp) * 8];
-                    s0 = fma(m.x, al[2 * cp], s0);
-                    s1 = fma(m.y, al[2 * cp + 1], s1);
-                }
-                sb[k < C::FULL ? q + 8 * k : rem_row] = s0 + s1;
-            }
-        }
-        scale += dexp[id];
-    }
-    __syncwarp();
-    if (!PRED || active) {
-#ifdef IMC_ZIP_READBACK64
-#pragma unroll
-        for (int k = 0; k < C::KP; ++k) al[k] = sb[k];
-#else
-#pragma unroll
-        for (int cp = 0; cp < C::CP; ++cp) {
-            const double2 v = reinterpret_cast<const double2*>(sb)[cp];
-            al[2 * cp] = v.x;
-            al[2 * cp + 1] = v.y;
-        }
-#endif
-    }
-}
-
-template <int K>
-__device__ __forceinline__ void zip_rescale(double (&al)[ZipCfg<K>::KP], long long& scale, bool& dead, bool& isnan) {
+template <class C>
+__device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scale, bool& dead, bool& isnan) {
     double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) sum += al[k];
+    for (int k = 0; k < C::KP; ++k) sum += al[k];       // padding registers hold 0
     if (sum > 0.0 && sum < 1.7e308) {
         const int e = exponent_of(sum);
         const double f = pow2_neg(e);
 #pragma unroll
-        for (int k = 0; k < K; ++k) al[k] *= f;
+        for (int k = 0; k < C::KP; ++k) al[k] *= f;
         scale += e;
     } else {
         dead = true;
@@ -142,31 +239,18 @@ __device__ __forceinline__ void zip_rescale(double (&al)[ZipCfg<K>::KP], long lo
     }
 }
 
-template <int K, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
-    using C = ZipCfg<K>;
-    constexpr int KP = C::KP, NW = THREADS / 32;
-    extern __shared__ __align__(128) unsigned char zsm_raw[];
-    double* dict = reinterpret_cast<double*>(zsm_raw);
-    const int M = a.M, S = a.S;
-    double* sE = dict + (size_t)M * C::STRIDE_D;      // [K][S]
-    double* spi = sE + C::se_doubles(S);              // [KP]
-    double* sbuf = spi + KP;                          // [THREADS/8][GS]
-    int* dexp = reinterpret_cast<int*>(sbuf + (THREADS / 8) * C::GS);   // [M]
-    int* s_next = dexp + M;
-
+// Build the dictionary of parameter point n in shared memory (all threads of the CTA).
+template <class C, int THREADS>
+__device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, int* dexp) {
+    constexpr int K = C::K, KP = C::KP, NW = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = blockIdx.x / a.J, j = blockIdx.x % a.J;
+    const int M = a.M, S = a.S;
     const double* Tg = a.T + (size_t)n * K * K;
     const double* Eg = a.E + (size_t)n * K * S;
     const double* pig = a.pi + (size_t)n * K;
-
-    // ---- phase 1: dictionary ------------------------------------------------------------------------
     for (int x = tid; x < M * C::STRIDE_D; x += THREADS) dict[x] = 0.0;
     for (int x = tid; x < K * S; x += THREADS) sE[x] = Eg[x];
     for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? pig[x] : 0.0;
-    for (int x = tid; x < (THREADS / 8) * C::GS; x += THREADS) sbuf[x] = 0.0;   // the padding column of odd K stays 0
-    if (tid == 0) *s_next = 0;
     __syncthreads();
     for (int lv = -1; lv < a.nlevels; ++lv) {
         const int lo = lv < 0 ? 0 : a.level_start[lv], hi = lv < 0 ? S : a.level_start[lv + 1];
@@ -212,79 +296,137 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
         }
         __syncthreads();
     }
+}
 
-    // ---- phase 2: chains ----------------------------------------------------------------------------
-    const int q = lane & 7, grp = lane >> 3;
-    int rem_row = -1;
-    if (C::REM) {
-        const int p = q - (grp % C::REP) * C::REM;
-        if (p >= 0 && p < C::REM) rem_row = 8 * C::FULL + p;
+// One warp-load of chains (C::CPW of them, one per lane group) of parameter point n: the chunks
+// unit*CPW .. unit*CPW + CPW-1 of the sorted chunk list.
+template <class C>
+__device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
+                                             const double* spi, const int* dexp, const typename C::Lane& L) {
+    constexpr int K = C::K, KP = C::KP;
+    const int S = a.S;
+    const int ci = unit * C::CPW + L.grp;
+    const bool have = ci < a.nchunks;
+    const ZipChunk ch = a.chunks[have ? ci : unit * C::CPW];
+    const int nt = have ? ch.ntok : 0;
+    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off);
+    int maxnt = nt;
+#pragma unroll
+    for (int m = 16; m >= C::G; m >>= 1) maxnt = max(maxnt, __shfl_xor_sync(0xffffffffu, maxnt, m));
+
+    double al[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int st = C::state_of(L, k);
+        al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
     }
-    double* sb0 = sbuf + (size_t)(warp * 4 + grp) * C::GS + (grp >> 1) * 2;
-    const int cnt = (a.nchunks - j + a.J - 1) / a.J;       // chunks owned by this CTA
-    for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(s_next, 4);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= cnt) break;
-        const int ci = base + grp;
-        const bool have = ci < cnt;
-        const ZipChunk ch = a.chunks[j + (have ? ci : base) * a.J];
-        const int nt = have ? ch.ntok : 0;
-        const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off);
-        int maxnt = nt;
+    long long scale = 0;
+    bool dead = false, isnan = false;
+    int buf = 0;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (nt > 0) cur = tp[0];
+    for (int blk = 0; blk * 16 < maxnt; ++blk) {
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if ((blk + 1) * 16 < nt) nxt = tp[blk + 1];
+        const int rem = nt - blk * 16;
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        if (__all_sync(0xffffffffu, rem >= 16)) {
 #pragma unroll
-        for (int m = 16; m >= 8; m >>= 1) maxnt = max(maxnt, __shfl_xor_sync(0xffffffffu, maxnt, m));
-
-        double al[KP];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) al[k] = k < K ? spi[k] * sE[k * S + ch.first_sym] : 0.0;
-        long long scale = 0;
-        bool dead = false, isnan = false;
-        int buf = 0;
-        uint4 cur = make_uint4(0, 0, 0, 0);
-        if (nt > 0) cur = tp[0];
-        for (int blk = 0; blk * 16 < maxnt; ++blk) {
-            uint4 nxt = make_uint4(0, 0, 0, 0);
-            if ((blk + 1) * 16 < nt) nxt = tp[blk + 1];
-            const int rem = nt - blk * 16;
-            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-            if (__all_sync(0xffffffffu, rem >= 16)) {
-#pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    uint32_t wv = w[wi];
+            for (int wi = 0; wi < 4; ++wi) {
+                uint32_t wv = w[wi];
 #pragma unroll C::UNROLL
-                    for (int b = 0; b < 4; ++b) {
-                        const int id = wv & 0xffu;
-                        wv >>= 8;
-                        zip_step<K, false>(al, dict, dexp, id, sb0 + buf * KP, q, rem_row, scale, true);
-                        buf ^= 1;
-                    }
-                    if (wi & 1) zip_rescale<K>(al, scale, dead, isnan);
+                for (int b = 0; b < 4; ++b) {
+                    const int id = wv & 0xffu;
+                    wv >>= 8;
+                    C::template step<false>(al, dict, dexp, id, L, buf, scale, true);
+                    buf ^= 1;
                 }
-            } else {
+                if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
+            }
+        } else {
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    uint32_t wv = w[wi];
+            for (int wi = 0; wi < 4; ++wi) {
+                uint32_t wv = w[wi];
 #pragma unroll 1
-                    for (int b = 0; b < 4; ++b) {
-                        const int id = wv & 0xffu;
-                        wv >>= 8;
-                        zip_step<K, true>(al, dict, dexp, id, sb0 + buf * KP, q, rem_row, scale, wi * 4 + b < rem);
-                        buf ^= 1;
-                    }
-                    if (wi & 1) zip_rescale<K>(al, scale, dead, isnan);
+                for (int b = 0; b < 4; ++b) {
+                    const int id = wv & 0xffu;
+                    wv >>= 8;
+                    C::template step<true>(al, dict, dexp, id, L, buf, scale, wi * 4 + b < rem);
+                    buf ^= 1;
+                }
+                if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
+            }
+        }
+        cur = nxt;
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) sum += al[k];
+    double result;
+    if (dead || !(sum > 0.0)) result = (isnan || sum != sum) ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
+    else result = log(sum) + (double)scale * LN2;
+    if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
+}
+
+// Persistent CTAs.  Work unit = (parameter point, warp-load of C::CPW chunks); point_next[n] counts the units of
+// point n already claimed (zeroed before the launch).  A CTA first serves the points blockIdx.x, blockIdx.x +
+// gridDim.x, ... (building each point's dictionary once and letting its warps claim units), then helps whichever
+// point still has unclaimed units, so that the SMs finish together no matter how points and chunks divide among them.
+template <class C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
+    constexpr int KP = C::KP;
+    extern __shared__ __align__(128) unsigned char zsm_raw[];
+    double* dict = reinterpret_cast<double*>(zsm_raw);
+    const int M = a.M, S = a.S;
+    double* sE = dict + (size_t)M * C::STRIDE_D;      // [K][S]
+    double* spi = sE + ZipSmem<C>::se_doubles(S);     // [KP]
+    double* sbuf = spi + KP;                          // [THREADS/G][GS]
+    int* dexp = reinterpret_cast<int*>(sbuf + (THREADS / C::G) * C::GS);   // [M]
+    int* s_point = dexp + M;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const typename C::Lane L(lane, warp, sbuf);
+    for (int x = tid; x < (THREADS / C::G) * C::GS; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
+    const int nunits = (a.nchunks + C::CPW - 1) / C::CPW;
+    int primary = blockIdx.x;          // next point of this CTA's own share
+    int scan = (int)(((long long)blockIdx.x * 7919) % a.N);   // where the search for points to help starts
+    if (tid == 0) s_point[1] = 0x7fffffff;
+    for (;;) {
+        // ---- choose a point: own share first, then any point with unclaimed quads.  s_point[0] = point, -1 = none
+        // left anywhere, -2 = own point already finished by helpers.  All decisions go through shared memory so
+        // that they are uniform over the CTA.
+        __syncthreads();               // everybody is done with the previous point's dictionary and s_point[0]
+        if (primary < a.N) {
+            if (tid == 0) s_point[0] = *((volatile int*)(a.point_next + primary)) < nunits ? primary : -2;
+            primary += gridDim.x;
+        } else {
+            if (tid == 0) s_point[0] = -1;
+            for (int r0 = 0; r0 < a.N; r0 += THREADS) {
+                __syncthreads();       // s_point[1] == INT_MAX here
+                const int idx = r0 + tid;
+                if (idx < a.N && *((volatile int*)(a.point_next + (scan + idx) % a.N)) < nunits) atomicMin(s_point + 1, idx);
+                __syncthreads();
+                const int best = s_point[1];
+                if (best != 0x7fffffff) {
+                    __syncthreads();   // everyone has read `best`
+                    if (tid == 0) { s_point[0] = (scan + best) % a.N; s_point[1] = 0x7fffffff; }
+                    break;
                 }
             }
-            cur = nxt;
         }
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) sum += al[k];
-        double result;
-        if (dead || !(sum > 0.0)) result = (isnan || sum != sum) ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
-        else result = log(sum) + (double)scale * LN2;
-        if (have && q == 0) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
+        __syncthreads();
+        const int n = s_point[0];
+        if (n == -1) break;
+        if (n == -2) continue;
+        if (primary >= a.N) scan = (n + 1) % a.N;
+        zip_build_dictionary<C, THREADS>(a, n, dict, sE, spi, dexp);
+        for (;;) {
+            int unit = 0;
+            if (lane == 0) unit = atomicAdd(a.point_next + n, 1);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+            if (unit >= nunits) break;
+            zip_run_unit<C>(a, n, unit, dict, sE, spi, dexp, L);
+        }
     }
 }
 

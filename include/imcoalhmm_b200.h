@@ -134,8 +134,9 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       2 lane-pair DFMA, 3 DMMA tiles (1-3 walk every site), 4 zip (compressed token streams,
  *                       dictionary matrices in shared memory).  Forcing a kernel that does not cover (K, S)
  *                       returns IMC_ERR_UNSUPPORTED.
- * key "zip_split":      CTAs per parameter point for the zip kernel (0 = auto: one per 32 chunks).
- * key "zip_ctas_per_sm": 1 or 2 resident CTAs per SM (0 = auto); 2 halves the shared memory for the dictionary.
+ * key "zip_ctas_per_sm": 1 = one persistent CTA per SM with all of shared memory for the dictionary, 2 = two CTAs of
+ *                       256 threads with half each (K <= 24 only); 0 = auto.
+ * key "zip_lanes":      lanes that share one chain's mat-vec in the zip kernel: 8, 4 (K >= 8) or 0 = auto.
  * key "zip_max_entries": cap on the dictionary ids used (0 = as many as fit).
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy

@@ -21,9 +21,9 @@ def _reset_options():
     m.set_option("forward_kernel", 0)
     m.set_option("dmma_mtiles", 0)
     m.set_option("fold_emission", 0)
-    m.set_option("zip_split", 0)
     m.set_option("zip_ctas_per_sm", 0)
     m.set_option("zip_max_entries", 0)
+    m.set_option("zip_lanes", 0)
 
 
 def oracle_batch(chunks, pis, Ts, Es):
@@ -102,7 +102,9 @@ def test_random_hmms_all_instantiated_sizes(K):
         if k == "zip" and K not in ZIP_K:
             continue
         m.set_option("forward_kernel", code)
-        np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d %s" % (K, k))
+        for lanes in ((4, 8) if k == "zip" else (0,)):
+            m.set_option("zip_lanes", lanes)
+            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d %s %d" % (K, k, lanes))
 
 
 @pytest.mark.parametrize("K", [3, 5, 7, 9, 11, 13, 20, 40, 65, 100, 128])
@@ -204,9 +206,9 @@ def test_properties_at_scale():
     np.testing.assert_allclose(whole, oracle_batch([obs], pis[:8], Ts[:8], Es[:8]), rtol=RTOL)
 
 
-@pytest.mark.parametrize("K", [3, 5, 10, 20, 40])
+@pytest.mark.parametrize("K", [3, 5, 8, 10, 12, 20, 40])
 def test_zip_kernel_configurations(K):
-    """The compressed kernel under every launch shape: CTAs per point, resident CTAs per SM, dictionary caps
+    """The compressed kernel under every launch shape: resident CTAs per SM (256 / 512 threads), dictionary caps
     (3 = base symbols only, i.e. no compression), on compressible and on incompressible data."""
     import imcoalhmm_b200 as m
     rng = np.random.default_rng(500 + K)
@@ -221,13 +223,31 @@ def test_zip_kernel_configurations(K):
     want = oracle_batch(chunks, pis, Ts, Es)
     s = make_set(chunks)
     m.set_option("forward_kernel", 4)
-    for split, ctas, cap in ((0, 0, 0), (1, 1, 0), (2, 2, 16), (5, 1, 3), (1000, 2, 4), (3, 0, 64)):
-        m.set_option("zip_split", split)
+    for lanes, ctas, cap in ((0, 0, 0), (8, 1, 0), (8, 2, 16), (4, 1, 3), (4, 2, 4), (4, 0, 64), (8, 0, 5), (4, 1, 0)):
+        m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)
         m.set_option("zip_max_entries", cap)
         got = s.forward_batch(pis, Ts, Es)
         assert m.last_forward_kernel() == "zip"
-        np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="K=%d split=%d ctas=%d cap=%d" % (K, split, ctas, cap))
+        np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="K=%d lanes=%d ctas=%d cap=%d" % (K, lanes, ctas, cap))
+
+
+def test_zip_kernel_work_stealing_many_points():
+    """More parameter points than persistent CTAs, and fewer: every (point, chunk) pair is scored exactly once."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(77)
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    chunks = [rng.choice(3, size=int(n), p=[0.95, 0.01, 0.04]).astype(np.uint8) for n in rng.integers(50, 3000, size=45)]
+    want16 = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    reps = 44                                             # 704 points > 296 resident CTAs
+    big = [np.tile(x, (reps,) + (1,) * (x.ndim - 1)) for x in (pis, Ts, Es)]
+    for lanes, ctas in ((8, 1), (8, 2), (4, 1), (4, 2)):
+        m.set_option("zip_lanes", lanes)
+        m.set_option("zip_ctas_per_sm", ctas)
+        got = s.forward_batch(*big)
+        np.testing.assert_allclose(got, np.tile(want16, reps), rtol=RTOL)
+        np.testing.assert_allclose(s.forward_batch(pis[:3], Ts[:3], Es[:3]), want16[:3], rtol=RTOL)
 
 
 @pytest.mark.parametrize("nsym", [1, 2, 4, 9])

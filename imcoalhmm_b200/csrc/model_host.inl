@@ -346,8 +346,8 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
         CUDA_TRY(cudaFuncSetAttribute(model_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain));
         chain_attr = smem_chain;
     }
-    model_chain_kernel<<<N, 128, smem_chain, st>>>(m->dev, (const double*)m->d_pbuf.p, (const double*)m->d_prebuf.p,
-                                                   d_status, d_pi, d_T);
+    model_chain_kernel<<<N, 128, smem_chain, st>>>(m->dev, (const double*)m->d_params.p, (const double*)m->d_pbuf.p,
+                                                   (const double*)m->d_prebuf.p, d_status, d_pi, d_T);
     CUDA_TRY(cudaGetLastError());
     g_launches += 3;
     return IMC_OK;

@@ -51,8 +51,10 @@ struct ModelDev {
 
 // per parameter point, written by model_params_kernel
 struct PointParams {
-    // layout in a double array: [0] t0, [1..5] pre-phase rates, then per interval i: 5 rates + dt  -> 6 doubles
-    static __host__ __device__ int size(int K) { return 6 + 6 * K; }
+    // layout in a double array: [0] t0, [1..5] pre-phase rates, then per interval i: 5 rates + dt  -> 6 doubles,
+    // then K doubles rep[i]: the first interval whose transition matrix interval i shares (see model_params_kernel)
+    static __host__ __device__ int size(int K) { return 6 + 7 * K; }
+    static __host__ __device__ int rep_off(int K) { return 6 + 6 * K; }
 };
 
 __device__ __forceinline__ double trunc_exp_mid(double t1, double t2, double rate) {   // emissions.py:11-25
@@ -89,6 +91,7 @@ __global__ void model_params_kernel(ModelDev m, int N, const double* theta, doub
     status[n] = ok ? 0 : 1;
     if (!ok) {   // keep the downstream kernels finite; the result is overwritten with -inf
         for (int x = 0; x < PointParams::size(K); ++x) pp[x] = 0.0;
+        for (int i = 0; i < K; ++i) pp[PointParams::rep_off(K) + i] = i;
         for (int x = 0; x < K * 3; ++x) E[(size_t)n * K * 3 + x] = 1.0;
         return;
     }
@@ -165,6 +168,24 @@ __global__ void model_params_kernel(ModelDev m, int N, const double* theta, doub
         }
     }
     for (int i = 0; i + 1 < K; ++i) iv[i * 6 + 5] = bp[i + 1] - bp[i];   // duration of interval i (the last is the pseudo interval)
+    // Consecutive intervals with the same state space, the same rates and the same duration have the same transition
+    // matrix (the reference memoises expm on the duration, CTMC.py:39-51; uniform break points give durations that are
+    // equal up to the rounding of t_{i+1} - t_i, so "same" is taken as 1e-13 relative).  Only the first is computed.
+    // An interval that hands over to a different state space stores a projected matrix and stays on its own.
+    double* rep = pp + PointParams::rep_off(K);
+    for (int i = 0; i < K; ++i) {
+        int r = i;
+        if (i > 0 && i + 1 < K) {
+            const int j = (int)rep[i - 1];
+            const bool plain_i = m.interval_space[i + 1] == m.interval_space[i];
+            const bool plain_j = m.interval_space[j + 1] == m.interval_space[j];
+            bool same = plain_i && plain_j && m.interval_space[i] == m.interval_space[j];
+            for (int l = 0; l < 5; ++l) same = same && (iv[i * 6 + l] == iv[j * 6 + l]);
+            same = same && fabs(iv[i * 6 + 5] - iv[j * 6 + 5]) <= 1e-13 * fabs(iv[j * 6 + 5]);
+            if (same) r = j;
+        }
+        rep[i] = r;
+    }
     write_emissions(ebp, er, K, E + (size_t)n * K * 3);
 }
 
@@ -221,6 +242,7 @@ __global__ void __launch_bounds__(256) model_expm_kernel(ModelDev m, const doubl
         if (m.pre_space_n == 0) return;
         sp = SP_ISO; rates = pp + 1; dt = pp[0];
     } else {
+        if ((int)pp[PointParams::rep_off(K) + interval] != interval) return;   // shares an earlier interval's matrix
         sp = m.interval_space[interval]; rates = pp + 6 + interval * 6; dt = rates[5];
     }
     const SpaceDev& S = m.space[sp];
@@ -307,8 +329,8 @@ __global__ void __launch_bounds__(256) model_expm_kernel(ModelDev m, const doubl
 // ------------------------------------------------------------------------------------------------
 // u chain, L-block products, joint matrix J -> pi, T   (transitions.py:204-248).  One CTA per point.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const double* pbuf, const double* prebuf,
-                                                          int* status, double* pi, double* T) {
+__global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const double* params, const double* pbuf,
+                                                          const double* prebuf, int* status, double* pi, double* T) {
     extern __shared__ double sm[];
     const int n_pt = blockIdx.x, K = m.K, tid = threadIdx.x, nt = blockDim.x;
     if (status[n_pt] != 0) {   // invalid point: a harmless HMM; its log-likelihood is replaced by -inf afterwards
@@ -325,6 +347,7 @@ __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const doub
     double* esum = upth + K * MAX_L;         // [K][MAX_L]   sum over E(space(j+1)) of P_j[l][e], l in L(space(j))
     double* red = esum + K * MAX_L;          // [nt]
     const double* P = pbuf + (size_t)n_pt * m.p_stride;
+    const double* rep = params + (size_t)n_pt * PointParams::size(K) + PointParams::rep_off(K);
     for (int x = tid; x < K * K; x += nt) J[x] = 0.0;
     // u_0: row `initial` of upto0
     {
@@ -354,7 +377,7 @@ __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const doub
             for (int l = tid; l < S.nL; l += nt) esum[i * MAX_L + l] = 1.0;
             break;
         }
-        const double* Pi = P + m.p_off[i];
+        const double* Pi = P + m.p_off[(int)rep[i]];
         const int n1 = S.n, n2 = Sn.n;
         // esum_i[l] = sum_{e in E(next)} P_i[L[l]][e]
         for (int l = tid; l < S.nL; l += nt) {
@@ -417,7 +440,7 @@ __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const doub
             if (lane == 0) { J[i * K + j] = t; J[j * K + i] = t; }
             if (j + 1 < K) {
                 const SpaceDev& Sn = m.space[m.interval_space[j + 1]];
-                const double* Pj = P + m.p_off[j];
+                const double* Pj = P + m.p_off[(int)rep[j]];
                 double nw = 0.0;
                 for (int l = 0; l < S.nL; ++l) {
                     const double wl = __shfl_sync(0xffffffffu, w, l);

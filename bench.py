@@ -176,7 +176,8 @@ def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
     zipped = [F.zip_preprocess(c.astype(np.int32), 3) for c in chunks]
     t_prep = time.perf_counter() - t0
     t0 = time.perf_counter()
-    F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every core of the affinity mask explicitly
+    F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped, nthreads=ncores)
     t_cal = time.perf_counter() - t0
     per_step = budget_s / max(1, steps + warmup)
     scale = max(1, min(wl["points"] // n_p, int(per_step / max(t_cal, 1e-4))))
@@ -184,7 +185,7 @@ def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        _, used = F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped)
+        _, used = F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip", zipped=zipped, nthreads=ncores)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -242,10 +243,21 @@ def main():
     import imcoalhmm_b200 as m
     assert args.warmup >= 3 or args.steps <= 2, "timing rules: at least 3 warm-up steps"
     dist = None
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
+        # NCCL announces its version on stdout when the first communicator is created: keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local_rank)))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     m._lib.check(m._lib.load().imc_init(local_rank))
     dev = torch.device("cuda", local_rank)
 

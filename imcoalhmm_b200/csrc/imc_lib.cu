@@ -57,6 +57,7 @@ struct Context {
     long long opt_fold_emission = 0;   // measured slower than the emission-row multiply on B200 (profiles/r01_pair_micro2.txt)
     long long opt_zip_ctas_per_sm = 0; // 1 or 2 resident CTAs per SM for the zip kernel (0 = auto)
     long long opt_zip_lanes = 0;       // lanes per chain in the zip kernel: 8, 4 or 0 = auto
+    long long opt_zip_segment_tokens = 0;  // tokens per segment in segmented mode: 0 = auto, -1 = never, > 0 = forced
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
 };
 static Context g_ctx;
@@ -111,10 +112,18 @@ struct DeviceBuf {
 };
 
 // device copy of the token streams derived for one dictionary size M (see zip_device)
+struct ZipSplit {                 // segmented variant of a ZipDevice's chunk list (same token buffer)
+    int K = 0, seglen = 0, nchains = 0, nsegchunks = 0;
+    DeviceBuf chunks, segs;
+};
+
 struct ZipDevice {
     int M = 0, nlevels = 0;
     long long total_tokens = 0;
+    int max_ntok = 0;
+    std::vector<ZipChunk> host_chunks;        // sorted by ntok, descending
     DeviceBuf tokens, chunks, pairs, levels;
+    std::vector<ZipSplit*> splits;
 };
 
 struct imc_seqset {
@@ -133,7 +142,7 @@ struct imc_seqset {
     std::vector<int> stream_of_chunk;             // chunk index as given to imc_seqset_create -> stream (-1: empty chunk)
     // device side (lazy)
     bool uploaded = false;
-    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext;
+    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext, d_vec;
     std::vector<ZipDevice*> zip_dev;      // one per dictionary size in use
 };
 
@@ -345,9 +354,14 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
     if (mine) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
         set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release(); set->d_pnext.release();
+        set->d_vec.release();
     }
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
+        for (ZipSplit* sp : z->splits) {
+            if (mine) { sp->chunks.release(); sp->segs.release(); }
+            delete sp;
+        }
         delete z;
     }
     delete set;
@@ -480,6 +494,8 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     z->M = M;
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
+    z->max_ntok = ns ? chunks[0].ntok : 0;
+    z->host_chunks = chunks;
     int rc;
     if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
         (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
@@ -499,6 +515,50 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     }
     set->zip_dev.push_back(z);
     *out = z;
+    return IMC_OK;
+}
+
+// chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen)
+static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
+    for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
+    std::vector<ZipChunk> chains;
+    std::vector<ZipSegChunk> segs;
+    for (const ZipChunk& ch : z->host_chunks) {
+        const int nseg = std::max(1, (ch.ntok + seglen - 1) / seglen);
+        ZipSegChunk sc;
+        sc.first_chain = (int)chains.size(); sc.nseg = nseg; sc.out_index = ch.out_index; sc.pad = 0;
+        segs.push_back(sc);
+        for (int sg = 0; sg < nseg; ++sg) {
+            ZipChunk c = ch;
+            c.tok_off = ch.tok_off + (long long)sg * seglen;
+            c.ntok = std::min(seglen, ch.ntok - sg * seglen);
+            if (c.ntok < 0) c.ntok = 0;
+            for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
+                c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
+                c.out_index = (int)chains.size();
+                chains.push_back(c);
+            }
+        }
+    }
+    // the kernel takes chunks in list order, longest first: full segments first, tails last (stable: out_index keeps identity)
+    std::vector<ZipChunk> sorted = chains;
+    std::stable_sort(sorted.begin(), sorted.end(), [](const ZipChunk& x, const ZipChunk& y) { return x.ntok > y.ntok; });
+    ZipSplit* sp = new (std::nothrow) ZipSplit;
+    if (!sp) return fail(IMC_ERR_NOMEM, "out of memory");
+    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size(); sp->nsegchunks = (int)segs.size();
+    int rc;
+    if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) || (rc = sp->segs.reserve(sizeof(ZipSegChunk) * segs.size()))) {
+        sp->chunks.release(); sp->segs.release(); delete sp;
+        return rc;
+    }
+    cudaError_t e = cudaMemcpy(sp->chunks.p, sorted.data(), sizeof(ZipChunk) * sorted.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sp->segs.p, segs.data(), sizeof(ZipSegChunk) * segs.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sp->chunks.release(); sp->segs.release(); delete sp;
+        return fail(IMC_ERR_CUDA, "uploading segment descriptors failed: %s", cudaGetErrorString(e));
+    }
+    z->splits.push_back(sp);
+    *out = sp;
     return IMC_OK;
 }
 
@@ -697,9 +757,44 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         za.pi = d_pi; za.T = d_T; za.E = d_E;
         za.chain_out = (double*)set->d_chain.p;
         za.out_stride = ns;
-        g_last_kernel = "zip";
+        za.vec_out = nullptr;
+        za.vec_stride = 0;
+        // Chain-scarce call (few chunks x few points)?  Cut the chunks into segments: K times the arithmetic on the
+        // segments after the first, but enough chains to fill the machine (zip_kernels.cuh, "segmented mode").
+        ZipSplit* split = nullptr;
+        {
+            const long long slots = (long long)(g_ctx.sm_count > 0 ? g_ctx.sm_count : 148) * plan.ctas_per_sm * (plan.threads / plan.lanes);
+            long long seglen = g_ctx.opt_zip_segment_tokens;
+            if (seglen == 0 && (long long)N * ns * 4 <= slots && z->max_ntok >= 1024 && K <= 64) {
+                seglen = (long long)N * z->total_tokens * K / (2 * slots);
+                seglen = std::max<long long>(256, seglen);
+            }
+            if (seglen > 0 && K <= 64) {
+                seglen = (seglen + 15) / 16 * 16;
+                if (seglen < z->max_ntok) {
+                    if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
+                    const size_t vec_bytes = sizeof(double) * (size_t)N * split->nchains * (K + 1);
+                    if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
+                    else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
+                }
+            }
+        }
+        if (split) {
+            za.chunks = (const ZipChunk*)split->chunks.p;
+            za.nchunks = split->nchains;
+            za.vec_out = (double*)set->d_vec.p;
+            za.vec_stride = K + 1;
+        }
+        g_last_kernel = split ? "zip-segmented" : "zip";
         if ((rc = launch_zip(za, plan, st))) return rc;
         CUDA_TRY(cudaGetLastError());
+        if (split) {
+            zip_combine_kernel<<<dim3(split->nsegchunks, N), 64, 0, st>>>(za.vec_out, za.vec_stride, split->nchains,
+                                                                        (const ZipSegChunk*)split->segs.p, split->nsegchunks, K,
+                                                                        za.chain_out, za.out_stride);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 1;
+        }
         reduce_chains_kernel<<<N, 256, 0, st>>>(za.chain_out, ns, d_out);
         CUDA_TRY(cudaGetLastError());
         g_launches += 2;
@@ -848,6 +943,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     }
     if (!strcmp(key, "fold_emission")) { g_ctx.opt_fold_emission = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "zip_ctas_per_sm")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_ctas_per_sm must be 0, 1 or 2"); g_ctx.opt_zip_ctas_per_sm = value; return IMC_OK; }
+    if (!strcmp(key, "zip_segment_tokens")) { if (value < -1) return fail(IMC_ERR_INVALID, "zip_segment_tokens must be >= -1"); g_ctx.opt_zip_segment_tokens = value; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4 or 8"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
@@ -858,6 +954,7 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "dmma_mtiles")) { *value_out = g_ctx.opt_dmma_mtiles; return IMC_OK; }
     if (!strcmp(key, "fold_emission")) { *value_out = g_ctx.opt_fold_emission; return IMC_OK; }
     if (!strcmp(key, "zip_ctas_per_sm")) { *value_out = g_ctx.opt_zip_ctas_per_sm; return IMC_OK; }
+    if (!strcmp(key, "zip_segment_tokens")) { *value_out = g_ctx.opt_zip_segment_tokens; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { *value_out = g_ctx.opt_zip_lanes; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);

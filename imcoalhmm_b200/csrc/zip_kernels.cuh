@@ -22,7 +22,8 @@ namespace imc {
 struct ZipChunk {
     long long tok_off;   // byte offset of the chunk's first token (16-byte aligned, 16 readable bytes past the end)
     int ntok;            // tokens (the chunk's symbols 1..L-1 after compression)
-    int first_sym;       // symbol at position 0
+    int first_sym;       // >= 0: symbol at position 0 (alpha_0 = pi o E[:,first_sym]);  < 0: the chain starts from the
+                         // unit vector e_c, c = -1 - first_sym (column c of a segment's transfer matrix, see zip_combine_kernel)
     int out_index;       // column of chain_out this chunk writes
     int pad;
 };
@@ -40,8 +41,21 @@ struct ZipArgs {
     const double* pi;            // [N][K]
     const double* T;             // [N][K][K]
     const double* E;             // [N][K][S]
-    double* chain_out;           // [N][out_stride]
+    double* chain_out;           // [N][out_stride]  log-likelihood per chain (vec_out == NULL)
     int out_stride;
+    double* vec_out;             // segmented mode: [N][nchunks][vec_stride] final vector (K doubles, unnormalised) + exponent
+    int vec_stride;
+};
+
+// Segmented mode (chain-scarce calls: few chunks x few points).  A long chunk is cut into segments of `seglen` tokens.
+// Segment 0 runs as usual from pi; segment s > 0 is run K times from the unit vectors e_0..e_{K-1}, which yields the
+// columns of its transfer matrix P_s = C_tok[last] ... C_tok[first] (K times the arithmetic, but K * #segments times
+// the parallelism).  zip_combine_kernel then folds alpha <- P_s alpha over the segments of each chunk.
+struct ZipSegChunk {
+    int first_chain;     // index (in vec_out) of the segment-0 chain; segment s >= 1, column c is first_chain + 1 + (s-1)*K + c
+    int nseg;
+    int out_index;       // column of chain_out
+    int pad;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -318,7 +332,8 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
         const int st = C::state_of(L, k);
-        al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
+        if (ch.first_sym >= 0) al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
+        else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
     }
     long long scale = 0;
     bool dead = false, isnan = false;
@@ -362,8 +377,21 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
     double sum = 0.0;
 #pragma unroll
     for (int k = 0; k < KP; ++k) sum += al[k];
+    const bool bad = isnan || sum != sum;
+    if (a.vec_out) {       // segmented mode: hand the vector on (a dead chain hands on zeros; a unit-vector chain may
+        if (have && L.writer()) {                 // legitimately end at zero, which is not an error by itself)
+            double* out = a.vec_out + ((size_t)n * a.nchunks + ch.out_index) * a.vec_stride;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int st = C::state_of(L, k);
+                if (st < K) out[st] = bad ? __longlong_as_double(0x7ff8000000000000LL) : (dead ? 0.0 : al[k]);
+            }
+            out[K] = (double)scale;
+        }
+        return;
+    }
     double result;
-    if (dead || !(sum > 0.0)) result = (isnan || sum != sum) ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
+    if (dead || !(sum > 0.0)) result = bad ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
     else result = log(sum) + (double)scale * LN2;
     if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
 }
@@ -427,6 +455,65 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
             if (unit >= nunits) break;
             zip_run_unit<C>(a, n, unit, dict, sE, spi, dexp, L);
         }
+    }
+}
+
+// alpha <- P_s alpha over the segments of one chunk; one CTA of 64 threads per (parameter point, chunk), K <= 64.
+__global__ void __launch_bounds__(64) zip_combine_kernel(const double* vec, int vec_stride, int nchains, const ZipSegChunk* segs,
+                                                         int nsegchunks, int K, double* chain_out, int out_stride) {
+    __shared__ double w[64];
+    __shared__ double red[2];
+    __shared__ int s_e[2];
+    const int n = blockIdx.y, j = threadIdx.x;
+    const ZipSegChunk sc = segs[blockIdx.x];
+    const double* base = vec + (size_t)n * nchains * vec_stride;
+    const double* v0 = base + (size_t)sc.first_chain * vec_stride;
+    double alpha = j < K ? v0[j] : 0.0;
+    double scale = v0[K];
+    for (int s = 1; s < sc.nseg; ++s) {
+        const double* cols = base + (size_t)(sc.first_chain + 1 + (s - 1) * K) * vec_stride;
+        // column c carries 2^e_c; bring all columns to the largest exponent among those that matter
+        const double ec = j < K ? cols[(size_t)j * vec_stride + K] : 0.0;
+        bool matters = j < K && alpha != 0.0;
+        if (matters) {                                 // an all-zero column (impossible continuation) carries no scale
+            bool any = false;
+            for (int r = 0; r < K; ++r) any = any || cols[(size_t)j * vec_stride + r] != 0.0;
+            matters = any;
+        }
+        int e = matters ? (int)ec : -0x40000000;
+        for (int m = 16; m >= 1; m >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, m));
+        if ((j & 31) == 0) s_e[j >> 5] = e;
+        __syncthreads();
+        const int emax = max(s_e[0], s_e[1]);
+        const int d = (int)ec - emax;                  // <= 0 where alpha != 0
+        w[j] = matters ? (d < -1000 ? 0.0 : alpha * pow2_neg(-d)) : 0.0;
+        __syncthreads();
+        double acc = 0.0;
+        if (j < K)
+            for (int c = 0; c < K; ++c) acc = fma(w[c], cols[(size_t)c * vec_stride + j], acc);
+        double sum = acc;
+        for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
+        __syncthreads();                               // w and s_e are free again
+        if ((j & 31) == 0) red[j >> 5] = sum;
+        __syncthreads();
+        sum = red[0] + red[1];
+        int en = 0;
+        if (sum > 0.0 && sum < 1.7e308) { en = exponent_of(sum); acc *= pow2_neg(en); }
+        alpha = acc;
+        scale += (emax > -0x40000000 ? (double)emax : 0.0) + (double)en;
+        __syncthreads();
+    }
+    double sum = alpha;
+    for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
+    if ((j & 31) == 0) red[j >> 5] = sum;
+    __syncthreads();
+    if (j == 0) {
+        sum = red[0] + red[1];
+        double r;
+        if (sum != sum) r = sum;
+        else if (!(sum > 0.0)) r = -INFINITY;
+        else r = log(sum) + scale * LN2;
+        chain_out[(size_t)n * out_stride + sc.out_index] = r;
     }
 }
 

@@ -28,6 +28,10 @@ class Likelihood(object):
     def __call__(self, *parameters):
         if not self.model.valid_parameters(*parameters):
             return -float("inf")
+        if self.forwarder_set is not None and len(parameters) == 1 and hasattr(self.model, "batched_log_likelihood"):
+            # fused on the device: theta -> (pi, T, E) -> logL without the host round trip of the matrices
+            return float(self.model.batched_log_likelihood(np.asarray(parameters[0], dtype=np.float64)[None],
+                                                           self.forwarder_set)[0])
         pi, T, E = self.model.build_hidden_markov_model(*parameters)
         if self.forwarder_set is not None:
             return self.forwarder_set.forward(pi, T, E)

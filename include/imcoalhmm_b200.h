@@ -137,6 +137,9 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  * key "zip_ctas_per_sm": 1 = one persistent CTA per SM with all of shared memory for the dictionary, 2 = two CTAs of
  *                       256 threads with half each (K <= 24 only); 0 = auto.
  * key "zip_lanes":      lanes that share one chain's mat-vec in the zip kernel: 8, 4 (K >= 8) or 0 = auto.
+ * key "zip_segment_tokens": segmented mode of the zip kernel for chain-scarce calls (few chunks x few points): chunks
+ *                       are cut into segments of this many tokens whose K x K transfer matrices are computed
+ *                       column by column in parallel and folded afterwards.  0 = auto, -1 = never, > 0 = forced length.
  * key "zip_max_entries": cap on the dictionary ids used (0 = as many as fit).
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
@@ -148,7 +151,8 @@ int imc_get_option(const char* key, int64_t* value_out);
 int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t imc_kernel_launches(void);
-/* name of the forward kernel chosen by the last forward call on this thread ("generic", "pair", "dmma") */
+/* name of the forward kernel chosen by the last forward call on this thread
+ * ("generic", "pair", "dmma", "zip", "zip-segmented") */
 const char* imc_last_forward_kernel(void);
 
 #ifdef __cplusplus

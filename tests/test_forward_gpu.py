@@ -24,6 +24,7 @@ def _reset_options():
     m.set_option("zip_ctas_per_sm", 0)
     m.set_option("zip_max_entries", 0)
     m.set_option("zip_lanes", 0)
+    m.set_option("zip_segment_tokens", 0)
 
 
 def oracle_batch(chunks, pis, Ts, Es):
@@ -44,8 +45,11 @@ def test_example_alignment_reference_models():
     f = m.Forwarder.from_symbols(obs, 3)
     _, pi, T, E = golden_model("isolation_k10")
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3729.5586472699, rel=1e-11)
-    assert m.last_forward_kernel() == "zip"
+    assert m.last_forward_kernel() == "zip-segmented"      # one chunk x one point: chain-scarce
     _, pi, T, E = golden_model("im_k10_10")
+    assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
+    assert m.last_forward_kernel() == "zip-segmented"
+    m.set_option("zip_segment_tokens", -1)
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
     assert m.last_forward_kernel() == "zip"
     for code, name in ((2, "pair"), (3, "dmma")):
@@ -78,7 +82,7 @@ def test_batch_parity_on_reference_models(model, kernels):
     for k in kernels:
         m.set_option("forward_kernel", KERNELS[k])
         got = s.forward_batch(pis, Ts, Es)
-        assert m.last_forward_kernel() == k
+        assert m.last_forward_kernel().split("-")[0] == k     # "zip-segmented" when the call is chain-scarce
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="%s / %s" % (model, k))
         one = s.forward(pis[-1], Ts[-1], Es[-1])
         assert one == pytest.approx(want[-1], rel=RTOL)
@@ -228,7 +232,7 @@ def test_zip_kernel_configurations(K):
         m.set_option("zip_ctas_per_sm", ctas)
         m.set_option("zip_max_entries", cap)
         got = s.forward_batch(pis, Ts, Es)
-        assert m.last_forward_kernel() == "zip"
+        assert m.last_forward_kernel() .startswith("zip")
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="K=%d lanes=%d ctas=%d cap=%d" % (K, lanes, ctas, cap))
 
 
@@ -250,6 +254,45 @@ def test_zip_kernel_work_stealing_many_points():
         np.testing.assert_allclose(s.forward_batch(pis[:3], Ts[:3], Es[:3]), want16[:3], rtol=RTOL)
 
 
+@pytest.mark.parametrize("model", ["isolation_k10", "im_k10_10", "isolation_k4"])
+def test_zip_segmented_mode(model):
+    """Chain-scarce calls cut chunks into segments whose transfer matrices are built column by column and folded
+    afterwards (the associative form of the forward recursion): same logL as the sequential pass."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(5)
+    _, pis, Ts, Es = golden_model(model)
+    obs = synthetic_sequence(rng, pis[0], Ts[0], Es[0], 300_000)
+    chunks = [obs, obs[:70_001], obs[100_000:100_700], obs[:1], np.zeros(0, dtype=np.uint8)]
+    want = oracle_batch(chunks, pis[:3], Ts[:3], Es[:3])
+    s = make_set(chunks)
+    m.set_option("zip_segment_tokens", -1)
+    base = s.forward_batch(pis[:3], Ts[:3], Es[:3])
+    assert m.last_forward_kernel() == "zip"
+    np.testing.assert_allclose(base, want, rtol=RTOL)
+    for lanes in (8, 4):
+        m.set_option("zip_lanes", lanes)
+        for seg in (0, 16, 48, 256, 1000):
+            m.set_option("zip_segment_tokens", seg)
+            got = s.forward_batch(pis[:3], Ts[:3], Es[:3])
+            assert m.last_forward_kernel() == "zip-segmented", (lanes, seg)
+            np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="lanes=%d seg=%d" % (lanes, seg))
+            assert s.forward(pis[1], Ts[1], Es[1]) == pytest.approx(want[1], rel=RTOL)
+    # many points: auto mode goes back to the plain zip kernel
+    m.set_option("zip_segment_tokens", 0)
+    reps = -(-6000 // len(pis))                           # 6000 points x 4 chunks: far more chains than chain slots
+    big = [np.tile(x, (reps,) + (1,) * (x.ndim - 1)) for x in (pis, Ts, Es)]
+    s.forward_batch(*big)
+    assert m.last_forward_kernel() == "zip"
+    # an impossible observation inside a later segment still gives -inf
+    E0 = Es[0].copy()
+    E0[:, 1] = 0.0
+    bad = obs.copy()
+    bad[250_000] = 1
+    m.set_option("zip_segment_tokens", 64)
+    assert make_set([bad]).forward(pis[0], Ts[0], E0) == -np.inf
+    assert np.isfinite(make_set([np.where(obs == 1, 0, obs)]).forward(pis[0], Ts[0], E0))
+
+
 @pytest.mark.parametrize("nsym", [1, 2, 4, 9])
 def test_zip_kernel_other_alphabets(nsym):
     """NSYM other than 3 (the ILS scripts use alphabetSize=9, scripts/prepare-alignments.py:201) runs on the zip kernel."""
@@ -260,7 +303,7 @@ def test_zip_kernel_other_alphabets(nsym):
     chunks = [rng.integers(0, nsym, size=n).astype(np.int32) for n in (1, 50, 1000, 4097)]
     want = oracle_batch(chunks, pi[None], T[None], E[None])[0]
     got = make_set(chunks, nsym).forward(pi, T, E)
-    assert m.last_forward_kernel() == "zip"
+    assert m.last_forward_kernel() .startswith("zip")
     assert got == pytest.approx(want, rel=RTOL)
 
 

@@ -6,6 +6,7 @@ Public surface (mirrors /root/reference/src/IMCoalHMM for this path only):
     ForwarderSet(forwarders).forward / .forward_batch                     likelihood.py:33, batched
     Likelihood(model, forwarders)(theta) / .batched(thetas)               likelihood.py:8-33
     ziphmm.preprocess_raw_observations / ziphmm.zip_forward               hmm.py:16,20-21
+    mcmc.BatchedMCMC / mcmc.MC3 / mcmc.ParticleSwarm                      mcmc.py, particle_swarm.py, one batched call per step
 
 Importing the package needs the in-tree shared library (python imcoalhmm_b200/build.py); there is no
 CPU fallback.  CUDA itself is initialised lazily by the first forward call.
@@ -20,8 +21,9 @@ from .likelihood import Likelihood  # noqa: E402
 from .models import (Model, IsolationModel, IsolationMigrationModel, VariableCoalescenceRateIsolationModel,  # noqa: E402
                      VariableCoalAndMigrationRateModel, IsolationMigrationEpochsModel)
 from . import ziphmm  # noqa: E402
+from . import mcmc  # noqa: E402
 
-__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm", "Model", "IsolationModel",
+__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm", "mcmc", "Model", "IsolationModel",
            "IsolationMigrationModel", "VariableCoalescenceRateIsolationModel", "VariableCoalAndMigrationRateModel",
            "IsolationMigrationEpochsModel",
            "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak"]

@@ -33,6 +33,10 @@ _SIGNATURES = {
     "imc_seq_create": (ctypes.c_int, [c_i32p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "imc_seq_create_u8": (ctypes.c_int, [c_u8p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "imc_seq_from_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seq_from_pair": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(c_vp)]),
+    "imc_seq_from_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "imc_seq_save": (ctypes.c_int, [c_vp, ctypes.c_char_p]),
+    "imc_seq_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "imc_seq_length": (ctypes.c_int, [c_vp, c_i64p]),
     "imc_seq_nsym": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "imc_seq_symbol_counts": (ctypes.c_int, [c_vp, c_i64p]),

@@ -195,6 +195,63 @@ class Forwarder(object):
         self._finish(_Seq(h), NSYM)
         return self
 
+    # -- ingest (reference: scripts/prepare-alignments.py:77-111, pairwise case) --------------------------------
+    @classmethod
+    def from_pair(cls, sequence1, sequence2):
+        """Two aligned sequences (str / bytes) -> symbols 0 equal, 1 different, 2 either base not in ACGT."""
+        s1 = sequence1.encode("ascii", "replace") if isinstance(sequence1, str) else bytes(sequence1)
+        s2 = sequence2.encode("ascii", "replace") if isinstance(sequence2, str) else bytes(sequence2)
+        if len(s1) != len(s2):
+            raise ValueError("aligned sequences differ in length (%d vs %d)" % (len(s1), len(s2)))
+        self = cls.__new__(cls)
+        h = _lib.c_vp()
+        check(_lib.load().imc_seq_from_pair(s1, s2, len(s1), ctypes.byref(h)))
+        self._finish(_Seq(h), 3)
+        return self
+
+    @classmethod
+    def from_fasta(cls, path, names=None):
+        """The two named records of a FASTA alignment (or its only two) as one pairwise Forwarder."""
+        self = cls.__new__(cls)
+        h = _lib.c_vp()
+        n1, n2 = (None, None) if names is None else (str(names[0]).encode(), str(names[1]).encode())
+        lib = _lib.load()
+        rc = lib.imc_seq_from_fasta(os.fsencode(path), n1, n2, ctypes.byref(h))
+        if rc == -5 and not os.path.exists(path):
+            raise IOError(lib.imc_last_error().decode())
+        if rc in (-5, -1):
+            raise ValueError(lib.imc_last_error().decode())
+        check(rc)
+        self._finish(_Seq(h), 3)
+        return self
+
+    def save(self, path):
+        """Binary container (2 bits per symbol for NSYM <= 4); read it back with Forwarder.load."""
+        check(_lib.load().imc_seq_save(self._seq.handle, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path):
+        self = cls.__new__(cls)
+        h = _lib.c_vp()
+        lib = _lib.load()
+        rc = lib.imc_seq_load(os.fsencode(path), ctypes.byref(h))
+        if rc == -5:
+            raise IOError(lib.imc_last_error().decode())
+        check(rc)
+        n = ctypes.c_int()
+        check(lib.imc_seq_nsym(h, ctypes.byref(n)))
+        self._finish(_Seq(h), n.value)
+        return self
+
+    def write_text(self, path):
+        """The reference's text format (prepare-alignments.py:93-105: integers separated by single blanks)."""
+        with open(path, "w", 1 << 16) as f:
+            sym = self._seq.symbols()
+            for a in range(0, sym.size, 1 << 20):
+                f.write(" ".join(map(str, sym[a:a + (1 << 20)].tolist())))
+                if a + (1 << 20) < sym.size:
+                    f.write(" ")
+
     # -- legacy pyZipHMM constructors -------------------------------------------------------------
     @classmethod
     def fromSequence(cls, seqFilename, alphabetSize, minNoEvals=500):
@@ -228,20 +285,24 @@ class Forwarder(object):
             nsym = int(obs.max(initial=0)) + 1
         return cls.from_symbols(obs.astype(np.int32), nsym)
 
-    # -- reference attributes (hmm.py:15-16).  No pair compression is applied on the host: the identity
-    # re-encoding is exact, and ziphmm.zip_forward accepts it. ---------------------------------------
+    # -- reference attributes (hmm.py:15-16): the zipHMM-style re-encoding this library computed on the host
+    # (position 0 is kept as a raw symbol, the rest are dictionary ids; sym2pair[i] = parts of id NSYM + i). ----
     @property
     def new_obs(self):
         from .ziphmm import _tag
-        return _tag(self._seq.symbols().astype(np.int32), self)
+        n = self._seq.length
+        if n == 0:
+            return _tag(np.zeros(0, dtype=np.int32), self)
+        first = self._seq.symbols()[:1].astype(np.int32)
+        return _tag(np.concatenate([first, self._as_set().zip_tokens(0).astype(np.int32)]), self)
 
     @property
     def sym2pair(self):
-        return np.zeros((0, 2), dtype=np.int32)
+        return self._as_set().zip_pairs().astype(np.int32)
 
     @property
     def new_nsyms(self):
-        return self.NSYM
+        return self._as_set().zip_info()["ids_available"]
 
     def __len__(self):
         return self._seq.length

@@ -4,9 +4,10 @@ The reference imports `ziphmm` (hmm.py:7) and uses exactly two functions (hmm.py
     preprocess_raw_observations(obs, nsym) -> (new_obs, sym2pair, new_nsyms)
     zip_forward(pi, T, E, sym2pair, new_obs, nsym, new_nsyms) -> float
 Putting this file's directory-level alias on sys.path as `ziphmm` routes both to
-the B200 kernels.  zipHMM's pair compression is a CPU-side optimisation; any exact re-encoding gives
-the same likelihood, so preprocessing here is the identity re-encoding (new_nsyms == nsym, empty
-sym2pair) with the device-resident sequence riding along on the returned array.
+the B200 kernels.  preprocess_raw_observations returns this library's own pair compression (csrc/tokenizer.inl:
+greedy most-frequent-pair merges, at most 256 ids); any exact re-encoding gives the same likelihood, so the merges
+need not be mini-ziphmm's.  The Forwarder that owns the device-resident token streams rides along on the returned
+array; zip_forward also accepts encodings produced elsewhere (they are expanded and re-encoded).
 """
 import numpy as np
 
@@ -26,7 +27,7 @@ def preprocess_raw_observations(obs, nsym):
     from .hmm import Forwarder
     obs = np.ascontiguousarray(obs, dtype=np.int32)
     fwd = Forwarder.from_symbols(obs, nsym)
-    return _tag(obs, fwd), np.zeros((0, 2), dtype=np.int32), int(nsym)
+    return fwd.new_obs, fwd.sym2pair, fwd.new_nsyms
 
 
 def _expand(sym2pair, new_obs, nsym, new_nsyms):

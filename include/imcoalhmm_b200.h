@@ -51,6 +51,14 @@ int imc_seq_create(const int32_t* obs, int64_t L, int nsym, imc_seq** out);
 int imc_seq_create_u8(const uint8_t* obs, int64_t L, int nsym, imc_seq** out);
 /* Text file of whitespace-separated integers (hmm.py:13-14; written by scripts/prepare-alignments.py:93-105). */
 int imc_seq_from_file(const char* path, int nsym, imc_seq** out);
+/* Ingest.  Two aligned sequences -> pairwise symbols by the rule of scripts/prepare-alignments.py:99-111:
+ * upper-case; 2 if either base is not one of ACGT, 0 if equal, 1 otherwise (NSYM = 3).  The FASTA reader takes the two
+ * named records (record name = header text up to the first blank), or the only two when both names are NULL. */
+int imc_seq_from_pair(const char* seq1, const char* seq2, int64_t L, imc_seq** out);
+int imc_seq_from_fasta(const char* path, const char* name1, const char* name2, imc_seq** out);
+/* Binary container for a symbol sequence (2 bits per symbol for NSYM <= 4): 16x smaller than the text format. */
+int imc_seq_save(const imc_seq* seq, const char* path);
+int imc_seq_load(const char* path, imc_seq** out);
 int imc_seq_length(const imc_seq* seq, int64_t* L_out);
 int imc_seq_nsym(const imc_seq* seq, int* nsym_out);
 /* counts[nsym] <- number of occurrences of each symbol */

@@ -1,0 +1,67 @@
+"""Batched samplers / swarm (imcoalhmm_b200/mcmc.py; reference mcmc.py:59-196, particle_swarm.py:102-214) on a toy
+likelihood -- host logic only, no GPU."""
+import numpy as np
+
+from imcoalhmm_b200.mcmc import BatchedMCMC, ExpLogNormPrior, LogNormPrior, MC3, ParticleSwarm
+
+
+class ToyLikelihood(object):
+    """log N(log theta; mu, 0.05) summed over parameters, with the scalar and the batched face of Likelihood."""
+
+    def __init__(self, mu):
+        self.mu, self.calls, self.rows = np.asarray(mu, dtype=np.float64), 0, 0
+
+    def __call__(self, theta):
+        return float(self.batched(np.asarray(theta)[None])[0])
+
+    def batched(self, thetas):
+        self.calls += 1
+        self.rows += len(thetas)
+        return -0.5 * (((np.log(thetas) - self.mu) / 0.05) ** 2).sum(axis=1)
+
+
+def test_batched_mcmc_one_likelihood_call_per_step_and_converges():
+    rng = np.random.default_rng(1)
+    lik = ToyLikelihood([np.log(2.0), np.log(0.5)])
+    priors = [LogNormPrior(0.0), ExpLogNormPrior(1.0)]
+    chains = BatchedMCMC(priors, lik, thinning=10, no_chains=64, rng=rng)
+    assert lik.calls == 1 and lik.rows == 64
+    for _ in range(40):
+        theta, prior, like, post = chains.sample()
+    assert lik.calls == 1 + 400 and lik.rows == 64 * 401
+    assert theta.shape == (64, 2) and np.allclose(post, prior + like)
+    assert abs(np.log(theta[:, 0]).mean() - np.log(2.0)) < 0.05
+    assert abs(np.log(theta[:, 1]).mean() - np.log(0.5)) < 0.05
+    # acceptance rule: a proposal with -inf posterior is never taken (mcmc.py:87-92)
+    chains._loglik = lambda th: np.full(len(th), -np.inf)
+    before = chains.current_theta.copy()
+    assert not chains.step().any() and np.array_equal(before, chains.current_theta)
+
+
+def test_log_prior_matches_reference_rule():
+    chains = BatchedMCMC([LogNormPrior(0.0), ExpLogNormPrior(2.0)], ToyLikelihood([0.0, 0.0]), 1, 3, rng=np.random.default_rng(0))
+    th = np.array([[1.0, 2.0], [0.5, 0.1], [3.0, 4.0]])
+    want = [np.log(LogNormPrior(0.0).pdf(a)) + np.log(ExpLogNormPrior(2.0).pdf(b)) for a, b in th]
+    assert np.allclose(chains.log_prior(th), want)
+
+
+def test_mc3_returns_cold_chain_and_keeps_a_permutation():
+    rng = np.random.default_rng(2)
+    lik = ToyLikelihood([np.log(1.5)])
+    mc3 = MC3([LogNormPrior(0.0)], lik, no_chains=4, thinning=20, switching=5, temperature_scale=2.0, rng=rng)
+    assert [mc3.chain_temperature(k) for k in range(4)] == [1.0, 2.0, 4.0, 6.0]
+    for _ in range(30):
+        theta, prior, like, post = mc3.sample()
+    assert sorted(mc3.order.tolist()) == [0, 1, 2, 3]
+    assert theta.shape == (1,) and abs(np.log(theta[0]) - np.log(1.5)) < 0.3
+    assert np.isclose(post, prior + like)
+    mc3.terminate()
+
+
+def test_particle_swarm_finds_the_maximum_with_one_call_per_iteration():
+    rng = np.random.default_rng(3)
+    lik = ToyLikelihood([np.log(0.3), np.log(0.7)])
+    pso = ParticleSwarm(particle_count=40, max_iterations=120, rng=rng)
+    pos, fit, it = pso.maximise(lik, 2, transform=lambda p: np.clip(p, 1e-6, None))
+    assert it == 120 and lik.calls == 121
+    assert np.allclose(pos, [0.3, 0.7], atol=0.02) and fit > -1.0

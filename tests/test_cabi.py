@@ -31,9 +31,13 @@ def test_host_side_sequence_handling_without_gpu(tmp_path):
     p = tmp_path / "a.txt"
     p.write_text("0 0 1 2\n0\t1  2 0")          # any whitespace (hmm.py:13-14)
     f = m.Forwarder(str(p), 3)
-    assert len(f) == 8 and f.NSYM == 3 and f.new_nsyms == 3
+    assert len(f) == 8 and f.NSYM == 3 and f.new_nsyms == 3      # too short for any pair to pay off
     assert f.new_obs.tolist() == [0, 0, 1, 2, 0, 1, 2, 0] and f.new_obs.dtype == np.int32
     assert f.sym2pair.shape == (0, 2)
+    g = m.Forwarder.from_symbols(np.tile(np.array([0, 0, 0, 1], dtype=np.int32), 200), 3)
+    assert g.new_nsyms > 3 and g.sym2pair.shape == (g.new_nsyms - 3, 2) and len(g.new_obs) < 200
+    from imcoalhmm_b200 import ziphmm
+    assert ziphmm._expand(g.sym2pair, g.new_obs, 3, g.new_nsyms).tolist() == [0, 0, 0, 1] * 200
     with pytest.raises(IOError):
         m.Forwarder(str(tmp_path / "missing.txt"), 3)
     bad = tmp_path / "bad.txt"

@@ -1,0 +1,79 @@
+"""Ingest: FASTA pair -> symbols by the rule of scripts/prepare-alignments.py:99-111, bit exact; binary
+container round trip; the reference's text format.  Host only."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import example_symbols
+
+
+def python_rule(a, b):
+    clean = set("ACGT")
+    return np.array([2 if (x.upper() not in clean or y.upper() not in clean) else (0 if x.upper() == y.upper() else 1)
+                     for x, y in zip(a, b)], dtype=np.uint8)
+
+
+def test_pair_rule_bit_exact_on_every_byte_pair():
+    import imcoalhmm_b200 as m
+    alphabet = "ACGTacgtNn-.*RYKMSWBDHVX? "
+    a = "".join(x for x in alphabet for _ in alphabet)
+    b = alphabet * len(alphabet)
+    f = m.Forwarder.from_pair(a, b)
+    assert f.NSYM == 3 and np.array_equal(f._seq.symbols(), python_rule(a, b))
+    with pytest.raises(ValueError):
+        m.Forwarder.from_pair("ACGT", "ACG")
+    assert len(m.Forwarder.from_pair("", "")) == 0
+
+
+def test_fasta_reader_and_named_records(tmp_path):
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(0)
+    seqs = {name: "".join(rng.choice(list("ACGTacgtN-"), size=1234, p=[.2, .2, .2, .2, .04, .04, .04, .04, .02, .02]))
+            for name in ("hg18", "pantro2", "gorilla")}
+    p = tmp_path / "aln.fa"
+    with open(p, "w") as f:
+        for name, s in seqs.items():
+            f.write(">%s some description\r\n" % name)
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + "\n")
+            f.write("\n")
+    f12 = m.Forwarder.from_fasta(str(p), names=("hg18", "pantro2"))
+    assert np.array_equal(f12._seq.symbols(), python_rule(seqs["hg18"], seqs["pantro2"]))
+    f31 = m.Forwarder.from_fasta(str(p), names=("gorilla", "hg18"))
+    assert np.array_equal(f31._seq.symbols(), python_rule(seqs["gorilla"], seqs["hg18"]))
+    with pytest.raises(ValueError):
+        m.Forwarder.from_fasta(str(p))                       # three records: names are required
+    with pytest.raises(ValueError):
+        m.Forwarder.from_fasta(str(p), names=("hg18", "orang"))
+    with pytest.raises(IOError):
+        m.Forwarder.from_fasta(str(tmp_path / "missing.fa"))
+    two = tmp_path / "two.fa"
+    two.write_text(">a\nACGTN\n>b\nACCTA")
+    assert m.Forwarder.from_fasta(str(two))._seq.symbols().tolist() == [0, 0, 1, 0, 2]
+
+
+def test_binary_container_and_text_round_trip(tmp_path):
+    import imcoalhmm_b200 as m
+    sym = example_symbols()
+    f = m.Forwarder.from_symbols(sym, 3)
+    f.save(str(tmp_path / "x.imcseq"))
+    assert os.path.getsize(tmp_path / "x.imcseq") == 24 + (len(sym) + 3) // 4
+    g = m.Forwarder.load(str(tmp_path / "x.imcseq"))
+    assert g.NSYM == 3 and np.array_equal(g._seq.symbols(), sym)
+    f.write_text(str(tmp_path / "x.txt"))                    # the reference's own format ...
+    h = m.Forwarder(str(tmp_path / "x.txt"), 3)              # ... read back by the reference-style constructor
+    assert np.array_equal(h._seq.symbols(), sym)
+    nine = m.Forwarder.from_symbols(np.arange(1000) % 9, 9)  # alphabets > 4 symbols are stored one byte each
+    nine.save(str(tmp_path / "n.imcseq"))
+    assert np.array_equal(m.Forwarder.load(str(tmp_path / "n.imcseq"))._seq.symbols(), np.arange(1000) % 9)
+    (tmp_path / "bad.imcseq").write_bytes(b"IMCSEQ1\0" + b"\x03\0\0\0\x02\0\0\0" + (100).to_bytes(8, "little") + b"\0" * 3)
+    with pytest.raises(IOError):
+        m.Forwarder.load(str(tmp_path / "bad.imcseq"))        # truncated
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/example_data.fa"), reason="reference tree not present")
+def test_reference_example_alignment_matches_committed_fixture():
+    import imcoalhmm_b200 as m
+    f = m.Forwarder.from_fasta("/root/reference/examples/example_data.fa", names=("hg18", "pantro2"))
+    assert np.array_equal(f._seq.symbols(), example_symbols())

@@ -373,6 +373,13 @@ def main():
                 "peak_source": "measured in this run (imc_measure_fp64_peak): DFMA %.1f, DMMA %.1f TFLOP/s; "
                 "MEASURED_PEAKS.json has no FP64 entry" % (peak_dfma, peak_dmma),
                 "algorithmic_flop_per_site_point": flops_per_site_point(K), "kernel_ms": 1e3 * t_kernel}
+    try:    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr and kernel == "zip" and args.forward_kernel == 0:
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = "%s, ncu --set full: %s" % (tr["kernel"], tr["source"])
+    except (OSError, ValueError):
+        pass
     if kernel == "zip":
         # The kernel runs the reference's own algorithm (zipHMM: one mat-vec per COMPRESSED symbol), so the
         # algorithmic rate above (plain-forward flops of SURVEY 8(d) / time) exceeds the FP64 peak by about the

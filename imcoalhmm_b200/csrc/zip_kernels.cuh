@@ -275,7 +275,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
             int ebase = 0;
             if (lv < 0) {     // C_s[r][c] = E[r][s] * T[c][r]
                 for (int x = lane; x < K * K; x += 32) {
-                    const int r = x / K, c = x % K;
+                    const int r = x % K, c = x / K;      // rows fastest: consecutive lanes touch consecutive 16-byte units
                     const double v = sE[r * S + e] * Tg[c * K + r];
                     C::store(D, r, c, v);
                     mx = fmax(mx, fabs(v));
@@ -287,7 +287,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
                 const double* B = dict + (size_t)ir * C::STRIDE_D;
                 ebase = dexp[il] + dexp[ir];
                 for (int x = lane; x < K * K; x += 32) {
-                    const int r = x / K, c = x % K;
+                    const int r = x % K, c = x / K;      // B[r][k]: conflict-free across lanes; A[k][c]: (near) broadcast
                     double acc = 0.0;
 #pragma unroll 4
                     for (int k = 0; k < K; ++k) acc = fma(B[C::off(r, k)], A[C::off(k, c)], acc);
@@ -304,7 +304,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
                 ex = exponent_of(mx);
                 if (ex < -1000) ex = -1000;
                 const double f = pow2_neg(ex);
-                for (int x = lane; x < K * K; x += 32) C::store(D, x / K, x % K, D[C::off(x / K, x % K)] * f);
+                for (int x = lane; x < K * K; x += 32) C::store(D, x % K, x / K, D[C::off(x % K, x / K)] * f);
             }
             if (lane == 0) dexp[e] = ebase + ex;
         }

@@ -116,7 +116,7 @@ struct ZipCfg8 {
     };
     __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
     template <bool PRED>
-    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const int* dexp, int id,
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
                                                 const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + buf * KP;
         if (!PRED || active) {
@@ -188,7 +188,7 @@ struct ZipCfg4 {
     // register k of a slot-c lane holds state 2*((k/2)^c) + k%2
     __device__ static __forceinline__ int state_of(const Lane& L, int k) { return 2 * ((k >> 1) ^ L.c) + (k & 1); }
     template <bool PRED>
-    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const int* dexp, int id,
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
                                                 const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + buf * KP;
         if (!PRED || active) {
@@ -226,12 +226,12 @@ struct ZipSmem {
     __host__ __device__ static constexpr int se_doubles(int S) { return (C::K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
     static size_t bytes(int M, int S, int threads) {
         size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / C::G) * C::GS;
-        return d * sizeof(double) + ((size_t)M + 4) * sizeof(int);   // dexp[M], s_point[2]
+        return d * sizeof(double) + (size_t)M * sizeof(long long) + 4 * sizeof(int);   // dexp[M], s_point[2]
     }
     static int max_entries(size_t budget, int S, int threads) {
         const size_t fixed = bytes(0, S, threads);
         if (budget <= fixed) return 0;
-        const size_t m = (budget - fixed) / (C::STRIDE_D * sizeof(double) + sizeof(int));
+        const size_t m = (budget - fixed) / (C::STRIDE_D * sizeof(double) + sizeof(long long));
         return (int)(m > 256 ? 256 : m);
     }
 };
@@ -255,7 +255,7 @@ __device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scal
 
 // Build the dictionary of parameter point n in shared memory (all threads of the CTA).
 template <class C, int THREADS>
-__device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, int* dexp) {
+__device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, long long* dexp) {
     constexpr int K = C::K, KP = C::KP, NW = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = a.M, S = a.S;
@@ -272,7 +272,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
             double* D = dict + (size_t)e * C::STRIDE_D;
             double mx = 0.0;
             bool bad = false;
-            int ebase = 0;
+            long long ebase = 0;
             if (lv < 0) {     // C_s[r][c] = E[r][s] * T[c][r]
                 for (int x = lane; x < K * K; x += 32) {
                     const int r = x % K, c = x / K;      // rows fastest: consecutive lanes touch consecutive 16-byte units
@@ -316,7 +316,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
 // unit*CPW .. unit*CPW + CPW-1 of the sorted chunk list.
 template <class C>
 __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
-                                             const double* spi, const int* dexp, const typename C::Lane& L) {
+                                             const double* spi, const long long* dexp, const typename C::Lane& L) {
     constexpr int K = C::K, KP = C::KP;
     const int S = a.S;
     const int ci = unit * C::CPW + L.grp;
@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     double* sE = dict + (size_t)M * C::STRIDE_D;      // [K][S]
     double* spi = sE + ZipSmem<C>::se_doubles(S);     // [KP]
     double* sbuf = spi + KP;                          // [THREADS/G][GS]
-    int* dexp = reinterpret_cast<int*>(sbuf + (THREADS / C::G) * C::GS);   // [M]
-    int* s_point = dexp + M;
+    long long* dexp = reinterpret_cast<long long*>(sbuf + (THREADS / C::G) * C::GS);   // [M] (64-bit: an entry can span millions of sites)
+    int* s_point = reinterpret_cast<int*>(dexp + M);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const typename C::Lane L(lane, warp, sbuf);

@@ -1,0 +1,66 @@
+"""BASELINE.json configs[1] at FULL size (100 x 1 Mbp, 256 parameter points) through size-independent properties,
+plus oracle spot checks -- the oracle cannot score 2.6e10 site-points in a test, the GPU does it in milliseconds."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def full_c2():
+    import bench
+    import imcoalhmm_b200 as m
+    wl = bench.WORKLOADS["c2"]
+    model = m.IsolationModel(10)
+    thetas = bench.thetas_around(wl["default"], wl["points"])
+    pis, Ts, Es, st = model.build_hidden_markov_models(thetas)
+    assert (st == 0).all()
+    chunks = bench.make_chunks(wl, pis, Ts, Es, range(wl["chunks"]))
+    return m, model, thetas, pis, Ts, Es, chunks
+
+
+def test_full_size_properties(full_c2):
+    m, model, thetas, pis, Ts, Es, chunks = full_c2
+    mk = lambda cs: m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in cs])
+    whole_set = mk(chunks)
+    assert whole_set.total_sites == 100_000_000
+    info = whole_set.zip_info(10)
+    assert info["tokens"] * 100 < whole_set.total_sites            # > 100x compression on this alignment
+    whole = whole_set.forward_batch(pis, Ts, Es)
+    assert m.last_forward_kernel() == "zip" and np.isfinite(whole).all()
+    # chunk additivity: two halves have their OWN dictionaries and token streams -> an independent evaluation
+    halves = mk(chunks[:37]).forward_batch(pis, Ts, Es) + mk(chunks[37:]).forward_batch(pis, Ts, Es)
+    np.testing.assert_allclose(halves, whole, rtol=1e-12)
+    # the fused theta -> logL entry gives the same numbers as build + forward
+    np.testing.assert_allclose(model.batched_log_likelihood(thetas, whole_set), whole, rtol=1e-12)
+    # the uncompressed per-site kernel (every one of the 1e8 sites walked, T in registers) agrees on all 256 points
+    m.set_option("forward_kernel", 2)
+    try:
+        plain = whole_set.forward_batch(pis, Ts, Es)
+        assert m.last_forward_kernel() == "pair"
+    finally:
+        m.set_option("forward_kernel", 0)
+    np.testing.assert_allclose(plain, whole, rtol=1e-11)
+    # time reversal (the reference's chains are reversible, transitions.py:237) on 10 Mbp
+    fw = mk(chunks[:10]).forward_batch(pis[:16], Ts[:16], Es[:16])
+    bw = mk([c[::-1].copy() for c in chunks[:10]]).forward_batch(pis[:16], Ts[:16], Es[:16])
+    np.testing.assert_allclose(bw, fw, rtol=1e-11)
+    # single-point calls take the segmented route and must agree with the batch
+    one = whole_set.forward(pis[3], Ts[3], Es[3])
+    assert m.last_forward_kernel() == "zip-segmented"
+    assert one == pytest.approx(whole[3], rel=1e-12)
+
+
+def test_full_size_oracle_spot_check(full_c2):
+    m, model, thetas, pis, Ts, Es, chunks = full_c2
+    from oracle import forward as F
+    sub = [chunks[0], chunks[57], chunks[99]]
+    got = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in sub]).forward_batch(pis[:4], Ts[:4], Es[:4])
+    want, _ = F.forward_batch([c.astype(np.int32) for c in sub], pis[:4], Ts[:4], Es[:4])
+    np.testing.assert_allclose(got, want, rtol=1e-11)

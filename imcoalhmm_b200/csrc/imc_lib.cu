@@ -516,15 +516,18 @@ static int seqset_upload(imc_seqset* set) {
 enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3, KERNEL_ZIP = 4 };
 
 #define ZIP_K_LIST(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(32) X(40)
-static bool zip_supported(int K) {
-    switch (K) {
-#define X(k) case k:
+// smallest instantiated tile that holds K states (the kernels take the actual K at run time and leave the padding
+// rows / columns of the tile at zero), or 0
+static int zip_tile(int K) {
+    static const int tiles[] = {
+#define X(k) k,
         ZIP_K_LIST(X)
 #undef X
-        return true;
-    }
-    return false;
+    };
+    for (int t : tiles) if (t >= K) return t;
+    return 0;
 }
+static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
 
 struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
 static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
@@ -568,7 +571,7 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
 
 static int zip_plan(int K, int S, int avail_ids, ZipPlan* out) {
     const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = (int)g_ctx.opt_zip_lanes;
-    switch (K) {
+    switch (zip_tile(K)) {
 #define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
         ZIP_K_LIST(X)
 #undef X
@@ -716,7 +719,7 @@ static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
     const long long units = (long long)a.N * ((nunits + nw - 1) / nw);
     const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
     const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
-    switch (a.K) {
+    switch (zip_tile(a.K)) {
 #define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
         ZIP_K_LIST(X)
 #undef X

@@ -37,7 +37,7 @@ struct ZipArgs {
     const int* level_start;      // [nlevels + 1]
     int nlevels;
     int M;
-    int N, K, S;
+    int N, K, S;                 // K = actual number of states (<= the tile size the kernel was instantiated for)
     const double* pi;            // [N][K]
     const double* T;             // [N][K][K]
     const double* E;             // [N][K][S]
@@ -256,7 +256,8 @@ __device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scal
 // Build the dictionary of parameter point n in shared memory (all threads of the CTA).
 template <class C, int THREADS>
 __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, long long* dexp) {
-    constexpr int K = C::K, KP = C::KP, NW = THREADS / 32;
+    constexpr int KP = C::KP, NW = THREADS / 32;
+    const int K = a.K;          // actual state count <= C::K (the kernel's tile); rows / columns beyond it stay zero
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = a.M, S = a.S;
     const double* Tg = a.T + (size_t)n * K * K;
@@ -317,8 +318,8 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
 template <class C>
 __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
                                              const double* spi, const long long* dexp, const typename C::Lane& L) {
-    constexpr int K = C::K, KP = C::KP;
-    const int S = a.S;
+    constexpr int KP = C::KP;
+    const int K = a.K, S = a.S;
     const int ci = unit * C::CPW + L.grp;
     const bool have = ci < a.nchunks;
     const ZipChunk ch = a.chunks[have ? ci : unit * C::CPW];

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-11
 
 KERNELS = {"generic": 1, "pair": 2, "dmma": 3, "zip": 4}
-ZIP_K = (2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40)
+ZIP_MAX_K = 40      # tiles 2..40; any K below runs in the next tile with zero padding
 
 
 @pytest.fixture(autouse=True)
@@ -103,7 +103,7 @@ def test_random_hmms_all_instantiated_sizes(K):
             continue
         if k == "dmma" and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
             continue
-        if k == "zip" and K not in ZIP_K:
+        if k == "zip" and K > ZIP_MAX_K:
             continue
         m.set_option("forward_kernel", code)
         for lanes in ((4, 8) if k == "zip" else (0,)):
@@ -120,6 +120,26 @@ def test_generic_kernel_any_K(K):
     want = oracle_batch(chunks, pi[None], T[None], E[None])[0]
     m.set_option("forward_kernel", 1)
     assert make_set(chunks).forward(pi, T, E) == pytest.approx(want, rel=RTOL)
+
+
+@pytest.mark.parametrize("K", [1, 7, 9, 11, 13, 14, 15, 18, 23, 30, 37])
+def test_zip_kernel_any_K_up_to_40(K):
+    """State counts between the instantiated tiles run zero-padded in the next tile (both lane decompositions)."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(300 + K)
+    hmms = [random_hmm(rng, K) for _ in range(3)]
+    pis, Ts, Es = (np.stack([h[i] for h in hmms]) for i in range(3))
+    Ts = 0.9 * np.eye(K)[None] + 0.1 * Ts
+    chunks = [rng.choice(3, size=int(n), p=[0.95, 0.01, 0.04]).astype(np.uint8) for n in (3000, 17, 1, 64, 5000, 70000)]
+    want = oracle_batch(chunks, pis, Ts, Es)
+    s = make_set(chunks)
+    assert s.forward(pis[0], Ts[0], Es[0]) == pytest.approx(want[0], rel=RTOL)
+    assert m.last_forward_kernel().startswith("zip")               # the default for every K <= 40
+    for lanes in (8, 4):
+        for seg in (-1, 64):
+            m.set_option("zip_lanes", lanes)
+            m.set_option("zip_segment_tokens", seg)
+            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d lanes=%d seg=%d" % (K, lanes, seg))
 
 
 @pytest.mark.parametrize("mt", [1, 2, 4])

@@ -435,11 +435,11 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
         set->first_sym.resize(ns);
         set->stream_of_chunk.assign(C, -1);
         for (int k = 0; k < ns; ++k) set->stream_of_chunk[order[k]] = k;
-        parallel_for(ns, [&](int k) {
-            const auto& sy = seqs[order[k]]->sym;
-            set->first_sym[k] = sy[0];
-            zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
-        });
+        if (!parallel_for(ns, [&](int k) {
+                const auto& sy = seqs[order[k]]->sym;
+                set->first_sym[k] = sy[0];
+                zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
+            })) throw std::bad_alloc();
         for (int b0 = 0; set->packable && b0 < ns; b0 += 32) {
             const int nb = std::min(32, ns - b0);
             const long long maxlen = (long long)seqs[order[b0]]->sym.size();
@@ -587,10 +587,10 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     const int ns = (int)set->streams.size();
     ZipLevels zl = zip_levels(set->merges, M);
     std::vector<std::vector<uint8_t>> tok(ns);
-    parallel_for(ns, [&](int k) {
-        zip_expand(set->merges, set->tok_full[k], M, tok[k]);
-        for (auto& t : tok[k]) t = zl.perm[t];
-    });
+    if (!parallel_for(ns, [&](int k) {
+            zip_expand(set->merges, set->tok_full[k], M, tok[k]);
+            for (auto& t : tok[k]) t = zl.perm[t];
+        })) return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams");
     std::vector<int> order(ns);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tok[x].size() > tok[y].size(); });
@@ -858,7 +858,9 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
 
     int which = (int)g_ctx.opt_forward_kernel;
     if (which == KERNEL_AUTO) {
-        if (zip_supported(K)) which = KERNEL_ZIP;
+        ZipPlan probe;
+        // zip wherever its dictionary fits; large alphabets x large K that do not fit fall back to the per-site kernels
+        if (zip_supported(K) && (zip_plan(K, S, set->merges.size(), &probe) == IMC_OK || !set->packable)) which = KERNEL_ZIP;
         else which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
     }
     if (which == KERNEL_ZIP) {

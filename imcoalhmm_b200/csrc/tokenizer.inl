@@ -124,19 +124,23 @@ static ZipLevels zip_levels(const ZipMerges& mg, int M) {
     return zl;
 }
 
+// fn(i) for i in [0, n) on the host cores of the affinity mask; returns false if any call threw (out of memory)
 template <typename F>
-static void parallel_for(int n, F&& fn) {
+static bool parallel_for(int n, F&& fn) {
     unsigned hw = std::thread::hardware_concurrency();
     int nt = (int)std::min<unsigned>(hw ? hw : 4u, 32u);
     cpu_set_t cs;
     if (sched_getaffinity(0, sizeof cs, &cs) == 0) nt = std::min(nt, std::max(1, CPU_COUNT(&cs)));
     nt = std::min(nt, n);
-    if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<bool> ok{true};
+    auto guarded = [&](int i) { try { fn(i); } catch (...) { ok = false; } };
+    if (nt <= 1) { for (int i = 0; i < n; ++i) guarded(i); return ok; }
     std::atomic<int> next{0};
     std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t)
-        th.emplace_back([&]() { for (int i = next++; i < n; i = next++) fn(i); });
+        th.emplace_back([&]() { for (int i = next++; i < n; i = next++) guarded(i); });
     for (auto& t : th) t.join();
+    return ok;
 }
 
 }  // namespace imc

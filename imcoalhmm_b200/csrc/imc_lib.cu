@@ -113,8 +113,9 @@ struct DeviceBuf {
 
 // device copy of the token streams derived for one dictionary size M (see zip_device)
 struct ZipSplit {                 // segmented variant of a ZipDevice's chunk list (same token buffer)
-    int K = 0, seglen = 0, nchains = 0, nsegchunks = 0;
-    DeviceBuf chunks, segs;
+    int K = 0, seglen = 0, nchains = 0;
+    int n_level1 = 0, n_final = 0, nvec2 = 0;     // fold items of the two levels, vectors written by level 1
+    DeviceBuf chunks, items1, items2;
 };
 
 struct ZipDevice {
@@ -480,7 +481,7 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
         for (ZipSplit* sp : z->splits) {
-            if (mine) { sp->chunks.release(); sp->segs.release(); }
+            if (mine) { sp->chunks.release(); sp->items1.release(); sp->items2.release(); }
             delete sp;
         }
         delete z;
@@ -646,39 +647,58 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
 static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
     for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
     std::vector<ZipChunk> chains;
-    std::vector<ZipSegChunk> segs;
+    std::vector<ZipFoldItem> items1, items2;
+    int nvec2 = 0;
     for (const ZipChunk& ch : z->host_chunks) {
         const int nseg = std::max(1, (ch.ntok + seglen - 1) / seglen);
-        ZipSegChunk sc;
-        sc.first_chain = (int)chains.size(); sc.nseg = nseg; sc.out_index = ch.out_index; sc.pad = 0;
-        segs.push_back(sc);
+        const int first_chain = (int)chains.size();
         for (int sg = 0; sg < nseg; ++sg) {
             ZipChunk c = ch;
             c.tok_off = ch.tok_off + (long long)sg * seglen;
-            c.ntok = std::min(seglen, ch.ntok - sg * seglen);
-            if (c.ntok < 0) c.ntok = 0;
+            c.ntok = std::max(0, std::min(seglen, ch.ntok - sg * seglen));
             for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
                 c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
                 c.out_index = (int)chains.size();
                 chains.push_back(c);
             }
         }
+        // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
+        if (nseg <= 32) {
+            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0});
+        } else {        // two levels: groups of gs segments folded in parallel, then the groups
+            const int gs = (int)std::ceil(std::sqrt((double)nseg)), ngroups = (nseg + gs - 1) / gs;
+            const int base2 = nvec2;
+            for (int g = 0; g < ngroups; ++g) {
+                const int s0 = g * gs, s1 = std::min(nseg, s0 + gs);     // segments [s0, s1)
+                if (g == 0) {
+                    items1.push_back({first_chain, first_chain + 1, s1 - 1, nvec2++, 0, 1});
+                } else {
+                    for (int col = 0; col < K; ++col)
+                        items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1});
+                }
+            }
+            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0});
+        }
     }
-    // the kernel takes chunks in list order, longest first: full segments first, tails last (stable: out_index keeps identity)
+    // the kernel takes chunks in list order, longest first: full segments first, tails last (out_index keeps identity)
     std::vector<ZipChunk> sorted = chains;
     std::stable_sort(sorted.begin(), sorted.end(), [](const ZipChunk& x, const ZipChunk& y) { return x.ntok > y.ntok; });
     ZipSplit* sp = new (std::nothrow) ZipSplit;
     if (!sp) return fail(IMC_ERR_NOMEM, "out of memory");
-    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size(); sp->nsegchunks = (int)segs.size();
+    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size();
+    sp->n_level1 = (int)items1.size(); sp->n_final = (int)items2.size(); sp->nvec2 = nvec2;
     int rc;
-    if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) || (rc = sp->segs.reserve(sizeof(ZipSegChunk) * segs.size()))) {
-        sp->chunks.release(); sp->segs.release(); delete sp;
+    if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) ||
+        (rc = sp->items1.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items1.size(), 1))) ||
+        (rc = sp->items2.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items2.size(), 1)))) {
+        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
         return rc;
     }
     cudaError_t e = cudaMemcpy(sp->chunks.p, sorted.data(), sizeof(ZipChunk) * sorted.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(sp->segs.p, segs.data(), sizeof(ZipSegChunk) * segs.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !items1.empty()) e = cudaMemcpy(sp->items1.p, items1.data(), sizeof(ZipFoldItem) * items1.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !items2.empty()) e = cudaMemcpy(sp->items2.p, items2.data(), sizeof(ZipFoldItem) * items2.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-        sp->chunks.release(); sp->segs.release(); delete sp;
+        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
         return fail(IMC_ERR_CUDA, "uploading segment descriptors failed: %s", cudaGetErrorString(e));
     }
     z->splits.push_back(sp);
@@ -899,7 +919,7 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
                 seglen = (seglen + 15) / 16 * 16;
                 if (seglen < z->max_ntok) {
                     if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
-                    const size_t vec_bytes = sizeof(double) * (size_t)N * split->nchains * (K + 1);
+                    const size_t vec_bytes = sizeof(double) * (size_t)N * ((size_t)split->nchains + split->nvec2) * (K + 1);
                     if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
                     else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
                 }
@@ -915,9 +935,15 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         if ((rc = launch_zip(za, plan, st))) return rc;
         CUDA_TRY(cudaGetLastError());
         if (split) {
-            zip_combine_kernel<<<dim3(split->nsegchunks, N), 64, 0, st>>>(za.vec_out, za.vec_stride, split->nchains,
-                                                                        (const ZipSegChunk*)split->segs.p, split->nsegchunks, K,
-                                                                        za.chain_out, za.out_stride);
+            double* vec2 = za.vec_out + (size_t)N * split->nchains * za.vec_stride;
+            if (split->n_level1 > 0) {
+                zip_fold_kernel<<<dim3(split->n_level1, N), 64, 0, st>>>(za.vec_out, split->nchains, vec2, split->nvec2, za.vec_stride,
+                                                                        (const ZipFoldItem*)split->items1.p, K, za.chain_out, za.out_stride);
+                CUDA_TRY(cudaGetLastError());
+                g_launches += 1;
+            }
+            zip_fold_kernel<<<dim3(split->n_final, N), 64, 0, st>>>(za.vec_out, split->nchains, vec2, split->nvec2, za.vec_stride,
+                                                                   (const ZipFoldItem*)split->items2.p, K, za.chain_out, za.out_stride);
             CUDA_TRY(cudaGetLastError());
             g_launches += 1;
         }

@@ -23,7 +23,7 @@ struct ZipChunk {
     long long tok_off;   // byte offset of the chunk's first token (16-byte aligned, 16 readable bytes past the end)
     int ntok;            // tokens (the chunk's symbols 1..L-1 after compression)
     int first_sym;       // >= 0: symbol at position 0 (alpha_0 = pi o E[:,first_sym]);  < 0: the chain starts from the
-                         // unit vector e_c, c = -1 - first_sym (column c of a segment's transfer matrix, see zip_combine_kernel)
+                         // unit vector e_c, c = -1 - first_sym (column c of a segment's transfer matrix, see zip_fold_kernel)
     int out_index;       // column of chain_out this chunk writes
     int pad;
 };
@@ -51,12 +51,6 @@ struct ZipArgs {
 // Segment 0 runs as usual from pi; segment s > 0 is run K times from the unit vectors e_0..e_{K-1}, which yields the
 // columns of its transfer matrix P_s = C_tok[last] ... C_tok[first] (K times the arithmetic, but K * #segments times
 // the parallelism).  zip_combine_kernel then folds alpha <- P_s alpha over the segments of each chunk.
-struct ZipSegChunk {
-    int first_chain;     // index (in vec_out) of the segment-0 chain; segment s >= 1, column c is first_chain + 1 + (s-1)*K + c
-    int nseg;
-    int out_index;       // column of chain_out
-    int pad;
-};
 
 // ------------------------------------------------------------------------------------------------
 // Lane decompositions.  A config class C describes how one chain's mat-vec is spread over G lanes:
@@ -459,20 +453,29 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     }
 }
 
-// alpha <- P_s alpha over the segments of one chunk; one CTA of 64 threads per (parameter point, chunk), K <= 64.
-__global__ void __launch_bounds__(64) zip_combine_kernel(const double* vec, int vec_stride, int nchains, const ZipSegChunk* segs,
-                                                         int nsegchunks, int K, double* chain_out, int out_stride) {
+// Fold alpha <- P_s alpha over a run of consecutive segments.  One CTA of 64 threads per (item, parameter point), K <= 64.
+// An item starts from vector `start` of its source buffer, folds in `nfold` segments whose column c sits at index
+// first_cols + i*K + c, and writes either a log-likelihood (dst == 0: chain_out[n][out_index]) or the folded vector
+// (dst == 1: vec2[n][out_index]).  Long chunks are folded in two levels (groups of ~sqrt(#segments) segments in
+// parallel, then the groups), so the sequential depth stays ~2 sqrt(#segments) whatever the chunk length.
+struct ZipFoldItem {
+    int start, first_cols, nfold, out_index;
+    int src, dst;        // src: 0 = vec (kernel output), 1 = vec2 (level-1 output)
+};
+
+__global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nvec, double* vec2, int nvec2, int vec_stride,
+                                                      const ZipFoldItem* items, int K, double* chain_out, int out_stride) {
     __shared__ double w[64];
     __shared__ double red[2];
     __shared__ int s_e[2];
     const int n = blockIdx.y, j = threadIdx.x;
-    const ZipSegChunk sc = segs[blockIdx.x];
-    const double* base = vec + (size_t)n * nchains * vec_stride;
-    const double* v0 = base + (size_t)sc.first_chain * vec_stride;
+    const ZipFoldItem it = items[blockIdx.x];
+    const double* base = it.src == 0 ? vec + (size_t)n * nvec * vec_stride : vec2 + (size_t)n * nvec2 * vec_stride;
+    const double* v0 = base + (size_t)it.start * vec_stride;
     double alpha = j < K ? v0[j] : 0.0;
     double scale = v0[K];
-    for (int s = 1; s < sc.nseg; ++s) {
-        const double* cols = base + (size_t)(sc.first_chain + 1 + (s - 1) * K) * vec_stride;
+    for (int s = 0; s < it.nfold; ++s) {
+        const double* cols = base + (size_t)(it.first_cols + s * K) * vec_stride;
         // column c carries 2^e_c; bring all columns to the largest exponent among those that matter
         const double ec = j < K ? cols[(size_t)j * vec_stride + K] : 0.0;
         bool matters = j < K && alpha != 0.0;
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(64) zip_combine_kernel(const double* vec, int 
         if ((j & 31) == 0) s_e[j >> 5] = e;
         __syncthreads();
         const int emax = max(s_e[0], s_e[1]);
-        const int d = (int)ec - emax;                  // <= 0 where alpha != 0
+        const int d = (int)ec - emax;                  // <= 0 where it matters
         w[j] = matters ? (d < -1000 ? 0.0 : alpha * pow2_neg(-d)) : 0.0;
         __syncthreads();
         double acc = 0.0;
@@ -504,6 +507,12 @@ __global__ void __launch_bounds__(64) zip_combine_kernel(const double* vec, int 
         scale += (emax > -0x40000000 ? (double)emax : 0.0) + (double)en;
         __syncthreads();
     }
+    if (it.dst == 1) {
+        double* out = vec2 + ((size_t)n * nvec2 + it.out_index) * vec_stride;
+        if (j < K) out[j] = alpha;
+        if (j == 0) out[K] = scale;
+        return;
+    }
     double sum = alpha;
     for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
     if ((j & 31) == 0) red[j >> 5] = sum;
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(64) zip_combine_kernel(const double* vec, int 
         if (sum != sum) r = sum;
         else if (!(sum > 0.0)) r = -INFINITY;
         else r = log(sum) + scale * LN2;
-        chain_out[(size_t)n * out_stride + sc.out_index] = r;
+        chain_out[(size_t)n * out_stride + it.out_index] = r;
     }
 }
 

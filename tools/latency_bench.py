@@ -18,10 +18,13 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--chunks", type=int, default=0)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--chunk-len", type=int, default=0)
     args = ap.parse_args()
     wl = dict(bench.WORKLOADS[args.workload])
     if args.chunks:
         wl["chunks"] = args.chunks
+    if args.chunk_len:
+        wl["chunk_len"] = args.chunk_len
     model = getattr(m, wl["ctor"][0])(*wl["ctor"][1])
     theta = np.asarray(wl["default"], dtype=np.float64)
     pi, T, E = model.build_hidden_markov_model(theta)

@@ -736,7 +736,8 @@ static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaSt
 static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
     // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
     const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
-    const long long units = (long long)a.N * ((nunits + nw - 1) / nw);
+    (void)nw;
+    const long long units = (long long)a.N * nunits;     // scarce work spreads one warp-load per CTA over the SMs
     const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
     const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
     switch (zip_tile(a.K)) {
@@ -909,11 +910,33 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         // segments after the first, but enough chains to fill the machine (zip_kernels.cuh, "segmented mode").
         ZipSplit* split = nullptr;
         {
-            const long long slots = (long long)(g_ctx.sm_count > 0 ? g_ctx.sm_count : 148) * plan.ctas_per_sm * (plan.threads / plan.lanes);
+            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+            const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
             long long seglen = g_ctx.opt_zip_segment_tokens;
             if (seglen == 0 && (long long)N * ns * 4 <= slots && z->max_ntok >= 1024 && K <= 64) {
-                seglen = (long long)N * z->total_tokens * K / (2 * slots);
-                seglen = std::max<long long>(256, seglen);
+                // Cost model (SM clocks), constants from the round-1 measurements: a chain-step costs the SM c clocks of
+                // shared-memory pipe (K=10: 14, K=20: 35, K=40: 135) and a lone chain advances one step per ~lat clocks
+                // (K=10: 790, K=20: 2070, K=40: 3550: one warp issuing K*K/8 DFMA and K*K/16 LDS.128 per lane and step).
+                // A call takes max(longest chain x lat, total chain-steps x c / SMs); segments of s tokens shorten the
+                // chains but multiply the steps of all segments after the first by K.
+                const double c = 1.4 * K * K / 16.0 + 5.0, lat = 95.0 * K;
+                auto cost = [&](long long sl) {
+                    double steps = 0.0, longest = 0.0, nseg_max = 1.0;
+                    for (const ZipChunk& ch : z->host_chunks) {
+                        const double first = (double)std::min<long long>(sl, ch.ntok);
+                        steps += first + ((double)ch.ntok - first) * K;
+                        longest = std::max(longest, first);
+                        nseg_max = std::max(nseg_max, std::ceil((double)ch.ntok / (double)sl));
+                    }
+                    const double fold = nseg_max > 1.0 ? 20000.0 + 1500.0 * 2.0 * std::sqrt(nseg_max) : 0.0;
+                    return std::max(longest * lat, steps * N * c / sms) + fold;
+                };
+                const double whole = cost(z->max_ntok);
+                double best = whole;
+                for (long long sl = 256; sl < z->max_ntok; sl *= 2) {
+                    const double t = cost(sl);
+                    if (t < 0.8 * whole && t < best) { best = t; seglen = sl; }
+                }
             }
             if (seglen > 0 && K <= 64) {
                 seglen = (seglen + 15) / 16 * 16;

@@ -200,7 +200,12 @@ def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
     t = float(np.sum(times))
     value = sites * n_p * len(times) / t
     ratio = float(np.mean([len(c) / max(1, len(z[0])) for c, z in zip(chunks, zipped)]))
-    return {"value": value, "unit": "sites*points/s", "cores": int(used), "kind": "port",
+    # how the reference actually runs: one process, one thread (mcmc.py forks one such process per chain)
+    n1 = max(1, min(n_p, 4))
+    t0 = time.perf_counter()
+    F.forward_batch(None, pis[:n1], Ts[:n1], Es[:n1], mode="zip", zipped=zipped[:2], nthreads=1)
+    single = sum(len(c) for c in chunks[:2]) * n1 / (time.perf_counter() - t0)
+    return {"value": value, "unit": "sites*points/s", "cores": int(used), "kind": "port", "single_thread_value": single,
             "sample": "%d chunks x %d bp x %d points per step, zipHMM-style compressed forward (per-chunk dictionaries of "
                       "<= %d symbols, the fastest of 64..1024 on this host; %.0fx fewer symbols, preprocess %.1fs excluded "
                       "like hmm.py:16), OpenMP, %d steps" % (n_c, wl["chunk_len"], n_p, max_syms, ratio, t_prep, len(times)),
@@ -241,7 +246,7 @@ def main():
                 "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": 0,
-                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread_value")},
                 "e2e": {"value": res["value"], "unit": "sites*points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return

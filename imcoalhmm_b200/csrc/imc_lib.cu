@@ -546,8 +546,15 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
     ZipPlan p;
     p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
     if (K < 8) p.lanes = 8;
+    if (p.lanes == 32 && K < 10) p.lanes = 8;
     int m1, m2, t1;
-    if (p.lanes == 8) {
+    if (p.lanes == 32) {       // one chain per warp, one CTA per SM (latency mode)
+        using C = ZipCfg32<K>;
+        t1 = K <= 24 ? 512 : 256;
+        m2 = 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+        want_ctas = 1;
+    } else if (p.lanes == 8) {
         using C = ZipCfg8<K>;
         t1 = K <= 24 ? 512 : 256;
         m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
@@ -566,12 +573,13 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
     p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
     if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
     p.M = std::max(p.M, S);
-    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads);
+    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads)
+           : (p.lanes == 4 ? ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg32<K>>::bytes(p.M, S, p.threads));
     return p;
 }
 
-static int zip_plan(int K, int S, int avail_ids, ZipPlan* out) {
-    const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = (int)g_ctx.opt_zip_lanes;
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0) {
+    const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
     switch (zip_tile(K)) {
 #define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
         ZIP_K_LIST(X)
@@ -719,6 +727,12 @@ static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream
 
 template <int K>
 static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
+    if constexpr (K >= 10) {
+        if (p.lanes == 32) {
+            if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1>(a, p, grid, st);
+            else return launch_zip_k<ZipCfg32<K>, 256, 1>(a, p, grid, st);
+        }
+    }
     if constexpr (K >= 8) {
         if (p.lanes == 4) {
             if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2>(a, p, grid, st); }
@@ -733,13 +747,16 @@ static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaSt
     }
 }
 
-static int launch_zip(const ZipArgs& a, const ZipPlan& p, cudaStream_t st) {
+static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
     // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
     const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
     (void)nw;
     const long long units = (long long)a.N * nunits;     // scarce work spreads one warp-load per CTA over the SMs
     const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
     const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
+    // with fewer warp-loads than warps on the machine, let only as many warps per CTA claim work as it takes to cover
+    // them: the chains then spread over all SMs instead of piling onto the first CTAs that arrive
+    a.active_warps = (int)std::min<long long>(p.threads / 32, std::max<long long>(1, (units + grid - 1) / grid));
     switch (zip_tile(a.K)) {
 #define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
         ZIP_K_LIST(X)
@@ -889,6 +906,55 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         if ((rc = zip_plan(K, S, set->merges.size(), &plan))) return rc;
         ZipDevice* z = nullptr;
         if ((rc = zip_device(set, plan.M, &z))) return rc;
+        // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
+        // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
+        //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
+        //       (8 lanes: 36 K, 4 lanes: 49 K: one warp issuing K*K/lanes DFMA and half as many LDS.128 per step);
+        //   (b) one warp per chain (32 lanes): the shortest possible step, ~80 + 14.5 K clocks;
+        //   (c) segments of s tokens: K times the arithmetic on the segments after the first, but K * #segments times
+        //       the chains; throughput cost c clocks of shared-memory pipe per chain-step and SM (K=10: 14, K=20: 35).
+        ZipSplit* split = nullptr;
+        long long seglen = g_ctx.opt_zip_segment_tokens;
+        {
+            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+            const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
+            const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64;
+            if (scarce && (seglen == 0 || g_ctx.opt_zip_lanes == 0)) {
+                const double c = 1.4 * K * K / 16.0 + 5.0;
+                const double lat = (plan.lanes == 4 ? 49.0 : 36.0) * K, lat32 = 80.0 + 14.5 * K;
+                auto cost_seg = [&](long long sl) {
+                    double steps = 0.0, longest = 0.0, nseg_max = 1.0;
+                    for (const ZipChunk& ch : z->host_chunks) {
+                        const double first = (double)std::min<long long>(sl, ch.ntok);
+                        steps += first + ((double)ch.ntok - first) * K;
+                        longest = std::max(longest, first);
+                        nseg_max = std::max(nseg_max, std::ceil((double)ch.ntok / (double)sl));
+                    }
+                    const double fold = nseg_max > 1.0 ? 20000.0 + 1500.0 * 2.0 * std::sqrt(nseg_max) : 0.0;
+                    return std::max(longest * lat, 1.3 * steps * N * c / sms) + fold;      // 1.3: tails and imbalance
+                };
+                double best = cost_seg(z->max_ntok);          // (a)
+                long long best_seg = -1;
+                int best_lanes = plan.lanes;
+                if (seglen == 0) {
+                    for (long long sl = 256; sl < z->max_ntok; sl *= 2) {        // (c)
+                        const double t = cost_seg(sl);
+                        if (t < 0.8 * best) { best = t; best_seg = sl; }
+                    }
+                }
+                if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0) {   // (b)
+                    const long long warps = (long long)sms * (zip_tile(K) <= 24 ? 16 : 8);
+                    const double rounds = std::ceil((double)((long long)N * ns) / (double)warps);
+                    const double t = rounds * z->max_ntok * lat32;
+                    if (t < best) { best = t; best_seg = -1; best_lanes = 32; }
+                }
+                if (seglen == 0) seglen = best_seg;
+                if (best_lanes != plan.lanes) {
+                    if ((rc = zip_plan(K, S, set->merges.size(), &plan, best_lanes))) return rc;
+                    if ((rc = zip_device(set, plan.M, &z))) return rc;
+                }
+            }
+        }
         ZipArgs za;
         za.tokens = (const uint8_t*)z->tokens.p;
         za.chunks = (const ZipChunk*)z->chunks.p;
@@ -906,46 +972,13 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
         za.out_stride = ns;
         za.vec_out = nullptr;
         za.vec_stride = 0;
-        // Chain-scarce call (few chunks x few points)?  Cut the chunks into segments: K times the arithmetic on the
-        // segments after the first, but enough chains to fill the machine (zip_kernels.cuh, "segmented mode").
-        ZipSplit* split = nullptr;
-        {
-            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
-            const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
-            long long seglen = g_ctx.opt_zip_segment_tokens;
-            if (seglen == 0 && (long long)N * ns * 4 <= slots && z->max_ntok >= 1024 && K <= 64) {
-                // Cost model (SM clocks), constants from the round-1 measurements: a chain-step costs the SM c clocks of
-                // shared-memory pipe (K=10: 14, K=20: 35, K=40: 135) and a lone chain advances one step per ~lat clocks
-                // (K=10: 790, K=20: 2070, K=40: 3550: one warp issuing K*K/8 DFMA and K*K/16 LDS.128 per lane and step).
-                // A call takes max(longest chain x lat, total chain-steps x c / SMs); segments of s tokens shorten the
-                // chains but multiply the steps of all segments after the first by K.
-                const double c = 1.4 * K * K / 16.0 + 5.0, lat = 95.0 * K;
-                auto cost = [&](long long sl) {
-                    double steps = 0.0, longest = 0.0, nseg_max = 1.0;
-                    for (const ZipChunk& ch : z->host_chunks) {
-                        const double first = (double)std::min<long long>(sl, ch.ntok);
-                        steps += first + ((double)ch.ntok - first) * K;
-                        longest = std::max(longest, first);
-                        nseg_max = std::max(nseg_max, std::ceil((double)ch.ntok / (double)sl));
-                    }
-                    const double fold = nseg_max > 1.0 ? 20000.0 + 1500.0 * 2.0 * std::sqrt(nseg_max) : 0.0;
-                    return std::max(longest * lat, steps * N * c / sms) + fold;
-                };
-                const double whole = cost(z->max_ntok);
-                double best = whole;
-                for (long long sl = 256; sl < z->max_ntok; sl *= 2) {
-                    const double t = cost(sl);
-                    if (t < 0.8 * whole && t < best) { best = t; seglen = sl; }
-                }
-            }
-            if (seglen > 0 && K <= 64) {
-                seglen = (seglen + 15) / 16 * 16;
-                if (seglen < z->max_ntok) {
-                    if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
-                    const size_t vec_bytes = sizeof(double) * (size_t)N * ((size_t)split->nchains + split->nvec2) * (K + 1);
-                    if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
-                    else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
-                }
+        if (seglen > 0 && K <= 64) {
+            seglen = (seglen + 15) / 16 * 16;
+            if (seglen < z->max_ntok) {
+                if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
+                const size_t vec_bytes = sizeof(double) * (size_t)N * ((size_t)split->nchains + split->nvec2) * (K + 1);
+                if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
+                else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
             }
         }
         if (split) {
@@ -954,7 +987,7 @@ static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi,
             za.vec_out = (double*)set->d_vec.p;
             za.vec_stride = K + 1;
         }
-        g_last_kernel = split ? "zip-segmented" : "zip";
+        g_last_kernel = split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip");
         if ((rc = launch_zip(za, plan, st))) return rc;
         CUDA_TRY(cudaGetLastError());
         if (split) {
@@ -1119,7 +1152,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "fold_emission")) { g_ctx.opt_fold_emission = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "zip_ctas_per_sm")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_ctas_per_sm must be 0, 1 or 2"); g_ctx.opt_zip_ctas_per_sm = value; return IMC_OK; }
     if (!strcmp(key, "zip_segment_tokens")) { if (value < -1) return fail(IMC_ERR_INVALID, "zip_segment_tokens must be >= -1"); g_ctx.opt_zip_segment_tokens = value; return IMC_OK; }
-    if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4 or 8"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
+    if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8 && value != 32) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4, 8 or 32"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }

@@ -43,6 +43,7 @@ struct ZipArgs {
     const double* E;             // [N][K][S]
     double* chain_out;           // [N][out_stride]  log-likelihood per chain (vec_out == NULL)
     int out_stride;
+    int active_warps;            // warps per CTA that claim work (scarce work is spread over the SMs, one chain group per warp)
     double* vec_out;             // segmented mode: [N][nchunks][vec_stride] final vector (K doubles, unnormalised) + exponent
     int vec_stride;
 };
@@ -208,6 +209,65 @@ struct ZipCfg4 {
 #pragma unroll
             for (int cp = 0; cp < CP; ++cp) {
                 const double2 v = reinterpret_cast<const double2*>(sb)[cp ^ L.c];
+                al[2 * cp] = v.x;
+                al[2 * cp + 1] = v.y;
+            }
+        }
+    }
+};
+
+// G = 32: one chain per warp, lane q owns rows q and q+32.  Dense layout [column pair][row]: the lanes of a warp read
+// consecutive 16-byte units, so loads are conflict free; with K rows only K lanes are busy, which wastes issue slots
+// but makes ONE chain-step as short as it can be (K=20: 10 LDS.128 + 20 DFMA per lane instead of 50 + 100 with 4
+// lanes).  Used for chain-scarce calls (a single theta on few chunks), where latency per step is what counts.
+template <int K_>
+struct ZipCfg32 {
+    static constexpr int K = K_;
+    static constexpr int G = 32, CPW = 1;
+    static constexpr int KP = (K + 1) & ~1;
+    static constexpr int CP = KP / 2;
+    static constexpr int RPL = (K + 31) / 32;
+    static constexpr int STRIDE_D = CP * K * 2;        // dense: K units of 16 bytes per column pair
+    static constexpr int GS = 2 * KP + 2;              // one chain per warp: no cross-chain bank concerns
+    static constexpr int UNROLL = K <= 12 ? 4 : 1;
+    __host__ __device__ static constexpr int off(int r, int c) { return ((c >> 1) * K + r) * 2 + (c & 1); }
+    __device__ static __forceinline__ void store(double* D, int r, int c, double v) { D[off(r, c)] = v; }
+    struct Lane {
+        int q, grp;
+        double* sb0;
+        __device__ __forceinline__ Lane(int lane, int warp, double* sbuf) {
+            q = lane; grp = 0;
+            sb0 = sbuf + (size_t)warp * GS;
+        }
+        __device__ __forceinline__ bool writer() const { return q == 0; }
+    };
+    __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
+    template <bool PRED>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
+                                                const Lane& L, int buf, long long& scale, bool active) {
+        double* sb = L.sb0 + buf * KP;
+        if (!PRED || active) {
+            const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                if (L.q + 32 * k < K) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int cp = 0; cp < CP; ++cp) {
+                        const double2 m = mp[cp * K + 32 * k];
+                        s0 = fma(m.x, al[2 * cp], s0);
+                        s1 = fma(m.y, al[2 * cp + 1], s1);
+                    }
+                    sb[L.q + 32 * k] = s0 + s1;
+                }
+            }
+            scale += dexp[id];
+        }
+        __syncwarp();
+        if (!PRED || active) {
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp) {
+                const double2 v = reinterpret_cast<const double2*>(sb)[cp];
                 al[2 * cp] = v.x;
                 al[2 * cp + 1] = v.y;
             }
@@ -443,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
         if (n == -2) continue;
         if (primary >= a.N) scan = (n + 1) % a.N;
         zip_build_dictionary<C, THREADS>(a, n, dict, sE, spi, dexp);
-        for (;;) {
+        for (; warp < a.active_warps;) {
             int unit = 0;
             if (lane == 0) unit = atomicAdd(a.point_next + n, 1);
             unit = __shfl_sync(0xffffffffu, unit, 0);

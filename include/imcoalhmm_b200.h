@@ -144,7 +144,8 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       returns IMC_ERR_UNSUPPORTED.
  * key "zip_ctas_per_sm": 1 = one persistent CTA per SM with all of shared memory for the dictionary, 2 = two CTAs of
  *                       256 threads with half each (K <= 24 only); 0 = auto.
- * key "zip_lanes":      lanes that share one chain's mat-vec in the zip kernel: 8, 4 (K >= 8) or 0 = auto.
+ * key "zip_lanes":      lanes that share one chain's mat-vec in the zip kernel: 8, 4 (K >= 8), 32 (K >= 10: one warp
+ *                       per chain, the lowest latency per step) or 0 = auto.
  * key "zip_segment_tokens": segmented mode of the zip kernel for chain-scarce calls (few chunks x few points): chunks
  *                       are cut into segments of this many tokens whose K x K transfer matrices are computed
  *                       column by column in parallel and folded afterwards.  0 = auto, -1 = never, > 0 = forced length.
@@ -160,7 +161,7 @@ int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t imc_kernel_launches(void);
 /* name of the forward kernel chosen by the last forward call on this thread
- * ("generic", "pair", "dmma", "zip", "zip-segmented") */
+ * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls) */
 const char* imc_last_forward_kernel(void);
 
 #ifdef __cplusplus

@@ -45,13 +45,18 @@ def test_example_alignment_reference_models():
     f = m.Forwarder.from_symbols(obs, 3)
     _, pi, T, E = golden_model("isolation_k10")
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3729.5586472699, rel=1e-11)
-    assert m.last_forward_kernel() == "zip-segmented"      # one chunk x one point: chain-scarce
+    assert m.last_forward_kernel() in ("zip-segmented", "zip-warp")      # one chunk x one point: chain-scarce
     _, pi, T, E = golden_model("im_k10_10")
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
-    assert m.last_forward_kernel() == "zip-segmented"
+    assert m.last_forward_kernel() in ("zip-segmented", "zip-warp")
     m.set_option("zip_segment_tokens", -1)
+    m.set_option("zip_lanes", 4)
     assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
     assert m.last_forward_kernel() == "zip"
+    m.set_option("zip_lanes", 32)
+    assert f.forward(pi[0], T[0], E[0]) == pytest.approx(-3650.0493084297, rel=1e-11)
+    assert m.last_forward_kernel() == "zip-warp"
+    m.set_option("zip_lanes", 0)
     for code, name in ((2, "pair"), (3, "dmma")):
         m.set_option("forward_kernel", code)
         _, pi, T, E = golden_model("isolation_k10")
@@ -135,7 +140,7 @@ def test_zip_kernel_any_K_up_to_40(K):
     s = make_set(chunks)
     assert s.forward(pis[0], Ts[0], Es[0]) == pytest.approx(want[0], rel=RTOL)
     assert m.last_forward_kernel().startswith("zip")               # the default for every K <= 40
-    for lanes in (8, 4):
+    for lanes in (8, 4, 32):
         for seg in (-1, 64):
             m.set_option("zip_lanes", lanes)
             m.set_option("zip_segment_tokens", seg)
@@ -247,7 +252,7 @@ def test_zip_kernel_configurations(K):
     want = oracle_batch(chunks, pis, Ts, Es)
     s = make_set(chunks)
     m.set_option("forward_kernel", 4)
-    for lanes, ctas, cap in ((0, 0, 0), (8, 1, 0), (8, 2, 16), (4, 1, 3), (4, 2, 4), (4, 0, 64), (8, 0, 5), (4, 1, 0)):
+    for lanes, ctas, cap in ((0, 0, 0), (8, 1, 0), (8, 2, 16), (4, 1, 3), (4, 2, 4), (4, 0, 64), (8, 0, 5), (4, 1, 0), (32, 0, 0), (32, 0, 7)):
         m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)
         m.set_option("zip_max_entries", cap)
@@ -287,7 +292,7 @@ def test_zip_segmented_mode(model):
     s = make_set(chunks)
     m.set_option("zip_segment_tokens", -1)
     base = s.forward_batch(pis[:3], Ts[:3], Es[:3])
-    assert m.last_forward_kernel() == "zip"
+    assert m.last_forward_kernel() in ("zip", "zip-warp")
     np.testing.assert_allclose(base, want, rtol=RTOL)
     for lanes in (8, 4):
         m.set_option("zip_lanes", lanes)

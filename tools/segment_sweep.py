@@ -20,12 +20,14 @@ for name, nchunks, clen in (("c2", 100, 0), ("c2", 1, 100_000_000), ("c3_1gpu", 
     pi, T, E = model.build_hidden_markov_model(theta)
     chunks = bench.make_chunks(wl, pi[None], T[None], E[None], range(wl["chunks"]))
     fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
-    out = []
-    for seg in (-1, 0, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096):
-        m.set_option("zip_segment_tokens", seg)
-        fset.forward(pi, T, E)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            fset.forward(pi, T, E)
-        out.append("%d:%.3f" % (seg, (time.perf_counter() - t0) * 100))
-    print(name, nchunks, wl["chunk_len"], "K=%d" % wl["K"], " ".join(out), flush=True)
+    for lanes in (0, 32):
+        m.set_option("zip_lanes", lanes)
+        out = []
+        for seg in ((-1, 0, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096) if lanes == 0 else (-1, 1024, 2048, 4096, 8192)):
+            m.set_option("zip_segment_tokens", seg)
+            v = fset.forward(pi, T, E)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                fset.forward(pi, T, E)
+            out.append("%d:%.3f" % (seg, (time.perf_counter() - t0) * 100))
+        print(name, nchunks, wl["chunk_len"], "K=%d lanes=%d logL=%.6f" % (wl["K"], lanes, v), " ".join(out), flush=True)

@@ -54,6 +54,9 @@ _SIGNATURES = {
                                          c_f64p]),
     "imc_forward_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp,
                                              c_vp]),
+    "imc_comm_unique_id": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "imc_comm_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp]),
+    "imc_comm_destroy": (ctypes.c_int, []),
     "imc_model_create": (ctypes.c_int, [ctypes.c_int, c_i32p, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "imc_model_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "imc_model_destroy": (ctypes.c_int, [c_vp]),
@@ -112,6 +115,22 @@ def measure_fp64_peak():
     a, b = ctypes.c_double(), ctypes.c_double()
     check(load().imc_measure_fp64_peak(ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+def comm_unique_id():
+    """128 opaque bytes drawn by rank 0; hand them to every other rank (file, pipe, MPI, torch.distributed...)."""
+    buf = ctypes.create_string_buffer(128)
+    check(load().imc_comm_unique_id(buf, 128))
+    return buf.raw
+
+
+def comm_init(nranks, rank, unique_id=None):
+    """After imc_init(device): from now on every forward / likelihood call returns the sum over ranks (one all-reduce)."""
+    check(load().imc_comm_init(int(nranks), int(rank), ctypes.c_char_p(unique_id) if unique_id is not None else None))
+
+
+def comm_destroy():
+    check(load().imc_comm_destroy())
 
 
 def kernel_launches():

@@ -104,6 +104,17 @@ int imc_forward_batch(imc_seqset* set, int N, int K, int S, const double* pi, co
 int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T,
                           const double* d_E, double* d_out, void* stream);
 
+/* ---- multi-GPU (one process per GPU): chunks are sharded over the ranks, every rank scores the same parameter batch on
+ * its own sequence set, and once a communicator exists every forward / loglik entry point above and below returns the SUM
+ * over ranks -- one ncclAllReduce of float64[N] per batch, the only collective of the path (likelihood.py:33 sums over
+ * forwarders; here the forwarders live on different GPUs).  Rank 0 draws the id and hands its bytes to the other ranks by
+ * any means (file, pipe, MPI, torch.distributed); all ranks then call imc_comm_init after imc_init(device).  NCCL is
+ * loaded with dlopen at that point (no link-time dependency). */
+#define IMC_COMM_ID_BYTES 128
+int imc_comm_unique_id(void* id_out, int capacity);
+int imc_comm_init(int nranks, int rank, const void* nccl_id);
+int imc_comm_destroy(void);
+
 /* ---- batched model build: theta -> (pi, T, E) on the GPU ----------------------------------------------
  * Replaces Model.build_hidden_markov_model (model.py:44-49) and everything under it (state_spaces.py, CTMC.py,
  * transitions.py, emissions.py, break_points.py and the model files) for N parameter points per call.

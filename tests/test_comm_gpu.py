@@ -1,0 +1,68 @@
+"""The library's own all-reduce (imc_comm_init): two processes, one GPU each, chunks sharded between them;
+every forward / likelihood entry point must return the sum over ranks.  Needs two GPUs (skipped otherwise)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import golden_model, example_symbols
+
+pytestmark = pytest.mark.gpu
+
+
+def _rank(rank, world, tmp, lengths):
+    import imcoalhmm_b200 as m
+    lib = m._lib.load()
+    m._lib.check(lib.imc_init(rank))
+    idfile = os.path.join(tmp, "nccl_id")
+    if rank == 0:
+        uid = m._lib.comm_unique_id()
+        with open(idfile + ".tmp", "wb") as f:
+            f.write(uid)
+        os.rename(idfile + ".tmp", idfile)
+    else:
+        for _ in range(600):
+            if os.path.exists(idfile):
+                break
+            time.sleep(0.1)
+        uid = open(idfile, "rb").read()
+    m._lib.comm_init(world, rank, uid)
+    theta, pis, Ts, Es = golden_model("isolation_k10")
+    obs = example_symbols()
+    cuts = np.concatenate([[0], np.cumsum(lengths)])
+    mine = [obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths)) if c % world == rank]
+    fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in mine])
+    a = fset.forward_batch(pis[:6], Ts[:6], Es[:6])                       # host arrays in, summed over ranks
+    b = m.IsolationModel(10).batched_log_likelihood(theta[:6], fset)      # fused theta -> logL, summed over ranks
+    c = fset.forward(pis[2], Ts[2], Es[2])                                # chain-scarce single point
+    np.save(os.path.join(tmp, "out%d.npy" % rank), np.concatenate([a, b, [c]]))
+    m._lib.comm_destroy()
+
+
+def test_native_allreduce_sums_over_two_gpus(tmp_path):
+    import ctypes
+    import imcoalhmm_b200 as m
+    n = ctypes.c_int()
+    m._lib.load().imc_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    import multiprocessing as mp
+    from oracle import forward as F
+    lengths = [9000, 1, 14000, 8000, 12000, 254, 22000]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_rank, args=(r, 2, str(tmp_path), lengths)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    obs = example_symbols().astype(np.int32)
+    cuts = np.concatenate([[0], np.cumsum(lengths)])
+    want, _ = F.forward_batch([obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths))], pis[:6], Ts[:6], Es[:6])
+    for r in range(2):
+        got = np.load(tmp_path / ("out%d.npy" % r))
+        np.testing.assert_allclose(got[:6], want, rtol=1e-11)
+        np.testing.assert_allclose(got[6:12], want, rtol=1e-9)      # GPU-built (pi,T,E) vs reference-built fixture
+        assert got[12] == pytest.approx(want[2], rel=1e-11)

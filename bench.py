@@ -45,6 +45,11 @@ WORKLOADS = {
     "c3_1gpu": dict(model="im_k10_10", ctor=("IsolationMigrationModel", (10, 10)),
                     default=[1e-3, 1e-3, 2000.0, 0.4, 200.0], K=20, chunks=125, chunk_len=1_000_000, points=1024,
                     desc="configs[2] per-GPU shard: IM model K=10+10, 125 x 1 Mbp chunks, 1024 parameter points"),
+    # per-GPU slice of configs[3] (isolation-model-mcmc, 4096 lock-step chains, 3 Gbp on 8 GPUs = 375 chunks/GPU): one step
+    # = one proposal of every chain scored in one batched call (imcoalhmm_b200.mcmc.BatchedMCMC.step)
+    "c4_1gpu": dict(model="isolation_k10", ctor=("IsolationModel", (10,)), default=[1e-3, 2000.0, 0.4], K=10,
+                    chunks=375, chunk_len=1_000_000, points=4096,
+                    desc="configs[3] per-GPU shard: isolation model K=10, 375 x 1 Mbp chunks, 4096 MCMC proposals per step"),
     # per-GPU slice of configs[4] (psmc-style isolation model, 40 intervals, 3 Gbp, 1024 points on 8 GPUs = 375 chunks/GPU)
     "c5_1gpu": dict(model="psmc_iso_split_4x10", ctor=("VariableCoalescenceRateIsolationModel", ([4] * 10, True)),
                     default=[1e-3] + [1000.0] * 10 + [0.4], K=40, chunks=375, chunk_len=1_000_000, points=1024,

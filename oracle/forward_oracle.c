@@ -229,10 +229,108 @@ double imco_zip_forward(const double* pi, const double* T, const double* E, cons
     return logl;
 }
 
+/* ---------------------------------------------------------------- zip forward, tuned for the timed CPU arm ----
+ * Same algorithm as imco_zip_forward, written the way a performance-minded C implementation would be, so that the
+ * CPU baseline bench.py reports is not an artificially slow one: symbol matrices stored column-major so that the
+ * mat-vec and the pair products vectorise without reassociation (independent accumulators per row), rescaling by
+ * exact powers of two every 8 symbols with an integer exponent (no division and no log per symbol).
+ * tests/test_oracle_forward.py holds it to the plain and the simple zip forward. */
+typedef struct { int K; double* M; long long* ex; } zipfast;   /* M[s][k][r] = C_s[r][k] / 2^ex_s */
+
+static long long fast_normalise(double* M, int n)
+{
+    double mx = 0.0;
+    for (int x = 0; x < n; ++x) if (M[x] > mx) mx = M[x];
+    if (!(mx > 0.0) || !(mx < 1.7e308)) return 0;
+    int e;
+    frexp(mx, &e);
+    const double f = ldexp(1.0, -e);
+    for (int x = 0; x < n; ++x) M[x] *= f;
+    return e;
+}
+
+double imco_zip_forward_fast(const double* pi, const double* T, const double* E, const int32_t* sym2pair,
+                             const int32_t* new_obs, int64_t newL, int nsym, int new_nsyms, int K)
+{
+    if (newL <= 0) return 0.0;
+    const int KK = K * K;
+    zipfast z;
+    z.K = K;
+    z.M = (double*)malloc(sizeof(double) * (size_t)new_nsyms * KK);
+    z.ex = (long long*)malloc(sizeof(long long) * (size_t)new_nsyms);
+    for (int s = 0; s < nsym; ++s) {          /* C_s[r][k] = E[r][s] T[k][r], stored [k][r] */
+        double* M = z.M + (size_t)s * KK;
+        for (int k = 0; k < K; ++k)
+            for (int r = 0; r < K; ++r) M[k * K + r] = E[(size_t)r * nsym + s] * T[(size_t)k * K + r];
+        z.ex[s] = fast_normalise(M, KK);
+    }
+    for (int s = nsym; s < new_nsyms; ++s) {  /* C_(a,b) = C_b C_a:  out[:,c] = sum_k C_b[:,k] C_a[k,c] */
+        const int a = sym2pair[2 * (s - nsym)], b = sym2pair[2 * (s - nsym) + 1];
+        const double* A = z.M + (size_t)a * KK;
+        const double* B = z.M + (size_t)b * KK;
+        double* M = z.M + (size_t)s * KK;
+        for (int c = 0; c < K; ++c) {
+            double* out = M + c * K;
+            for (int r = 0; r < K; ++r) out[r] = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double w = A[c * K + k];            /* C_a[k][c] */
+                const double* col = B + k * K;            /* C_b[:, k] */
+                for (int r = 0; r < K; ++r) out[r] += col[r] * w;
+            }
+        }
+        z.ex[s] = z.ex[a] + z.ex[b] + fast_normalise(M, KK);
+    }
+    double* v = (double*)malloc(sizeof(double) * 2 * (size_t)K);
+    double* tmp = v + K;
+    long long scale = 0;
+    int dead = 0;
+    /* the first (possibly compound) symbol: walk its left spine down to a raw symbol, then apply the right parts */
+    int* stack = (int*)malloc(sizeof(int) * (size_t)(new_nsyms + 1));
+    int sp = 0, s0 = new_obs[0];
+    while (s0 >= nsym) { stack[sp++] = sym2pair[2 * (s0 - nsym) + 1]; s0 = sym2pair[2 * (s0 - nsym)]; }
+    for (int j = 0; j < K; ++j) v[j] = pi[j] * E[(size_t)j * nsym + s0];
+    int64_t t = 1;
+    int pending = sp;
+    for (int count = 0;; ++count) {
+        int s;
+        if (pending > 0) s = stack[--pending];
+        else if (t < newL) s = new_obs[t++];
+        else break;
+        const double* M = z.M + (size_t)s * KK;
+        for (int r = 0; r < K; ++r) tmp[r] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double w = v[k];
+            const double* col = M + k * K;
+            for (int r = 0; r < K; ++r) tmp[r] += col[r] * w;
+        }
+        scale += z.ex[s];
+        double* sw = v; v = tmp; tmp = sw;
+        if ((count & 7) == 7) {
+            double c = 0.0;
+            for (int r = 0; r < K; ++r) c += v[r];
+            if (c > 0.0 && c < 1.7e308) {
+                int e;
+                frexp(c, &e);
+                const double f = ldexp(1.0, -e);
+                for (int r = 0; r < K; ++r) v[r] *= f;
+                scale += e;
+            } else if (!(c > 0.0)) { dead = 1; }
+        }
+    }
+    double c = 0.0;
+    for (int r = 0; r < K; ++r) c += v[r];
+    const double result = (dead || !(c > 0.0)) ? (c != c ? c : -INFINITY) : log(c) + (double)scale * 0.693147180559945309417232121458;
+    free(v < tmp ? v : tmp);
+    free(stack);
+    free(z.M); free(z.ex);
+    return result;
+}
+
 /* ---------------------------------------------------------------- batched CPU baseline ------
  * out[n] = sum_c forward(seq_c; pi_n, T_n, E_n) -- what likelihood.py:33 computes for each of N
  * parameter points, fanned out over the host cores (one (n, c) pair per task).  mode 0 = plain,
- * mode 1 = zip (sequences already preprocessed: obs[c] is new_obs, pairs[c]/nsyms[c] its tables). */
+ * mode 1 = zip (sequences already preprocessed: obs[c] is new_obs, pairs[c]/nsyms[c] its tables),
+ * mode 2 = the same through imco_zip_forward_fast (the timed CPU arm). */
 int imco_forward_batch(int mode, int C, const int32_t* const* obs, const int64_t* lens,
                        const int32_t* const* pairs, const int* nsyms, int nsym,
                        int N, int K, const double* pi, const double* T, const double* E,
@@ -249,9 +347,9 @@ int imco_forward_batch(int mode, int C, const int32_t* const* obs, const int64_t
         const double* pin = pi + (size_t)n * K;
         const double* Tn = T + (size_t)n * K * K;
         const double* En = E + (size_t)n * K * nsym;
-        part[task] = mode == 0
-            ? imco_forward_plain(obs[c], lens[c], K, nsym, pin, Tn, En)
-            : imco_zip_forward(pin, Tn, En, pairs[c], obs[c], lens[c], nsym, nsyms[c], K);
+        part[task] = mode == 0 ? imco_forward_plain(obs[c], lens[c], K, nsym, pin, Tn, En)
+                   : mode == 1 ? imco_zip_forward(pin, Tn, En, pairs[c], obs[c], lens[c], nsym, nsyms[c], K)
+                               : imco_zip_forward_fast(pin, Tn, En, pairs[c], obs[c], lens[c], nsym, nsyms[c], K);
     }
     for (int n = 0; n < N; ++n) {
         double s = 0.0;

@@ -74,3 +74,35 @@ def test_zip_equals_plain_and_chunk_additivity():
     zipped = [F.zip_preprocess(c, 3) for c in chunks]
     outz, _ = F.forward_batch(None, pi[:4], T[:4], E[:4], mode="zip", zipped=zipped)
     np.testing.assert_allclose(outz, want, rtol=1e-12)
+
+
+def test_tuned_zip_forward_matches_the_simple_one():
+    """bench.py times imco_zip_forward_fast; it must be the same function as the simple restatement."""
+    import numpy as np
+    from conftest import golden_model, example_symbols
+    from oracle import forward as F
+    obs = example_symbols().astype(np.int32)
+    for name in ("isolation_k10", "im_k10_10", "isolation_k4"):
+        _, pis, Ts, Es = golden_model(name)
+        for max_syms in (3, 4, 64, 1024):
+            new_obs, s2p, ns = F.zip_preprocess(obs, 3, max_syms=max_syms)
+            want = F.forward_plain(obs, pis[1], Ts[1], Es[1])
+            assert abs(F.zip_forward_fast(pis[1], Ts[1], Es[1], s2p, new_obs, 3, ns) - want) <= 1e-11 * abs(want)
+            assert abs(F.zip_forward(pis[1], Ts[1], Es[1], s2p, new_obs, 3, ns) - want) <= 1e-11 * abs(want)
+        # compound first symbol, tiny inputs, impossible observation
+        for n in (1, 2, 3, 17):
+            new_obs, s2p, ns = F.zip_preprocess(obs[:n], 3, min_count=2, max_syms=8)
+            want = F.forward_plain(obs[:n], pis[0], Ts[0], Es[0])
+            assert abs(F.zip_forward_fast(pis[0], Ts[0], Es[0], s2p, new_obs, 3, ns) - want) <= 1e-12 * max(1.0, abs(want))
+    rep = np.tile(np.array([0, 0, 0, 0], dtype=np.int32), 64)
+    new_obs, s2p, ns = F.zip_preprocess(rep, 3, min_count=2, max_syms=16)
+    assert new_obs[0] >= 3                                    # the whole sequence starts with a compound symbol
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    want = F.forward_plain(rep, pis[0], Ts[0], Es[0])
+    assert abs(F.zip_forward_fast(pis[0], Ts[0], Es[0], s2p, new_obs, 3, ns) - want) <= 1e-12 * abs(want)
+    E0 = Es[0].copy()
+    E0[:, 1] = 0.0
+    bad = rep.copy()
+    bad[100] = 1
+    new_obs, s2p, ns = F.zip_preprocess(bad, 3, min_count=2, max_syms=16)
+    assert F.zip_forward_fast(pis[0], Ts[0], E0, s2p, new_obs, 3, ns) == -np.inf

@@ -249,8 +249,8 @@ static long long fast_normalise(double* M, int n)
     return e;
 }
 
-double imco_zip_forward_fast(const double* pi, const double* T, const double* E, const int32_t* sym2pair,
-                             const int32_t* new_obs, int64_t newL, int nsym, int new_nsyms, int K)
+static inline __attribute__((always_inline)) double zip_fast_impl(const double* pi, const double* T, const double* E, const int32_t* sym2pair,
+                                                              const int32_t* new_obs, int64_t newL, int nsym, int new_nsyms, const int K)
 {
     if (newL <= 0) return 0.0;
     const int KK = K * K;
@@ -324,6 +324,33 @@ double imco_zip_forward_fast(const double* pi, const double* T, const double* E,
     free(stack);
     free(z.M); free(z.ex);
     return result;
+}
+
+/* state counts of the benchmark configurations get their own copy with K known at compile time, so that the compiler
+ * unrolls and vectorises the length-K loops (what a hand-tuned implementation would do) */
+#define ZIP_FAST_K(KC)                                                                                                  \
+    static double zip_fast_k##KC(const double* pi, const double* T, const double* E, const int32_t* sym2pair,            \
+                                 const int32_t* new_obs, int64_t newL, int nsym, int new_nsyms)                          \
+    { return zip_fast_impl(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms, KC); }
+ZIP_FAST_K(4)
+ZIP_FAST_K(8)
+ZIP_FAST_K(10)
+ZIP_FAST_K(16)
+ZIP_FAST_K(20)
+ZIP_FAST_K(40)
+
+double imco_zip_forward_fast(const double* pi, const double* T, const double* E, const int32_t* sym2pair,
+                             const int32_t* new_obs, int64_t newL, int nsym, int new_nsyms, int K)
+{
+    switch (K) {
+        case 4: return zip_fast_k4(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+        case 8: return zip_fast_k8(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+        case 10: return zip_fast_k10(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+        case 16: return zip_fast_k16(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+        case 20: return zip_fast_k20(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+        case 40: return zip_fast_k40(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms);
+    }
+    return zip_fast_impl(pi, T, E, sym2pair, new_obs, newL, nsym, new_nsyms, K);
 }
 
 /* ---------------------------------------------------------------- batched CPU baseline ------

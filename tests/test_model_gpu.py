@@ -118,3 +118,34 @@ def test_survey_spot_values():
     # detailed balance (J symmetric, transitions.py:237)
     flux = pi[:, None] * T
     assert np.abs(flux - flux.T).max() < 1e-18
+
+
+def test_batched_callers_drive_the_gpu_likelihood():
+    """mcmc.BatchedMCMC / MC3 / ParticleSwarm on a real Likelihood: one batched GPU call per step, same numbers as the
+    one-theta-at-a-time reference pattern (likelihood.py:27-33)."""
+    import imcoalhmm_b200 as m
+    from imcoalhmm_b200.mcmc import BatchedMCMC, ExpLogNormPrior, LogNormPrior, MC3, ParticleSwarm
+    from conftest import example_symbols
+    obs = example_symbols()
+    lik = m.Likelihood(m.IsolationModel(10), [m.Forwarder.from_symbols(obs[:30000], 3), m.Forwarder.from_symbols(obs[30000:], 3)])
+    priors = [LogNormPrior(np.log(1e-3)), ExpLogNormPrior(2000.0), ExpLogNormPrior(0.4)]
+    chains = BatchedMCMC(priors, lik, thinning=3, no_chains=32, rng=np.random.default_rng(0))
+    before = m.kernel_launches()
+    theta, prior, like, post = chains.sample()
+    assert chains.likelihood_calls == 4 and m.kernel_launches() - before <= 3 * 8
+    assert np.isfinite(like).all() and np.allclose(post, prior + like)
+    # each chain's stored likelihood is what the scalar reference-style call returns for its theta
+    for i in (0, 7, 31):
+        assert lik(theta[i]) == pytest.approx(like[i], rel=1e-11)
+    # invalid proposals (a non-positive parameter) score -inf and are rejected, as in likelihood.py:29-30
+    bad = theta.copy()
+    bad[::2, 1] = -1.0
+    out = lik.batched(bad)
+    assert np.isneginf(out[::2]).all() and np.isfinite(out[1::2]).all()
+    mc3 = MC3(priors, lik, no_chains=4, thinning=4, switching=2, temperature_scale=2.0, rng=np.random.default_rng(1))
+    th, pr, li, po = mc3.sample()
+    assert th.shape == (3,) and np.isfinite(po)
+    pso = ParticleSwarm(particle_count=16, max_iterations=5, rng=np.random.default_rng(2))
+    scale = np.array([2e-3, 4000.0, 0.8])
+    pos, fit, it = pso.maximise(lik, 3, transform=lambda p: np.clip(p, 1e-3, None) * scale)
+    assert it == 5 and np.isfinite(fit) and fit > -5000.0

@@ -5,6 +5,7 @@ Public surface (mirrors /root/reference/src/IMCoalHMM for this path only):
     Forwarder.fromSequence / Forwarder.fromDirectory                      legacy pyZipHMM constructors
     ForwarderSet(forwarders).forward / .forward_batch                     likelihood.py:33, batched
     Likelihood(model, forwarders)(theta) / .batched(thetas)               likelihood.py:8-33
+    maximum_likelihood_estimate(log_likelihood, initial_parameters, ...)  likelihood.py:36-87
     ziphmm.preprocess_raw_observations / ziphmm.zip_forward               hmm.py:16,20-21
     mcmc.BatchedMCMC / mcmc.MC3 / mcmc.ParticleSwarm                      mcmc.py, particle_swarm.py, one batched call per step
 
@@ -17,13 +18,13 @@ _lib.load()   # fail loudly at import time if the CUDA library is missing
 
 from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel, measure_fp64_peak  # noqa: E402
 from .hmm import Forwarder, ForwarderSet  # noqa: E402
-from .likelihood import Likelihood  # noqa: E402
+from .likelihood import Likelihood, maximum_likelihood_estimate  # noqa: E402
 from .models import (Model, IsolationModel, IsolationMigrationModel, VariableCoalescenceRateIsolationModel,  # noqa: E402
                      VariableCoalAndMigrationRateModel, IsolationMigrationEpochsModel)
 from . import ziphmm  # noqa: E402
 from . import mcmc  # noqa: E402
 
-__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "IMCError", "ziphmm", "mcmc", "Model", "IsolationModel",
+__all__ = ["Forwarder", "ForwarderSet", "Likelihood", "maximum_likelihood_estimate", "IMCError", "ziphmm", "mcmc", "Model", "IsolationModel",
            "IsolationMigrationModel", "VariableCoalescenceRateIsolationModel", "VariableCoalAndMigrationRateModel",
            "IsolationMigrationEpochsModel",
            "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak"]

@@ -50,3 +50,28 @@ class Likelihood(object):
                                                        np.stack([h[1] for h in hmms]),
                                                        np.stack([h[2] for h in hmms]))
         return out
+
+
+def maximum_likelihood_estimate(log_likelihood, initial_parameters, optimizer_method="Nelder-Mead", log_file=None,
+                                log_param_transform=lambda x: x):
+    """Maximum likelihood estimation with a scipy optimiser: same signature, options and logging as the reference
+    (likelihood.py:36-87; the scripts call it as `maximum_likelihood_estimate(log_likelihood, init, log_file=...)`).
+    Every objective evaluation is one fused theta -> logL call on the GPU (chain-scarce form)."""
+    import scipy.optimize
+    log_callback = None
+    if log_file:
+        def log_callback(parameters):
+            log_file.write("\t".join(str(param) for param in log_param_transform(parameters)) + "\n")
+
+    def minimize_wrapper(parameters):
+        return -log_likelihood(np.asarray(parameters, dtype=np.float64))
+
+    options = {"disp": False}
+    if optimizer_method in ["Anneal", "L-BFGS-B", "TNC", "SLSQP"]:       # likelihood.py:76-80: positivity bounds
+        bounds = [(0, None)] * len(initial_parameters)
+        result = scipy.optimize.minimize(fun=minimize_wrapper, x0=initial_parameters, method=optimizer_method, bounds=bounds,
+                                         callback=log_callback, options=options)
+    else:
+        result = scipy.optimize.minimize(fun=minimize_wrapper, x0=initial_parameters, method=optimizer_method,
+                                         callback=log_callback, options=options)
+    return result.x

@@ -902,6 +902,15 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         // zip wherever its dictionary fits; large alphabets x large K that do not fit fall back to the per-site kernels
         if (zip_supported(K) && (zip_plan(K, S, set->merges.size(), &probe) == IMC_OK || !set->packable)) which = KERNEL_ZIP;
         else which = pair_supported(K) ? KERNEL_PAIR : (dmma_supported(K) ? KERNEL_DMMA : KERNEL_GENERIC);
+        // An alignment that hardly compresses (random-looking symbols) is scored faster by the per-site kernels, which
+        // keep T in registers and run at the FP64 rate: per chain-step the zip kernel pays ~14 / 35 / 135 SM clocks
+        // (K = 10 / 20 / 40) against ~3 / 10 / 31 per site for the pair / DMMA kernels, so below ~5 sites per token
+        // -- and with enough chains to fill the machine -- the per-site kernel wins.
+        if (which == KERNEL_ZIP && set->packable && (pair_supported(K) || dmma_supported(K)) && (long long)N * ns >= 4096) {
+            ZipDevice* zp = nullptr;
+            if (zip_device(set, probe.M, &zp) == IMC_OK && zp->total_tokens * 5 > set->total_sites)
+                which = pair_supported(K) ? KERNEL_PAIR : KERNEL_DMMA;
+        }
     }
     if (which == KERNEL_ZIP) {
         ZipPlan plan;

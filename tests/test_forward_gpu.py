@@ -345,3 +345,24 @@ def test_ziphmm_module_contract():
     # a genuinely pair-compressed encoding produced elsewhere is accepted too
     z_obs, z_pairs, z_n = F.zip_preprocess(obs, 3)
     assert ziphmm.zip_forward(pis[0], Ts[0], Es[0], z_pairs, z_obs, 3, z_n) == pytest.approx(want, rel=RTOL)
+
+
+def test_auto_selection_prefers_per_site_kernels_on_incompressible_data():
+    """Random-looking symbols do not compress; with many chains the per-site kernels are the faster route and the
+    automatic choice switches to them (same numbers either way)."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(11)
+    _, pis, Ts, Es = golden_model("isolation_k10")
+    chunks = [rng.integers(0, 3, size=3000).astype(np.uint8) for _ in range(300)]
+    s = make_set(chunks)
+    assert s.zip_info(10)["tokens"] * 5 > s.total_sites
+    got = s.forward_batch(pis, Ts, Es)                      # 16 points x 300 chunks = 4800 chains
+    assert m.last_forward_kernel() == "pair"
+    m.set_option("forward_kernel", 4)
+    np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), got, rtol=1e-11)
+    assert m.last_forward_kernel().startswith("zip")
+    m.set_option("forward_kernel", 0)
+    np.testing.assert_allclose(got, oracle_batch(chunks, pis, Ts, Es), rtol=RTOL)
+    comp = make_set([rng.choice(3, size=3000, p=[0.97, 0.01, 0.02]).astype(np.uint8) for _ in range(300)])
+    comp.forward_batch(pis, Ts, Es)
+    assert m.last_forward_kernel().startswith("zip")       # compressible: stays on the zip kernel

@@ -26,8 +26,18 @@ def _as_f64(a, shape_tail, what):
     return a
 
 
+def _from_legacy_matrix(x):
+    """pyZipHMM.Matrix objects (getHeight / getWidth / [i, j]) as used by the reference's legacy callers
+    (ILS.py:271-276, isolation_model.py:131-146) -> ndarray; anything else is returned unchanged."""
+    if hasattr(x, "getHeight") and hasattr(x, "getWidth"):
+        h, w = int(x.getHeight()), int(x.getWidth())
+        return np.array([[float(x[i, j]) for j in range(w)] for i in range(h)], dtype=np.float64)
+    return x
+
+
 def _hmm_arrays(pis, Ts, Es, batched):
     """Normalise (pi, T, E) to contiguous float64 arrays [N,K], [N,K,K], [N,K,S]."""
+    pis, Ts, Es = _from_legacy_matrix(pis), _from_legacy_matrix(Ts), _from_legacy_matrix(Es)
     Ts = np.ascontiguousarray(np.asarray(Ts, dtype=np.float64))
     if not batched:
         Ts = Ts[None]

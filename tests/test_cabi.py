@@ -83,3 +83,26 @@ def test_no_cpu_fallback_without_device(have_gpu):
     with pytest.raises(m.IMCError) as e:
         f.forward(np.ones(2) / 2, np.ones((2, 2)) / 2, np.ones((2, 3)) / 3)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_legacy_matrix_objects_are_accepted():
+    """pyZipHMM.Matrix-style arguments (getHeight/getWidth/[i,j]; ILS.py:271-276) are converted like ndarrays."""
+    from imcoalhmm_b200.hmm import _hmm_arrays
+
+    class Matrix(object):
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=float)
+
+        def getHeight(self):
+            return self.a.shape[0]
+
+        def getWidth(self):
+            return self.a.shape[1]
+
+        def __getitem__(self, ij):
+            return self.a[ij]
+    rng = np.random.default_rng(0)
+    pi, T, E = rng.random((4, 1)), rng.random((4, 4)), rng.random((4, 3))
+    a = _hmm_arrays(Matrix(pi), Matrix(T), Matrix(E), batched=False)
+    b = _hmm_arrays(pi, T, E, batched=False)
+    assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3:] == b[3:] == (1, 4, 3)

@@ -136,7 +136,8 @@ struct imc_seqset {
     int fold_sym = 0;                     // most frequent symbol over the whole set
     // host-side packed layout (plain kernels)
     bool packable = false;                // nsym <= 3
-    std::vector<uint32_t> words;          // bundles of 32 streams, word-interleaved, 16 two-bit symbols per word
+    std::vector<uint32_t> words;          // bundles of 32 streams, word-interleaved, 16 two-bit symbols per word (lazy)
+    long long n_words = 0;
     std::vector<StreamInfo> streams;      // non-empty chunks only, sorted by length (descending)
     // host-side compressed layout (zip kernel): one dictionary for the whole set, tokens per non-empty chunk
     ZipMerges merges;
@@ -443,31 +444,21 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
                 set->first_sym[k] = sy[0];
                 zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
             })) throw std::bad_alloc();
+        // stream geometry of the packed 2-bit layout; the words themselves are built on first use (seqset_pack)
         for (int b0 = 0; set->packable && b0 < ns; b0 += 32) {
             const int nb = std::min(32, ns - b0);
-            const long long maxlen = (long long)seqs[order[b0]]->sym.size();
-            const long long nwords = (maxlen + 15) / 16;
-            set->words.resize((size_t)(word_off + nwords * 32), 0xffffffffu);   // code 3 everywhere = padding
+            const long long nwords = ((long long)seqs[order[b0]]->sym.size() + 15) / 16;
             for (int k = 0; k < nb; ++k) {
-                const imc_seq* sq = seqs[order[b0 + k]];
-                const long long len = (long long)sq->sym.size();
+                const long long len = (long long)seqs[order[b0 + k]]->sym.size();
                 StreamInfo& si = set->streams[b0 + k];
                 si.base = word_off + k;
                 si.len = (int)len;
                 si.nwords = (int)((len + 15) / 16);
-                for (long long w = 0; w < si.nwords; ++w) {
-                    uint32_t v = 0xffffffffu;
-                    const long long t0 = w * 16, t1 = std::min(len, t0 + 16);
-                    for (long long t = t0; t < t1; ++t) {
-                        const int sh = 2 * (int)(t - t0);
-                        v = (v & ~(3u << sh)) | ((uint32_t)sq->sym[(size_t)t] << sh);
-                    }
-                    set->words[(size_t)(word_off + w * 32 + k)] = v;
-                }
             }
             word_off += nwords * 32;
         }
-    } catch (...) { delete set; return fail(IMC_ERR_NOMEM, "out of host memory while packing"); }
+        set->n_words = word_off;
+    } catch (...) { delete set; return fail(IMC_ERR_NOMEM, "out of host memory while preprocessing"); }
     *out = set;
     return IMC_OK;
 }
@@ -496,7 +487,30 @@ extern "C" int imc_seqset_info(const imc_seqset* set, int* n_chunks, int64_t* to
     if (!set) return fail(IMC_ERR_INVALID, "NULL set");
     if (n_chunks) *n_chunks = set->n_chunks;
     if (total_sites) *total_sites = set->total_sites;
-    if (packed_bytes) *packed_bytes = (int64_t)(set->words.size() * sizeof(uint32_t));
+    if (packed_bytes) *packed_bytes = (int64_t)(set->n_words * (long long)sizeof(uint32_t));
+    return IMC_OK;
+}
+
+// The packed layout of the per-site kernels, rebuilt from the token streams (the set keeps no copy of the raw symbols):
+// word w of stream k sits at base + 32 w, symbol t of the word in bits 2 (t % 16)..; code 3 = padding.
+static int seqset_pack(imc_seqset* set) {
+    if (!set->words.empty() || set->n_words == 0) return IMC_OK;
+    try {
+        set->words.assign((size_t)set->n_words, 0xffffffffu);
+        const int ns = (int)set->streams.size();
+        if (!parallel_for(ns, [&](int k) {
+                std::vector<uint8_t> sym;
+                zip_expand(set->merges, set->tok_full[k], set->nsym, sym);
+                const StreamInfo& si = set->streams[k];
+                auto put = [&](long long t, uint8_t v) {
+                    uint32_t& w = set->words[(size_t)(si.base + (t >> 4) * 32)];
+                    const int sh = 2 * (int)(t & 15);
+                    w = (w & ~(3u << sh)) | ((uint32_t)v << sh);
+                };
+                put(0, set->first_sym[k]);
+                for (size_t t = 0; t < sym.size(); ++t) put((long long)t + 1, sym[t]);
+            })) throw std::bad_alloc();
+    } catch (...) { set->words.clear(); return fail(IMC_ERR_NOMEM, "out of host memory while packing"); }
     return IMC_OK;
 }
 
@@ -504,11 +518,13 @@ static int seqset_upload(imc_seqset* set) {
     if (set->uploaded) return IMC_OK;
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = seqset_pack(set))) return rc;
     if (!set->streams.empty()) {
         if ((rc = set->d_words.reserve(set->words.size() * sizeof(uint32_t)))) return rc;
         if ((rc = set->d_streams.reserve(set->streams.size() * sizeof(StreamInfo)))) return rc;
         CUDA_TRY(cudaMemcpy(set->d_words.p, set->words.data(), set->words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(set->d_streams.p, set->streams.data(), set->streams.size() * sizeof(StreamInfo), cudaMemcpyHostToDevice));
+        std::vector<uint32_t>().swap(set->words);      // the device copy is the only one needed from here on
     }
     set->uploaded = true;
     return IMC_OK;

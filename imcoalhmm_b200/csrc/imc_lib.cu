@@ -424,15 +424,20 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
     try {
         // ---- zipHMM-style preprocessing (hmm.py:16): learn the merges on a bounded prefix sample, encode every chunk
         {
+            // sample: up to 16 M symbols taken from chunks spread evenly over the set (not just the first ones)
             std::vector<std::vector<uint8_t>> sample;
-            long long budget = 16LL << 20;
-            for (int c = 0; c < C && budget > 0; ++c) {
-                const auto& sy = seqs[c]->sym;
-                if (sy.size() < 2) continue;
-                const size_t take = (size_t)std::min<long long>((long long)sy.size() - 1, budget);
-                sample.emplace_back(sy.begin() + 1, sy.begin() + 1 + take);
-                budget -= (long long)take;
-            }
+            const long long budget_total = 16LL << 20;
+            long long budget = budget_total;
+            const int stride = std::max(1, C / 32);
+            for (int start = 0; start < stride && budget > 0; ++start)
+                for (int c = start; c < C && budget > 0; c += stride) {
+                    const auto& sy = seqs[c]->sym;
+                    if (sy.size() < 2) continue;
+                    const long long share = budget_total / std::min(32, std::max(1, C));
+                    const size_t take = (size_t)std::min<long long>({(long long)sy.size() - 1, budget, share});
+                    sample.emplace_back(sy.begin() + 1, sy.begin() + 1 + take);
+                    budget -= (long long)take;
+                }
             set->merges = zip_learn(sample, set->nsym, 256, 16);
         }
         set->tok_full.resize(ns);

@@ -223,9 +223,61 @@ __device__ __forceinline__ void smem_matmul(const double* A, const double* B, do
         }
 }
 
+__device__ __forceinline__ void dmma884_acc(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C = A * B for 16 < n <= 96 on the FP64 tensor path (mma.sync.m8n8k4.f64): 8 warps, warp w owns the 3 x 6 block of
+// 8x8 output tiles at tile rows 3 (w/2).., tile columns 6 (w%2)..; per k-slice of 4 it loads 3 A fragments and 6 B
+// fragments (one double per lane each) for 18 DMMAs, i.e. 0.5 bytes of shared memory per FMA, so the FP64 pipe and
+// not the shared-memory pipe is the limit (the 6x6 register-tiled DFMA version moves 2.7 B/FMA and ran at ~22 % of peak).
+__device__ __forceinline__ void smem_matmul_dmma(const double* A, const double* B, double* C, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;                  // fragment coordinates
+    const int tr0 = (warp >> 1) * 3, tc0 = (warp & 1) * 6;
+    double acc[3][6][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int k0 = 0; k0 < n; k0 += 4) {
+        const int kk = k0 + q;
+        double a[3], b[6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int row = 8 * (tr0 + i) + g;
+            a[i] = (row < n && kk < n) ? A[row * n + kk] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int col = 8 * (tc0 + j) + g;
+            b[j] = (col < n && kk < n) ? B[kk * n + col] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) dmma884_acc(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int row = 8 * (tr0 + i) + g, col = 8 * (tc0 + j) + 2 * q;
+            if (row < n) {
+                if (col < n) C[row * n + col] = acc[i][j][0];
+                if (col + 1 < n) C[row * n + col + 1] = acc[i][j][1];
+            }
+        }
+}
+
 __device__ __forceinline__ void smem_matmul_n(const double* A, const double* B, double* C, int n) {
     if (n <= 16) smem_matmul<1>(A, B, C, n);
+#ifdef IMC_EXPM_DFMA
     else smem_matmul<6>(A, B, C, n);
+#else
+    else smem_matmul_dmma(A, B, C, n);
+#endif
 }
 
 constexpr int EXPM_TAYLOR_DEGREE = 14;      // lambda <= 0.5: tail < 0.5^15/15! = 2.3e-17

@@ -224,7 +224,7 @@ def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -309,14 +309,14 @@ def main():
             dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods
 
     peak_dfma, peak_dmma = m.measure_fp64_peak()
+    sampler = ClockSampler(local_rank)       # samples nvidia-smi every 200 ms from the warm-up steps to the end of the timed region
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     launches0 = m.kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = []
     for _ in range(args.steps):
         flush.fill_(1)

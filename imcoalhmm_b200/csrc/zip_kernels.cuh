@@ -83,6 +83,16 @@ struct ZipCfg8 {
     // chain slot g of a warp lets lanes of copy g % REP own the remainder rows, so that the four quarter-warps
     // of one LDS.128 touch different bank groups instead of all hitting groups 0..REM-1.
     static constexpr int REP = REM ? 8 / REM : 1;
+    // Two remainder rows (the K = 10 tile): their REP = 4 copies let ONE full load fetch the remainder rows of FOUR
+    // consecutive tokens -- lane pair j reads copy j of the matrix of token j of a 4-token word -- instead of one
+    // partly filled load per token (5 full loads per 4 tokens in place of 20 partial ones: -19 % shared-memory wavefronts).
+    // Pair j then adds the two rows at step j from registers.  Used on the fast path (all chains of the warp inside a
+    // 16-token block); the tail falls back to per-token partial loads.
+#ifdef IMC_ZIP_NO_GROUP4
+    static constexpr bool GROUP4 = false;
+#else
+    static constexpr bool GROUP4 = (REM == 2 && FULL >= 1);
+#endif
     // element (row r, column c): slot r/8, unit (slot*CP + c/2)*8 + r%8 (first copy of the partial slot)
     __host__ __device__ static constexpr int off(int r, int c) {
         return (((r >> 3) * CP + (c >> 1)) * 8 + (r & 7)) * 2 + (c & 1);
@@ -110,6 +120,51 @@ struct ZipCfg8 {
         __device__ __forceinline__ bool writer() const { return q == 0; }
     };
     __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
+    // four tokens (one 32-bit word of the stream) on the fast path of the GROUP4 shape
+    __device__ static __forceinline__ void word4(double (&al)[KP], const double* dict, const long long* dexp, uint32_t wv,
+                                                 const Lane& L, int& buf, long long& scale) {
+        const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the word, remainder row pr
+        const int myid = (wv >> (8 * cj)) & 0xffu;
+        const double2* rp = reinterpret_cast<const double2*>(dict + (size_t)myid * STRIDE_D) + FULL * CP * 8 + L.q;
+        double2 rm[CP];
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) rm[cp] = rp[cp * 8];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int id = (wv >> (8 * b)) & 0xffu;
+            double* sb = L.sb0 + buf * KP;
+            const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
+#pragma unroll
+            for (int k = 0; k < FULL; ++k) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp) {
+                    const double2 m = mp[(k * CP + cp) * 8];
+                    s0 = fma(m.x, al[2 * cp], s0);
+                    s1 = fma(m.y, al[2 * cp + 1], s1);
+                }
+                sb[L.q + 8 * k] = s0 + s1;
+            }
+            if (cj == b) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp) {
+                    s0 = fma(rm[cp].x, al[2 * cp], s0);
+                    s1 = fma(rm[cp].y, al[2 * cp + 1], s1);
+                }
+                sb[8 * FULL + pr] = s0 + s1;
+            }
+            scale += dexp[id];
+            __syncwarp();
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp) {
+                const double2 v = reinterpret_cast<const double2*>(sb)[cp];
+                al[2 * cp] = v.x;
+                al[2 * cp + 1] = v.y;
+            }
+            buf ^= 1;
+        }
+    }
     template <bool PRED>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
                                                 const Lane& L, int buf, long long& scale, bool active) {
@@ -155,6 +210,7 @@ template <int K_>
 struct ZipCfg4 {
     static constexpr int K = K_;
     static constexpr int G = 4, CPW = 8;
+    static constexpr bool GROUP4 = false;
     static constexpr int KP = (K + 3) & ~3;            // states padded to a multiple of 4
     static constexpr int CP = KP / 2;                  // column pairs per row (even)
     static constexpr int RPL = KP / 4;                 // rows per lane
@@ -224,6 +280,7 @@ template <int K_>
 struct ZipCfg32 {
     static constexpr int K = K_;
     static constexpr int G = 32, CPW = 1;
+    static constexpr bool GROUP4 = false;
     static constexpr int KP = (K + 1) & ~1;
     static constexpr int CP = KP / 2;
     static constexpr int RPL = (K + 31) / 32;
@@ -404,12 +461,16 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 uint32_t wv = w[wi];
+                if constexpr (C::GROUP4) {
+                    C::word4(al, dict, dexp, wv, L, buf, scale);
+                } else {
 #pragma unroll C::UNROLL
-                for (int b = 0; b < 4; ++b) {
-                    const int id = wv & 0xffu;
-                    wv >>= 8;
-                    C::template step<false>(al, dict, dexp, id, L, buf, scale, true);
-                    buf ^= 1;
+                    for (int b = 0; b < 4; ++b) {
+                        const int id = wv & 0xffu;
+                        wv >>= 8;
+                        C::template step<false>(al, dict, dexp, id, L, buf, scale, true);
+                        buf ^= 1;
+                    }
                 }
                 if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
             }

@@ -148,7 +148,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -309,7 +309,7 @@ def main():
             dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods
 
     peak_dfma, peak_dmma = m.measure_fp64_peak()
-    sampler = ClockSampler(local_rank)       # samples nvidia-smi every 200 ms from the warm-up steps to the end of the timed region
+    sampler = ClockSampler(local_rank)       # samples nvidia-smi every ~100 ms from the warm-up steps to the end of the timed region
     sampler.start()
     for _ in range(args.warmup):
         step()

@@ -129,6 +129,7 @@ struct ZipCfg8 {
         double2 rm[CP];
 #pragma unroll
         for (int cp = 0; cp < CP; ++cp) rm[cp] = rp[cp * 8];
+        scale += dexp[myid];       // every lane pair books the exponent of ITS token; zip_run_unit adds the four pairs up
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int id = (wv >> (8 * b)) & 0xffu;
@@ -154,7 +155,6 @@ struct ZipCfg8 {
                 }
                 sb[8 * FULL + pr] = s0 + s1;
             }
-            scale += dexp[id];
             __syncwarp();
 #pragma unroll
             for (int cp = 0; cp < CP; ++cp) {
@@ -184,7 +184,7 @@ struct ZipCfg8 {
                     sb[k < FULL ? L.q + 8 * k : L.rem_row] = s0 + s1;
                 }
             }
-            scale += dexp[id];
+            if (!GROUP4 || L.q < 2) scale += dexp[id];      // GROUP4: token exponents are per-pair partial sums
         }
         __syncwarp();
         if (!PRED || active) {
@@ -447,7 +447,8 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
         if (ch.first_sym >= 0) al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
         else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
     }
-    long long scale = 0;
+    long long scale = 0;       // exponents taken out by zip_rescale (the same in every lane of the chain)
+    long long tscale = 0;      // exponents of the dictionary matrices applied (GROUP4: partial sum per lane pair)
     bool dead = false, isnan = false;
     int buf = 0;
     uint4 cur = make_uint4(0, 0, 0, 0);
@@ -462,13 +463,13 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
             for (int wi = 0; wi < 4; ++wi) {
                 uint32_t wv = w[wi];
                 if constexpr (C::GROUP4) {
-                    C::word4(al, dict, dexp, wv, L, buf, scale);
+                    C::word4(al, dict, dexp, wv, L, buf, tscale);
                 } else {
 #pragma unroll C::UNROLL
                     for (int b = 0; b < 4; ++b) {
                         const int id = wv & 0xffu;
                         wv >>= 8;
-                        C::template step<false>(al, dict, dexp, id, L, buf, scale, true);
+                        C::template step<false>(al, dict, dexp, id, L, buf, tscale, true);
                         buf ^= 1;
                     }
                 }
@@ -482,7 +483,7 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
                 for (int b = 0; b < 4; ++b) {
                     const int id = wv & 0xffu;
                     wv >>= 8;
-                    C::template step<true>(al, dict, dexp, id, L, buf, scale, wi * 4 + b < rem);
+                    C::template step<true>(al, dict, dexp, id, L, buf, tscale, wi * 4 + b < rem);
                     buf ^= 1;
                 }
                 if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
@@ -490,6 +491,11 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
         }
         cur = nxt;
     }
+    if constexpr (C::GROUP4) {      // add the four lane pairs' partial sums (lanes q and q^1 hold the same value)
+        tscale += __shfl_xor_sync(0xffffffffu, tscale, 2);
+        tscale += __shfl_xor_sync(0xffffffffu, tscale, 4);
+    }
+    scale += tscale;
     double sum = 0.0;
 #pragma unroll
     for (int k = 0; k < KP; ++k) sum += al[k];

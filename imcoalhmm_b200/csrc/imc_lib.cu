@@ -562,7 +562,9 @@ static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM 
 //   lanes per chain 4: one or (K <= 24) two CTAs of 256 threads (64 chains per CTA), K >= 8 only.
 // measured on B200 (gpurun_out/zip_bench_*.log, round 1): K=10 8.3 ms (8 lanes) vs 9.7 ms (4, padded to 12);
 // K=20 58.9 vs 43.7 ms; K=40 175 vs 190 ms (4 lanes need twice the exchange buffers, which costs dictionary entries)
-static int zip_default_lanes(int K) { return (K >= 12 && K <= 24) ? 4 : 8; }
+// (tools/k_sweep.py: tile 8 1.25 vs 1.34 ms with 4 lanes; tile 10 keeps 8 lanes, where one full load fetches the remainder
+// rows of four tokens)
+static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 : 8; }
 
 template <int K>
 static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {

@@ -75,7 +75,11 @@ struct ZipCfg8 {
     // skewed by 16 bytes: in 16-byte bank groups the four chains then start at 0,4,1,5 (mod 8), so the two chains of
     // each half-warp store their 64-byte row blocks into disjoint bank halves (STS.64: 2 wavefronts instead of 4)
     // AND the quarter-broadcast read-back touches four different bank groups.
-    static constexpr int GS = ((2 * KP * 8 + 16 + 63) / 128 * 128 + 64) / 8;
+    // Large K: a single buffer and a second warp barrier per step instead -- the shared memory saved buys one more
+    // dictionary matrix (K = 40: 17 instead of 16 entries, ~5 % fewer tokens), and a barrier is nothing against a step.
+    static constexpr int NBUF = K >= 32 ? 1 : 2;
+    static constexpr int GS = ((NBUF * KP * 8 + 63) / 128 * 128 + 64) / 8;
+    static constexpr int SBUF_PER_WARP = 4 * GS + 2;   // doubles: four chains + the 16-byte skew of chains 2,3
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
     static constexpr int FULL = K / 8;                 // slots in which all 8 lanes own a row
     static constexpr int REM = K % 8;                  // rows of the last, partial slot
@@ -115,7 +119,7 @@ struct ZipCfg8 {
                 const int p = q - (grp % REP) * REM;
                 if (p >= 0 && p < REM) rem_row = 8 * FULL + p;
             }
-            sb0 = sbuf + (size_t)(warp * 4 + grp) * GS + (grp >> 1) * 2;
+            sb0 = sbuf + (size_t)warp * SBUF_PER_WARP + grp * GS + (grp >> 1) * 2;
         }
         __device__ __forceinline__ bool writer() const { return q == 0; }
     };
@@ -168,7 +172,7 @@ struct ZipCfg8 {
     template <bool PRED>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
                                                 const Lane& L, int buf, long long& scale, bool active) {
-        double* sb = L.sb0 + buf * KP;
+        double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
 #pragma unroll
@@ -195,6 +199,7 @@ struct ZipCfg8 {
                 al[2 * cp + 1] = v.y;
             }
         }
+        if (NBUF == 1) __syncwarp();       // everybody has read the buffer before the next step overwrites it
     }
 };
 
@@ -218,6 +223,7 @@ struct ZipCfg4 {
     // exchange buffer per chain: 2 x KP doubles, stride = 32 (mod 128) bytes: the four chains of a half-warp store
     // their 32-byte row blocks into four different bank quarters (STS.64 in 2 wavefronts)
     static constexpr int GS = ((2 * KP * 8 + 95) / 128 * 128 + 32) / 8;
+    static constexpr int SBUF_PER_WARP = 8 * GS;
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
     __host__ __device__ static constexpr int off(int r, int c) {
         const int p = (r >> 2) * CP + (c >> 1);
@@ -286,6 +292,7 @@ struct ZipCfg32 {
     static constexpr int RPL = (K + 31) / 32;
     static constexpr int STRIDE_D = CP * K * 2;        // dense: K units of 16 bytes per column pair
     static constexpr int GS = 2 * KP + 2;              // one chain per warp: no cross-chain bank concerns
+    static constexpr int SBUF_PER_WARP = GS;
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
     __host__ __device__ static constexpr int off(int r, int c) { return ((c >> 1) * K + r) * 2 + (c & 1); }
     __device__ static __forceinline__ void store(double* D, int r, int c, double v) { D[off(r, c)] = v; }
@@ -336,7 +343,7 @@ template <class C>
 struct ZipSmem {
     __host__ __device__ static constexpr int se_doubles(int S) { return (C::K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
     static size_t bytes(int M, int S, int threads) {
-        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / C::G) * C::GS;
+        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP;
         return d * sizeof(double) + (size_t)M * sizeof(long long) + 4 * sizeof(int);   // dexp[M], s_point[2]
     }
     static int max_entries(size_t budget, int S, int threads) {
@@ -530,13 +537,13 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     const int M = a.M, S = a.S;
     double* sE = dict + (size_t)M * C::STRIDE_D;      // [K][S]
     double* spi = sE + ZipSmem<C>::se_doubles(S);     // [KP]
-    double* sbuf = spi + KP;                          // [THREADS/G][GS]
-    long long* dexp = reinterpret_cast<long long*>(sbuf + (THREADS / C::G) * C::GS);   // [M] (64-bit: an entry can span millions of sites)
+    double* sbuf = spi + KP;                          // [THREADS/32][SBUF_PER_WARP]
+    long long* dexp = reinterpret_cast<long long*>(sbuf + (THREADS / 32) * C::SBUF_PER_WARP);   // [M] (64-bit: an entry can span millions of sites)
     int* s_point = reinterpret_cast<int*>(dexp + M);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const typename C::Lane L(lane, warp, sbuf);
-    for (int x = tid; x < (THREADS / C::G) * C::GS; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
+    for (int x = tid; x < (THREADS / 32) * C::SBUF_PER_WARP; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
     const int nunits = (a.nchunks + C::CPW - 1) / C::CPW;
     int primary = blockIdx.x;          // next point of this CTA's own share
     int scan = (int)(((long long)blockIdx.x * 7919) % a.N);   // where the search for points to help starts

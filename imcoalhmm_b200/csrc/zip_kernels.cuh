@@ -222,7 +222,8 @@ struct ZipCfg4 {
     static constexpr int STRIDE_D = KP * KP;           // dense
     // exchange buffer per chain: 2 x KP doubles, stride = 32 (mod 128) bytes: the four chains of a half-warp store
     // their 32-byte row blocks into four different bank quarters (STS.64 in 2 wavefronts)
-    static constexpr int GS = ((2 * KP * 8 + 95) / 128 * 128 + 32) / 8;
+    static constexpr int NBUF = K >= 16 ? 1 : 2;        // larger K: single buffer + a second warp barrier (more dictionary)
+    static constexpr int GS = ((NBUF * KP * 8 + 95) / 128 * 128 + 32) / 8;
     static constexpr int SBUF_PER_WARP = 8 * GS;
     static constexpr int UNROLL = K <= 12 ? 4 : 1;
     __host__ __device__ static constexpr int off(int r, int c) {
@@ -247,7 +248,7 @@ struct ZipCfg4 {
     template <bool PRED>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
                                                 const Lane& L, int buf, long long& scale, bool active) {
-        double* sb = L.sb0 + buf * KP;
+        double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
             const char* me = mb + L.off_even;
@@ -275,6 +276,7 @@ struct ZipCfg4 {
                 al[2 * cp + 1] = v.y;
             }
         }
+        if (NBUF == 1) __syncwarp();       // everybody has read the buffer before the next step overwrites it
     }
 };
 

@@ -9,7 +9,7 @@
 //   * ONE dictionary is shared by all chunks of a sequence set (the kernel keeps one copy of every
 //     dictionary matrix per parameter point in shared memory), learned on a bounded prefix sample;
 //   * at most 256 ids (one byte per token); a forward call with K states uses the first M(K) ids that fit
-//     in shared memory, tokens with larger ids being expanded back into their parts (zip_derive);
+//     in shared memory, tokens with larger ids being expanded back into their parts (zip_expand);
 //   * position 0 of every chunk is kept out of the token stream (alpha_0 = pi o E[:,o_0] has no T factor).
 #include <array>
 #include <thread>

@@ -5,15 +5,15 @@
 //   C_(a,b)  = C_b C_a                               dictionary entry for "a then b", built level by level
 //   alpha_0  = pi o E[:,o_0];  alpha <- C_tok alpha  one mat-vec per token;  logL = log sum(alpha) + exponents
 //
-// One CTA = one parameter point x one share of the chunks.  Phase 1 builds the point's dictionary (M matrices,
-// each scaled by an exact power of two so that its largest entry is in [1,2), exponent kept aside) in shared
-// memory.  Phase 2 runs the chains: a chain is owned by EIGHT lanes (a quarter-warp); lane q owns output rows
-// q, q+8, ... and reads them with LDS.128 from a layout in which the 8 lanes of a quarter-warp always touch 8
-// consecutive 16-byte units of ONE matrix, so every load is bank-conflict free no matter which matrices the four
-// chains of a warp are using.  The new state is exchanged through a small double-buffered shared-memory
-// buffer (one STS.64 per owned row, K/2 quarter-broadcast LDS.128 back), after which every lane holds all of
-// alpha again.  The bound is the shared-memory pipe: K*K*8 bytes of matrix per chain-step against 128 B/clk/SM,
-// i.e. at most 1/4 of the FP64 rate -- times the compression ratio (50-150x on the benchmark alignments).
+// Persistent CTAs; a CTA serves one parameter point at a time.  zip_build_dictionary puts the point's dictionary (M
+// matrices, each scaled by an exact power of two so that its largest entry is in [1,2), exponent kept aside) into shared
+// memory; the warps then claim warp-loads of chunks of that point (work stealing across CTAs once a CTA's own points are
+// done) and run the chains.  One chain's mat-vec is spread over G lanes (three decompositions below: 8, 4 or 32 lanes),
+// each lane reading its rows with LDS.128 from a layout that is bank-conflict free no matter which matrices the chains
+// of a warp are using.  The new state is exchanged through a small shared-memory buffer (one STS.64 per owned row, K/2
+// broadcast LDS.128 back), after which every lane holds all of alpha again.  The bound is the shared-memory pipe: 8 K^2
+// bytes of matrix per chain-step against 128 B/clk/SM, i.e. at most 1/4 of the FP64 rate -- times the compression ratio
+// (50-150x on the benchmark alignments).  DESIGN.md section 4.1 has the measurements behind every choice made here.
 #pragma once
 #include "forward_kernels.cuh"
 
@@ -51,7 +51,7 @@ struct ZipArgs {
 // Segmented mode (chain-scarce calls: few chunks x few points).  A long chunk is cut into segments of `seglen` tokens.
 // Segment 0 runs as usual from pi; segment s > 0 is run K times from the unit vectors e_0..e_{K-1}, which yields the
 // columns of its transfer matrix P_s = C_tok[last] ... C_tok[first] (K times the arithmetic, but K * #segments times
-// the parallelism).  zip_combine_kernel then folds alpha <- P_s alpha over the segments of each chunk.
+// the parallelism).  zip_fold_kernel then folds alpha <- P_s alpha over the segments of each chunk.
 
 // ------------------------------------------------------------------------------------------------
 // Lane decompositions.  A config class C describes how one chain's mat-vec is spread over G lanes:

@@ -37,7 +37,8 @@ for trial in range(trials):
     seg = int(rng.choice([0, 0, -1, 16, 64, 700]))
     cap = int(rng.choice([0, 0, nsym, nsym + 1, 9, 40]))
     cap = cap if cap == 0 or cap >= nsym else nsym
-    for k, v in (("forward_kernel", 4), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap)):
+    fk = int(rng.choice([4, 4, 4, 0]))                       # mostly the zip kernel forced, sometimes the automatic choice
+    for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap)):
         m.set_option(k, v)
     got = fset.forward_batch(pis, Ts, Es)
     # the oracle's plain forward divides by the zero scale of an impossible observation and returns NaN where the

@@ -7,7 +7,7 @@ Public surface (mirrors /root/reference/src/IMCoalHMM for this path only):
     Likelihood(model, forwarders)(theta) / .batched(thetas)               likelihood.py:8-33
     maximum_likelihood_estimate(log_likelihood, initial_parameters, ...)  likelihood.py:36-87
     ziphmm.preprocess_raw_observations / ziphmm.zip_forward               hmm.py:16,20-21
-    mcmc.BatchedMCMC / mcmc.MC3 / mcmc.ParticleSwarm                      mcmc.py, particle_swarm.py, one batched call per step
+    mcmc.BatchedMCMC / MC3 / ParticleSwarm / GeneticAlgorithm             mcmc.py, particle_swarm.py, genetic_algorithm.py: one batched call per step
 
 Importing the package needs the in-tree shared library (python imcoalhmm_b200/build.py); there is no
 CPU fallback.  CUDA itself is initialised lazily by the first forward call.

@@ -187,3 +187,66 @@ class ParticleSwarm(object):
             if best_fit[g] > swarm_fit:
                 swarm_pos, swarm_fit = best_pos[g].copy(), best_fit[g]
         return swarm_pos, swarm_fit, iteration
+
+
+class GeneticAlgorithm(object):
+    """Genetic algorithm with the reference's default operators (genetic_algorithm.py:690-840: uniform initialisation in
+    the unit cube, tournament selection of 75 % breeders with 10 % tournaments, one-point crossover of breeders i and
+    i + n/2 with the fitter parent first, Gaussian point mutation (ratio 0.15, sigma 0.01, clipped to [0, 1]), elitism,
+    hall of fame) -- with every generation's offspring scored in ONE batched likelihood call instead of one call each
+    (genetic_algorithm.py:813-833).  `transform` maps genomes in the unit cube to model parameters."""
+
+    def __init__(self, population_size=100, elite_count=1, hall_of_fame_size=5, max_generations=500, selection_ratio=0.75,
+                 tournament_ratio=0.1, point_mutation_ratio=0.15, mutation_sigma=0.01, rng=None):
+        assert elite_count < population_size
+        self.population_size, self.elite_count, self.hall_of_fame_size = int(population_size), int(elite_count), int(hall_of_fame_size)
+        self.max_generations, self.selection_ratio, self.tournament_ratio = max_generations, selection_ratio, tournament_ratio
+        self.point_mutation_ratio, self.mutation_sigma = point_mutation_ratio, mutation_sigma
+        self.rng = np.random.default_rng() if rng is None else rng
+
+    def maximise(self, fitness_function, genome_length, transform=None, log_function=None):
+        assert genome_length >= 2
+        score = _batched(fitness_function)
+        rng, n = self.rng, self.population_size
+
+        def fitness(genomes):
+            f = np.asarray(score(np.ascontiguousarray(genomes if transform is None else transform(genomes))), dtype=np.float64)
+            f[np.isnan(f)] = -np.inf
+            return f
+        pop = rng.uniform(0.0, 1.0, size=(n, genome_length))
+        fit = fitness(pop)
+        hall = []                                                  # [(fitness, genome)], best first
+
+        def submit(genomes, fits):
+            hall.extend(zip(fits.tolist(), [g.copy() for g in genomes]))
+            hall.sort(key=lambda x: -x[0])
+            del hall[self.hall_of_fame_size:]
+        submit(pop, fit)
+        generation = 0
+        while self.max_generations is None or generation < self.max_generations:
+            generation += 1
+            if log_function is not None and log_function(generation, hall[0][0], hall[0][1]) is False:
+                break
+            # tournament selection over windows of the population (genetic_algorithm.py:342-367)
+            size = max(1, int(round(n * self.selection_ratio)))
+            tsize = max(1, int(round(n * self.tournament_ratio)))
+            starts = rng.integers(0, n - tsize + 1, size=size)
+            winners = np.array([a + int(np.argmax(fit[a:a + tsize])) for a in starts])
+            winners = winners[np.argsort(-fit[winners], kind="stable")]
+            elite = np.argsort(-fit, kind="stable")[:self.elite_count]
+            n_off = n - self.elite_count
+            i = np.arange(n_off) % size
+            j = (np.arange(n_off) + size // 2) % size
+            a, b = winners[i], winners[j]
+            swap = fit[b] > fit[a]                                 # the fitter parent supplies the left part
+            left, right = np.where(swap, b, a), np.where(swap, a, b)
+            cut = rng.integers(1, genome_length, size=n_off)       # one-point crossover (:426-445)
+            cols = np.arange(genome_length)[None, :]
+            off = np.where(cols < cut[:, None], pop[left], pop[right])
+            mutate = rng.uniform(size=off.shape) < self.point_mutation_ratio        # Gaussian mutation (:620-640)
+            off = np.where(mutate, np.clip(off + rng.normal(0.0, self.mutation_sigma, size=off.shape), 0.0, 1.0), off)
+            off_fit = fitness(off)                                 # the whole generation in one batched call
+            pop = np.concatenate([pop[elite], off])
+            fit = np.concatenate([fit[elite], off_fit])
+            submit(off, off_fit)
+        return hall[0][1], hall[0][0], generation

@@ -47,6 +47,10 @@ WORKLOADS = {
     "c3_1gpu": dict(model="im_k10_10", ctor=("IsolationMigrationModel", (10, 10)),
                     default=[1e-3, 1e-3, 2000.0, 0.4, 200.0], K=20, chunks=125, chunk_len=1_000_000, points=1024,
                     desc="configs[2] per-GPU shard: IM model K=10+10, 125 x 1 Mbp chunks, 1024 parameter points"),
+    # per-GPU slice of the north-star target: IM model K=10+10, 3 Gbp on 8 GPUs = 375 chunks/GPU, 1024 parameter points
+    "ns_1gpu": dict(model="im_k10_10", ctor=("IsolationMigrationModel", (10, 10)),
+                    default=[1e-3, 1e-3, 2000.0, 0.4, 200.0], K=20, chunks=375, chunk_len=1_000_000, points=1024,
+                    desc="north-star per-GPU shard: IM model K=10+10, 375 x 1 Mbp chunks (3 Gbp on 8 GPUs), 1024 parameter points"),
     # per-GPU slice of configs[3] (isolation-model-mcmc, 4096 lock-step chains, 3 Gbp on 8 GPUs = 375 chunks/GPU): one step
     # = one proposal of every chain scored in one batched call (imcoalhmm_b200.mcmc.BatchedMCMC.step)
     "c4_1gpu": dict(model="isolation_k10", ctor=("IsolationModel", (10,)), default=[1e-3, 2000.0, 0.4], K=10,

@@ -10,6 +10,9 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "forward_kernels.cuh"),
         os.path.join(HERE, "csrc", "zip_kernels.cuh"),
         os.path.join(HERE, "csrc", "tokenizer.inl"),
         os.path.join(HERE, "csrc", "model_host.inl"),
+        os.path.join(HERE, "csrc", "zip_host.inl"),
+        os.path.join(HERE, "csrc", "ingest_host.inl"),
+        os.path.join(HERE, "csrc", "comm_host.inl"),
         os.path.join(HERE, "csrc", "model_kernels.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "imcoalhmm_b200.h")]
 

@@ -248,126 +248,7 @@ extern "C" int imc_seq_from_file(const char* path, int nsym, imc_seq** out) {
     return seq_finish(s, out);
 }
 
-// ------------------------------------------------------------------------------------------ ingest
-// Pairwise symbol rule of the reference's preprocessing script (scripts/prepare-alignments.py:99-111):
-//   upper-case both bases; 2 if either is not one of A, C, G, T; 0 if equal; 1 otherwise.
-static inline uint8_t pair_symbol(unsigned char a, unsigned char b) {
-    static const struct Table { uint8_t code[256]; Table() {
-        for (int i = 0; i < 256; ++i) code[i] = 4;
-        code[(int)'A'] = code[(int)'a'] = 0; code[(int)'C'] = code[(int)'c'] = 1;
-        code[(int)'G'] = code[(int)'g'] = 2; code[(int)'T'] = code[(int)'t'] = 3;
-    } } tab;
-    const uint8_t x = tab.code[a], y = tab.code[b];
-    return (x > 3 || y > 3) ? 2 : (x == y ? 0 : 1);
-}
-
-extern "C" int imc_seq_from_pair(const char* seq1, const char* seq2, int64_t L, imc_seq** out) {
-    if (!out || L < 0 || (L > 0 && (!seq1 || !seq2))) return fail(IMC_ERR_INVALID, "bad arguments");
-    imc_seq* s = new (std::nothrow) imc_seq;
-    if (!s) return fail(IMC_ERR_NOMEM, "out of memory");
-    s->nsym = 3;
-    try { s->sym.resize((size_t)L); } catch (...) { delete s; return fail(IMC_ERR_NOMEM, "out of memory for %lld symbols", (long long)L); }
-    for (int64_t t = 0; t < L; ++t) s->sym[(size_t)t] = pair_symbol((unsigned char)seq1[t], (unsigned char)seq2[t]);
-    return seq_finish(s, out);
-}
-
-// FASTA: '>' starts a record, its name is the text up to the first whitespace; sequence lines are concatenated.
-static int read_fasta(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
-    std::vector<char> buf(1 << 20);
-    bool in_header = false, at_line_start = true;
-    size_t got;
-    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
-        for (size_t i = 0; i < got; ++i) {
-            const char ch = buf[i];
-            if (in_header) {
-                if (ch == '\n') { in_header = false; at_line_start = true; }
-                else names.back().push_back(ch);
-                continue;
-            }
-            if (ch == '\n' || ch == '\r') { at_line_start = (ch == '\n') || at_line_start; continue; }
-            if (at_line_start && ch == '>') { names.emplace_back(); seqs.emplace_back(); in_header = true; continue; }
-            at_line_start = false;
-            if (ch == ' ' || ch == '\t') continue;
-            if (seqs.empty()) { fclose(f); return fail(IMC_ERR_IO, "'%s' does not start with a FASTA header", path); }
-            seqs.back().push_back(ch);
-        }
-    }
-    fclose(f);
-    for (auto& n : names) {
-        while (!n.empty() && (n.back() == '\r' || n.back() == ' ' || n.back() == '\t')) n.pop_back();
-        const size_t sp = n.find_first_of(" \t");
-        if (sp != std::string::npos) n.resize(sp);
-    }
-    return IMC_OK;
-}
-
-extern "C" int imc_seq_from_fasta(const char* path, const char* name1, const char* name2, imc_seq** out) {
-    if (!path || !out) return fail(IMC_ERR_INVALID, "NULL argument");
-    std::vector<std::string> names, seqs;
-    int rc = read_fasta(path, names, seqs);
-    if (rc) return rc;
-    int i1 = -1, i2 = -1;
-    if (!name1 && !name2) {
-        if (names.size() != 2) return fail(IMC_ERR_INVALID, "'%s' holds %zu records; name the two to compare", path, names.size());
-        i1 = 0; i2 = 1;
-    } else {
-        if (!name1 || !name2) return fail(IMC_ERR_INVALID, "give both record names or neither");
-        for (size_t i = 0; i < names.size(); ++i) { if (names[i] == name1) i1 = (int)i; if (names[i] == name2) i2 = (int)i; }
-        if (i1 < 0 || i2 < 0) return fail(IMC_ERR_INVALID, "record '%s' not found in '%s'", i1 < 0 ? name1 : name2, path);
-    }
-    if (seqs[i1].size() != seqs[i2].size())
-        return fail(IMC_ERR_INVALID, "aligned sequences differ in length (%zu vs %zu)", seqs[i1].size(), seqs[i2].size());
-    return imc_seq_from_pair(seqs[i1].data(), seqs[i2].data(), (int64_t)seqs[i1].size(), out);
-}
-
-// Binary container: "IMCSEQ1\0", int32 nsym, int32 bits per symbol (2 or 8), int64 L, packed symbols (little endian,
-// symbol t of a 2-bit file sits in bits 2*(t%4).. of byte t/4).  16x smaller than the text format for NSYM = 3.
-extern "C" int imc_seq_save(const imc_seq* seq, const char* path) {
-    if (!seq || !path) return fail(IMC_ERR_INVALID, "NULL argument");
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(IMC_ERR_IO, "cannot create '%s': %s", path, strerror(errno));
-    const int32_t nsym = seq->nsym, bits = seq->nsym <= 4 ? 2 : 8;
-    const int64_t L = (int64_t)seq->sym.size();
-    bool ok = fwrite("IMCSEQ1", 1, 8, f) == 8 && fwrite(&nsym, 4, 1, f) == 1 && fwrite(&bits, 4, 1, f) == 1 && fwrite(&L, 8, 1, f) == 1;
-    if (ok && bits == 8) ok = L == 0 || fwrite(seq->sym.data(), 1, (size_t)L, f) == (size_t)L;
-    if (ok && bits == 2) {
-        std::vector<uint8_t> packed((size_t)((L + 3) / 4), 0);
-        for (int64_t t = 0; t < L; ++t) packed[(size_t)(t >> 2)] |= (uint8_t)(seq->sym[(size_t)t] << (2 * (t & 3)));
-        ok = packed.empty() || fwrite(packed.data(), 1, packed.size(), f) == packed.size();
-    }
-    if (fclose(f) != 0) ok = false;
-    return ok ? IMC_OK : fail(IMC_ERR_IO, "short write to '%s'", path);
-}
-
-extern "C" int imc_seq_load(const char* path, imc_seq** out) {
-    if (!path || !out) return fail(IMC_ERR_INVALID, "NULL argument");
-    FILE* f = fopen(path, "rb");
-    if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
-    char magic[8];
-    int32_t nsym = 0, bits = 0;
-    int64_t L = -1;
-    bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, "IMCSEQ1", 8) && fread(&nsym, 4, 1, f) == 1 && fread(&bits, 4, 1, f) == 1 &&
-              fread(&L, 8, 1, f) == 1 && nsym >= 1 && nsym <= 255 && (bits == 2 || bits == 8) && L >= 0 && !(bits == 2 && nsym > 4);
-    if (!ok) { fclose(f); return fail(IMC_ERR_IO, "'%s' is not an IMCSEQ1 file", path); }
-    imc_seq* s = new (std::nothrow) imc_seq;
-    if (!s) { fclose(f); return fail(IMC_ERR_NOMEM, "out of memory"); }
-    s->nsym = nsym;
-    try {
-        s->sym.resize((size_t)L);
-        if (bits == 8) ok = L == 0 || fread(s->sym.data(), 1, (size_t)L, f) == (size_t)L;
-        else {
-            std::vector<uint8_t> packed((size_t)((L + 3) / 4));
-            ok = packed.empty() || fread(packed.data(), 1, packed.size(), f) == packed.size();
-            for (int64_t t = 0; ok && t < L; ++t) s->sym[(size_t)t] = (packed[(size_t)(t >> 2)] >> (2 * (t & 3))) & 3;
-        }
-    } catch (...) { fclose(f); delete s; return fail(IMC_ERR_NOMEM, "out of memory for %lld symbols", (long long)L); }
-    fclose(f);
-    if (ok) for (uint8_t v : s->sym) if (v >= nsym) { ok = false; break; }
-    if (!ok) { delete s; return fail(IMC_ERR_IO, "'%s' is truncated or holds symbols outside [0, %d)", path, nsym); }
-    return seq_finish(s, out);
-}
+#include "ingest_host.inl"
 
 extern "C" int imc_seq_length(const imc_seq* seq, int64_t* L_out) {
     if (!seq || !L_out) return fail(IMC_ERR_INVALID, "NULL argument");
@@ -536,304 +417,7 @@ static int seqset_upload(imc_seqset* set) {
 }
 
 
-// ------------------------------------------------------------------------------------------ zip (compressed) path
-enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3, KERNEL_ZIP = 4 };
-
-#define ZIP_K_LIST(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(32) X(40)
-// smallest instantiated tile that holds K states (the kernels take the actual K at run time and leave the padding
-// rows / columns of the tile at zero), or 0
-static int zip_tile(int K) {
-    static const int tiles[] = {
-#define X(k) k,
-        ZIP_K_LIST(X)
-#undef X
-    };
-    for (int t : tiles) if (t >= K) return t;
-    return 0;
-}
-static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
-
-struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
-static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
-
-// Launch shapes (all persistent, see zip_forward_kernel):
-//   lanes per chain 8: two CTAs of 256 threads per SM (K <= 24), or one CTA with all the shared memory for the
-//                      dictionary -- 512 threads where the register file allows (K <= 24), else 256;
-//   lanes per chain 4: one or (K <= 24) two CTAs of 256 threads (64 chains per CTA), K >= 8 only.
-// measured on B200 (gpurun_out/zip_bench_*.log, round 1): K=10 8.3 ms (8 lanes) vs 9.7 ms (4, padded to 12);
-// K=20 58.9 vs 43.7 ms; K=40 175 vs 190 ms (4 lanes need twice the exchange buffers, which costs dictionary entries)
-// (tools/k_sweep.py: tile 8 1.25 vs 1.34 ms with 4 lanes; tile 10 keeps 8 lanes, where one full load fetches the remainder
-// rows of four tokens)
-static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 : 8; }
-
-template <int K>
-static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
-    ZipPlan p;
-    p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
-    if (K < 8) p.lanes = 8;
-    if (p.lanes == 32 && K < 10) p.lanes = 8;
-    int m1, m2, t1;
-    if (p.lanes == 32) {       // one chain per warp, one CTA per SM (latency mode)
-        using C = ZipCfg32<K>;
-        t1 = K <= 24 ? 512 : 256;
-        m2 = 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
-        want_ctas = 1;
-    } else if (p.lanes == 8) {
-        using C = ZipCfg8<K>;
-        t1 = K <= 24 ? 512 : 256;
-        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
-    } else {
-        using C = ZipCfg4<K>;
-        t1 = 256;
-        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
-    }
-    int ctas = want_ctas;
-    if (ctas == 2 && K > 24) ctas = 1;
-    if (ctas == 0) ctas = (K <= 24 && m2 >= avail_ids) ? 2 : 1;   // the bigger dictionary wins unless everything fits in half
-    p.ctas_per_sm = ctas;
-    p.threads = ctas == 2 ? 256 : t1;
-    p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
-    if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
-    p.M = std::max(p.M, S);
-    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads)
-           : (p.lanes == 4 ? ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg32<K>>::bytes(p.M, S, p.threads));
-    return p;
-}
-
-static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0) {
-    const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
-    switch (zip_tile(K)) {
-#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
-        ZIP_K_LIST(X)
-#undef X
-        default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
-    }
-    if (out->smem > ZIP_SMEM_SM) return fail(IMC_ERR_UNSUPPORTED, "zip kernel: %d symbols x K = %d do not fit in shared memory", S, K);
-    return IMC_OK;
-}
-
-// token streams over the first M dictionary ids, level-ordered, on the device (cached per M)
-static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
-    for (ZipDevice* z : set->zip_dev) if (z->M == M) { *out = z; return IMC_OK; }
-    const int ns = (int)set->streams.size();
-    ZipLevels zl = zip_levels(set->merges, M);
-    std::vector<std::vector<uint8_t>> tok(ns);
-    if (!parallel_for(ns, [&](int k) {
-            zip_expand(set->merges, set->tok_full[k], M, tok[k]);
-            for (auto& t : tok[k]) t = zl.perm[t];
-        })) return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams");
-    std::vector<int> order(ns);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tok[x].size() > tok[y].size(); });
-    std::vector<ZipChunk> chunks(ns);
-    long long off = 0;
-    for (int i = 0; i < ns; ++i) {
-        const int k = order[i];
-        if (tok[k].size() > 0x7fffffffULL) return fail(IMC_ERR_UNSUPPORTED, "a chunk has more than 2^31-1 tokens");
-        chunks[i].tok_off = off;
-        chunks[i].ntok = (int)tok[k].size();
-        chunks[i].first_sym = set->first_sym[k];
-        chunks[i].out_index = k;
-        chunks[i].pad = 0;
-        off += (long long)((tok[k].size() + 15) / 16) * 16 + 16;
-    }
-    std::vector<uint8_t> flat((size_t)off, 0);
-    long long total = 0;
-    for (int i = 0; i < ns; ++i) {
-        const auto& t = tok[order[i]];
-        if (!t.empty()) memcpy(flat.data() + chunks[i].tok_off, t.data(), t.size());
-        total += (long long)t.size();
-    }
-    ZipDevice* z = new (std::nothrow) ZipDevice;
-    if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
-    z->M = M;
-    z->nlevels = (int)zl.level_start.size() - 1;
-    z->total_tokens = total;
-    z->max_ntok = ns ? chunks[0].ntok : 0;
-    z->host_chunks = chunks;
-    int rc;
-    if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
-        (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
-        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
-        delete z;
-        return rc;
-    }
-    cudaError_t e = cudaSuccess;
-    if (!flat.empty()) e = cudaMemcpy(z->tokens.p, flat.data(), flat.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && ns) e = cudaMemcpy(z->chunks.p, chunks.data(), sizeof(ZipChunk) * ns, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && !zl.pairs.empty()) e = cudaMemcpy(z->pairs.p, zl.pairs.data(), zl.pairs.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(z->levels.p, zl.level_start.data(), sizeof(int) * zl.level_start.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
-        delete z;
-        return fail(IMC_ERR_CUDA, "uploading token streams failed: %s", cudaGetErrorString(e));
-    }
-    set->zip_dev.push_back(z);
-    *out = z;
-    return IMC_OK;
-}
-
-// chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen)
-static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
-    for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
-    std::vector<ZipChunk> chains;
-    std::vector<ZipFoldItem> items1, items2;
-    int nvec2 = 0;
-    for (const ZipChunk& ch : z->host_chunks) {
-        const int nseg = std::max(1, (ch.ntok + seglen - 1) / seglen);
-        const int first_chain = (int)chains.size();
-        for (int sg = 0; sg < nseg; ++sg) {
-            ZipChunk c = ch;
-            c.tok_off = ch.tok_off + (long long)sg * seglen;
-            c.ntok = std::max(0, std::min(seglen, ch.ntok - sg * seglen));
-            for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
-                c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
-                c.out_index = (int)chains.size();
-                chains.push_back(c);
-            }
-        }
-        // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
-        if (nseg <= 32) {
-            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0});
-        } else {        // two levels: groups of gs segments folded in parallel, then the groups
-            const int gs = (int)std::ceil(std::sqrt((double)nseg)), ngroups = (nseg + gs - 1) / gs;
-            const int base2 = nvec2;
-            for (int g = 0; g < ngroups; ++g) {
-                const int s0 = g * gs, s1 = std::min(nseg, s0 + gs);     // segments [s0, s1)
-                if (g == 0) {
-                    items1.push_back({first_chain, first_chain + 1, s1 - 1, nvec2++, 0, 1});
-                } else {
-                    for (int col = 0; col < K; ++col)
-                        items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1});
-                }
-            }
-            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0});
-        }
-    }
-    // the kernel takes chunks in list order, longest first: full segments first, tails last (out_index keeps identity)
-    std::vector<ZipChunk> sorted = chains;
-    std::stable_sort(sorted.begin(), sorted.end(), [](const ZipChunk& x, const ZipChunk& y) { return x.ntok > y.ntok; });
-    ZipSplit* sp = new (std::nothrow) ZipSplit;
-    if (!sp) return fail(IMC_ERR_NOMEM, "out of memory");
-    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size();
-    sp->n_level1 = (int)items1.size(); sp->n_final = (int)items2.size(); sp->nvec2 = nvec2;
-    int rc;
-    if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) ||
-        (rc = sp->items1.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items1.size(), 1))) ||
-        (rc = sp->items2.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items2.size(), 1)))) {
-        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
-        return rc;
-    }
-    cudaError_t e = cudaMemcpy(sp->chunks.p, sorted.data(), sizeof(ZipChunk) * sorted.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && !items1.empty()) e = cudaMemcpy(sp->items1.p, items1.data(), sizeof(ZipFoldItem) * items1.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && !items2.empty()) e = cudaMemcpy(sp->items2.p, items2.data(), sizeof(ZipFoldItem) * items2.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
-        return fail(IMC_ERR_CUDA, "uploading segment descriptors failed: %s", cudaGetErrorString(e));
-    }
-    z->splits.push_back(sp);
-    *out = sp;
-    return IMC_OK;
-}
-
-template <class C, int THREADS, int MINB>
-static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
-    static size_t attr_max = 0;
-    if (p.smem > attr_max) {
-        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<C, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        attr_max = p.smem;
-    }
-    zip_forward_kernel<C, THREADS, MINB><<<grid, THREADS, p.smem, st>>>(a);
-    return IMC_OK;
-}
-
-template <int K>
-static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
-    if constexpr (K >= 10) {
-        if (p.lanes == 32) {
-            if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1>(a, p, grid, st);
-            else return launch_zip_k<ZipCfg32<K>, 256, 1>(a, p, grid, st);
-        }
-    }
-    if constexpr (K >= 8) {
-        if (p.lanes == 4) {
-            if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2>(a, p, grid, st); }
-            return launch_zip_k<ZipCfg4<K>, 256, 1>(a, p, grid, st);
-        }
-    }
-    if constexpr (K <= 24) {
-        if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2>(a, p, grid, st);
-        return launch_zip_k<ZipCfg8<K>, 512, 1>(a, p, grid, st);
-    } else {
-        return launch_zip_k<ZipCfg8<K>, 256, 1>(a, p, grid, st);
-    }
-}
-
-static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
-    // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
-    const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
-    (void)nw;
-    const long long units = (long long)a.N * nunits;     // scarce work spreads one warp-load per CTA over the SMs
-    const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
-    const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
-    // with fewer warp-loads than warps on the machine, let only as many warps per CTA claim work as it takes to cover
-    // them: the chains then spread over all SMs instead of piling onto the first CTAs that arrive
-    a.active_warps = (int)std::min<long long>(p.threads / 32, std::max<long long>(1, (units + grid - 1) / grid));
-    switch (zip_tile(a.K)) {
-#define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
-        ZIP_K_LIST(X)
-#undef X
-    }
-    return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", a.K);
-}
-
-extern "C" int imc_seqset_zip_info(imc_seqset* set, int K, int* ids_available, int* ids_used, int64_t* tokens, int* levels) {
-    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
-    if (ids_available) *ids_available = set->merges.size();
-    if (!ids_used && !tokens && !levels) return IMC_OK;
-    ZipPlan plan;
-    int rc = zip_plan(K, set->nsym, set->merges.size(), &plan);
-    if (rc) return rc;
-    if (ids_used) *ids_used = plan.M;
-    if (levels) *levels = (int)zip_levels(set->merges, plan.M).level_start.size() - 1;
-    if (tokens) {
-        std::vector<long long> len(set->merges.size(), 1);
-        for (int id = std::max(plan.M, set->nsym); id < set->merges.size(); ++id) {
-            const auto& pr = set->merges.pairs[id - set->nsym];
-            len[id] = len[pr[0]] + len[pr[1]];
-        }
-        long long total = 0;
-        for (const auto& t : set->tok_full) for (uint8_t x : t) total += len[x];
-        *tokens = total;
-    }
-    return IMC_OK;
-}
-
-extern "C" int imc_seqset_zip_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs) {
-    if (!set || !pairs_out) return fail(IMC_ERR_INVALID, "NULL argument");
-    if (capacity_pairs < (int)set->merges.pairs.size()) return fail(IMC_ERR_INVALID, "capacity %d < %zu pairs", capacity_pairs, set->merges.pairs.size());
-    for (size_t i = 0; i < set->merges.pairs.size(); ++i) { pairs_out[2 * i] = set->merges.pairs[i][0]; pairs_out[2 * i + 1] = set->merges.pairs[i][1]; }
-    return IMC_OK;
-}
-
-extern "C" int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_t* out, int64_t capacity, int64_t* ntokens) {
-    if (!set || !ntokens) return fail(IMC_ERR_INVALID, "NULL argument");
-    if (chunk < 0 || chunk >= set->n_chunks) return fail(IMC_ERR_INVALID, "chunk %d out of range", chunk);
-    if (ids < set->nsym || ids > set->merges.size()) return fail(IMC_ERR_INVALID, "ids must be in [%d, %d]", set->nsym, set->merges.size());
-    const int k = set->stream_of_chunk[chunk];
-    if (k < 0) { *ntokens = 0; return IMC_OK; }
-    std::vector<uint8_t> tok;
-    zip_expand(set->merges, set->tok_full[k], ids, tok);
-    *ntokens = (int64_t)tok.size();
-    if (out) {
-        if (capacity < (int64_t)tok.size()) return fail(IMC_ERR_INVALID, "capacity %lld < %zu tokens", (long long)capacity, tok.size());
-        if (!tok.empty()) memcpy(out, tok.data(), tok.size());
-    }
-    return IMC_OK;
-}
+#include "zip_host.inl"
 
 // ------------------------------------------------------------------------------------------ launchers
 
@@ -1097,119 +681,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
     return IMC_OK;
 }
 
-// ------------------------------------------------------------------------------------------ multi-GPU: the one collective
-// Chunks are sharded over the ranks (one process per GPU); every rank scores the same parameter batch on its shard and
-// the partial logL[N] are summed by ONE all-reduce per batch.  NCCL is resolved at run time so that the
-// library has no link-time dependency on it: a single-GPU user never needs libnccl, and a process that already loaded
-// torch's NCCL reuses that copy.
-struct NcclApi {
-    void* handle = nullptr;
-    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
-    decltype(&ncclCommInitRank) CommInitRank = nullptr;
-    decltype(&ncclAllReduce) AllReduce = nullptr;
-    decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclGetErrorString) GetErrorString = nullptr;
-};
-static NcclApi g_nccl;
-static ncclComm_t g_comm = nullptr;
-
-static int nccl_load() {
-    if (g_nccl.handle) return IMC_OK;
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) return fail(IMC_ERR_UNSUPPORTED, "libnccl.so.2 cannot be loaded: %s", dlerror());
-    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
-    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
-    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
-    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
-    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
-        return fail(IMC_ERR_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
-    g_nccl.handle = h;
-    return IMC_OK;
-}
-#define NCCL_TRY(x)                                                                                       \
-    do {                                                                                                  \
-        ncclResult_t r_ = (x);                                                                            \
-        if (r_ != ncclSuccess) return fail(IMC_ERR_CUDA, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); \
-    } while (0)
-
-extern "C" int imc_comm_unique_id(void* id_out, int capacity) {
-    if (!id_out || capacity < (int)sizeof(ncclUniqueId)) return fail(IMC_ERR_INVALID, "id buffer must hold %zu bytes", sizeof(ncclUniqueId));
-    int rc = nccl_load();
-    if (rc) return rc;
-    ncclUniqueId id;
-    NCCL_TRY(g_nccl.GetUniqueId(&id));
-    memcpy(id_out, &id, sizeof id);
-    return IMC_OK;
-}
-
-extern "C" int imc_comm_init(int nranks, int rank, const void* nccl_id) {
-    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_id)) return fail(IMC_ERR_INVALID, "bad communicator arguments");
-    if (g_comm) return fail(IMC_ERR_INVALID, "communicator already initialised; call imc_comm_destroy first");
-    int rc = ensure_device();
-    if (rc) return rc;
-    if (nranks == 1) return IMC_OK;       // nothing to sum over
-    if ((rc = nccl_load())) return rc;
-    ncclUniqueId id;
-    memcpy(&id, nccl_id, sizeof id);
-    NCCL_TRY(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
-    return IMC_OK;
-}
-
-extern "C" int imc_comm_destroy(void) {
-    if (g_comm && g_ctx.pid == getpid()) g_nccl.CommDestroy(g_comm);
-    g_comm = nullptr;
-    return IMC_OK;
-}
-
-// this rank's partial log-likelihoods, then the sum over ranks when a communicator exists
-static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
-                       double* d_out, cudaStream_t st) {
-    int rc = forward_local_dev(set, N, K, S, d_pi, d_T, d_E, d_out, st);
-    if (rc || !g_comm || N <= 0) return rc;
-    NCCL_TRY(g_nccl.AllReduce(d_out, d_out, (size_t)N, ncclDouble, ncclSum, g_comm, st));
-    return IMC_OK;
-}
-
-extern "C" int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T,
-                                     const double* d_E, double* d_out, void* stream) {
-    int rc = ensure_device();
-    if (rc) return rc;
-    if (N > 0 && (!d_pi || !d_T || !d_E || !d_out)) return fail(IMC_ERR_INVALID, "NULL device pointer");
-    return forward_dev(set, N, K, S, d_pi, d_T, d_E, d_out, (cudaStream_t)stream);
-}
-
-extern "C" int imc_forward_batch(imc_seqset* set, int N, int K, int S, const double* pi, const double* T,
-                                 const double* E, double* out) {
-    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
-    if (N < 0 || K < 1 || S < 1) return fail(IMC_ERR_INVALID, "bad sizes N=%d K=%d S=%d", N, K, S);
-    if (N == 0) return IMC_OK;
-    if (!pi || !T || !E || !out) return fail(IMC_ERR_INVALID, "NULL host pointer");
-    int rc = ensure_device();
-    if (rc) return rc;
-    const size_t npi = (size_t)N * K, nT = (size_t)N * K * K, nE = (size_t)N * K * S;
-    if ((rc = set->d_pi.reserve(npi * sizeof(double)))) return rc;
-    if ((rc = set->d_T.reserve(nT * sizeof(double)))) return rc;
-    if ((rc = set->d_E.reserve(nE * sizeof(double)))) return rc;
-    if ((rc = set->d_out.reserve((size_t)N * sizeof(double)))) return rc;
-    cudaStream_t st = g_ctx.stream;
-    CUDA_TRY(cudaMemcpyAsync(set->d_pi.p, pi, npi * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(set->d_T.p, T, nT * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(set->d_E.p, E, nE * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = forward_dev(set, N, K, S, (const double*)set->d_pi.p, (const double*)set->d_T.p, (const double*)set->d_E.p,
-                     (double*)set->d_out.p, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, set->d_out.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return IMC_OK;
-}
-
-extern "C" int imc_forward(imc_seqset* set, int K, int S, const double* pi, const double* T, const double* E,
-                           double* logL_out) {
-    return imc_forward_batch(set, 1, K, S, pi, T, E, logL_out);
-}
+#include "comm_host.inl"
 
 // ------------------------------------------------------------------------------------------ FP64 peak probe
 extern "C" int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops) {

@@ -1,0 +1,302 @@
+// Host side of the compressed (zip) forward path (included by imc_lib.cu): launch plans, device copies of the token
+// streams, segment descriptors, introspection entry points and the launcher of zip_forward_kernel.
+
+// ------------------------------------------------------------------------------------------ zip (compressed) path
+enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_PAIR = 2, KERNEL_DMMA = 3, KERNEL_ZIP = 4 };
+
+#define ZIP_K_LIST(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(32) X(40)
+// smallest instantiated tile that holds K states (the kernels take the actual K at run time and leave the padding
+// rows / columns of the tile at zero), or 0
+static int zip_tile(int K) {
+    static const int tiles[] = {
+#define X(k) k,
+        ZIP_K_LIST(X)
+#undef X
+    };
+    for (int t : tiles) if (t >= K) return t;
+    return 0;
+}
+static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
+
+struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
+static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
+
+// Launch shapes (all persistent, see zip_forward_kernel):
+//   lanes per chain 8: two CTAs of 256 threads per SM (K <= 24), or one CTA with all the shared memory for the
+//                      dictionary -- 512 threads where the register file allows (K <= 24), else 256;
+//   lanes per chain 4: one or (K <= 24) two CTAs of 256 threads (64 chains per CTA), K >= 8 only.
+// measured on B200 (gpurun_out/zip_bench_*.log, round 1): K=10 8.3 ms (8 lanes) vs 9.7 ms (4, padded to 12);
+// K=20 58.9 vs 43.7 ms; K=40 175 vs 190 ms (4 lanes need twice the exchange buffers, which costs dictionary entries)
+// (tools/k_sweep.py: tile 8 1.25 vs 1.34 ms with 4 lanes; tile 10 keeps 8 lanes, where one full load fetches the remainder
+// rows of four tokens)
+static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 : 8; }
+
+template <int K>
+static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
+    ZipPlan p;
+    p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
+    if (K < 8) p.lanes = 8;
+    if (p.lanes == 32 && K < 10) p.lanes = 8;
+    int m1, m2, t1;
+    if (p.lanes == 32) {       // one chain per warp, one CTA per SM (latency mode)
+        using C = ZipCfg32<K>;
+        t1 = K <= 24 ? 512 : 256;
+        m2 = 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+        want_ctas = 1;
+    } else if (p.lanes == 8) {
+        using C = ZipCfg8<K>;
+        t1 = K <= 24 ? 512 : 256;
+        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+    } else {
+        using C = ZipCfg4<K>;
+        t1 = 256;
+        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+    }
+    int ctas = want_ctas;
+    if (ctas == 2 && K > 24) ctas = 1;
+    if (ctas == 0) ctas = (K <= 24 && m2 >= avail_ids) ? 2 : 1;   // the bigger dictionary wins unless everything fits in half
+    p.ctas_per_sm = ctas;
+    p.threads = ctas == 2 ? 256 : t1;
+    p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
+    if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
+    p.M = std::max(p.M, S);
+    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads)
+           : (p.lanes == 4 ? ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg32<K>>::bytes(p.M, S, p.threads));
+    return p;
+}
+
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0) {
+    const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
+    switch (zip_tile(K)) {
+#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
+        ZIP_K_LIST(X)
+#undef X
+        default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
+    }
+    if (out->smem > ZIP_SMEM_SM) return fail(IMC_ERR_UNSUPPORTED, "zip kernel: %d symbols x K = %d do not fit in shared memory", S, K);
+    return IMC_OK;
+}
+
+// token streams over the first M dictionary ids, level-ordered, on the device (cached per M)
+static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
+    for (ZipDevice* z : set->zip_dev) if (z->M == M) { *out = z; return IMC_OK; }
+    const int ns = (int)set->streams.size();
+    ZipLevels zl = zip_levels(set->merges, M);
+    std::vector<std::vector<uint8_t>> tok(ns);
+    if (!parallel_for(ns, [&](int k) {
+            zip_expand(set->merges, set->tok_full[k], M, tok[k]);
+            for (auto& t : tok[k]) t = zl.perm[t];
+        })) return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams");
+    std::vector<int> order(ns);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tok[x].size() > tok[y].size(); });
+    std::vector<ZipChunk> chunks(ns);
+    long long off = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int k = order[i];
+        if (tok[k].size() > 0x7fffffffULL) return fail(IMC_ERR_UNSUPPORTED, "a chunk has more than 2^31-1 tokens");
+        chunks[i].tok_off = off;
+        chunks[i].ntok = (int)tok[k].size();
+        chunks[i].first_sym = set->first_sym[k];
+        chunks[i].out_index = k;
+        chunks[i].pad = 0;
+        off += (long long)((tok[k].size() + 15) / 16) * 16 + 16;
+    }
+    std::vector<uint8_t> flat((size_t)off, 0);
+    long long total = 0;
+    for (int i = 0; i < ns; ++i) {
+        const auto& t = tok[order[i]];
+        if (!t.empty()) memcpy(flat.data() + chunks[i].tok_off, t.data(), t.size());
+        total += (long long)t.size();
+    }
+    ZipDevice* z = new (std::nothrow) ZipDevice;
+    if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
+    z->M = M;
+    z->nlevels = (int)zl.level_start.size() - 1;
+    z->total_tokens = total;
+    z->max_ntok = ns ? chunks[0].ntok : 0;
+    z->host_chunks = chunks;
+    int rc;
+    if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
+        (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
+        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
+        delete z;
+        return rc;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!flat.empty()) e = cudaMemcpy(z->tokens.p, flat.data(), flat.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ns) e = cudaMemcpy(z->chunks.p, chunks.data(), sizeof(ZipChunk) * ns, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !zl.pairs.empty()) e = cudaMemcpy(z->pairs.p, zl.pairs.data(), zl.pairs.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(z->levels.p, zl.level_start.data(), sizeof(int) * zl.level_start.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
+        delete z;
+        return fail(IMC_ERR_CUDA, "uploading token streams failed: %s", cudaGetErrorString(e));
+    }
+    set->zip_dev.push_back(z);
+    *out = z;
+    return IMC_OK;
+}
+
+// chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen)
+static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
+    for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
+    std::vector<ZipChunk> chains;
+    std::vector<ZipFoldItem> items1, items2;
+    int nvec2 = 0;
+    for (const ZipChunk& ch : z->host_chunks) {
+        const int nseg = std::max(1, (ch.ntok + seglen - 1) / seglen);
+        const int first_chain = (int)chains.size();
+        for (int sg = 0; sg < nseg; ++sg) {
+            ZipChunk c = ch;
+            c.tok_off = ch.tok_off + (long long)sg * seglen;
+            c.ntok = std::max(0, std::min(seglen, ch.ntok - sg * seglen));
+            for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
+                c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
+                c.out_index = (int)chains.size();
+                chains.push_back(c);
+            }
+        }
+        // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
+        if (nseg <= 32) {
+            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0});
+        } else {        // two levels: groups of gs segments folded in parallel, then the groups
+            const int gs = (int)std::ceil(std::sqrt((double)nseg)), ngroups = (nseg + gs - 1) / gs;
+            const int base2 = nvec2;
+            for (int g = 0; g < ngroups; ++g) {
+                const int s0 = g * gs, s1 = std::min(nseg, s0 + gs);     // segments [s0, s1)
+                if (g == 0) {
+                    items1.push_back({first_chain, first_chain + 1, s1 - 1, nvec2++, 0, 1});
+                } else {
+                    for (int col = 0; col < K; ++col)
+                        items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1});
+                }
+            }
+            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0});
+        }
+    }
+    // the kernel takes chunks in list order, longest first: full segments first, tails last (out_index keeps identity)
+    std::vector<ZipChunk> sorted = chains;
+    std::stable_sort(sorted.begin(), sorted.end(), [](const ZipChunk& x, const ZipChunk& y) { return x.ntok > y.ntok; });
+    ZipSplit* sp = new (std::nothrow) ZipSplit;
+    if (!sp) return fail(IMC_ERR_NOMEM, "out of memory");
+    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size();
+    sp->n_level1 = (int)items1.size(); sp->n_final = (int)items2.size(); sp->nvec2 = nvec2;
+    int rc;
+    if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) ||
+        (rc = sp->items1.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items1.size(), 1))) ||
+        (rc = sp->items2.reserve(sizeof(ZipFoldItem) * std::max<size_t>(items2.size(), 1)))) {
+        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
+        return rc;
+    }
+    cudaError_t e = cudaMemcpy(sp->chunks.p, sorted.data(), sizeof(ZipChunk) * sorted.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !items1.empty()) e = cudaMemcpy(sp->items1.p, items1.data(), sizeof(ZipFoldItem) * items1.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !items2.empty()) e = cudaMemcpy(sp->items2.p, items2.data(), sizeof(ZipFoldItem) * items2.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sp->chunks.release(); sp->items1.release(); sp->items2.release(); delete sp;
+        return fail(IMC_ERR_CUDA, "uploading segment descriptors failed: %s", cudaGetErrorString(e));
+    }
+    z->splits.push_back(sp);
+    *out = sp;
+    return IMC_OK;
+}
+
+template <class C, int THREADS, int MINB>
+static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
+    static size_t attr_max = 0;
+    if (p.smem > attr_max) {
+        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<C, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        attr_max = p.smem;
+    }
+    zip_forward_kernel<C, THREADS, MINB><<<grid, THREADS, p.smem, st>>>(a);
+    return IMC_OK;
+}
+
+template <int K>
+static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
+    if constexpr (K >= 10) {
+        if (p.lanes == 32) {
+            if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1>(a, p, grid, st);
+            else return launch_zip_k<ZipCfg32<K>, 256, 1>(a, p, grid, st);
+        }
+    }
+    if constexpr (K >= 8) {
+        if (p.lanes == 4) {
+            if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2>(a, p, grid, st); }
+            return launch_zip_k<ZipCfg4<K>, 256, 1>(a, p, grid, st);
+        }
+    }
+    if constexpr (K <= 24) {
+        if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2>(a, p, grid, st);
+        return launch_zip_k<ZipCfg8<K>, 512, 1>(a, p, grid, st);
+    } else {
+        return launch_zip_k<ZipCfg8<K>, 256, 1>(a, p, grid, st);
+    }
+}
+
+static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
+    // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
+    const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
+    (void)nw;
+    const long long units = (long long)a.N * nunits;     // scarce work spreads one warp-load per CTA over the SMs
+    const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+    const int grid = (int)std::min<long long>(units, (long long)sms * p.ctas_per_sm);
+    // with fewer warp-loads than warps on the machine, let only as many warps per CTA claim work as it takes to cover
+    // them: the chains then spread over all SMs instead of piling onto the first CTAs that arrive
+    a.active_warps = (int)std::min<long long>(p.threads / 32, std::max<long long>(1, (units + grid - 1) / grid));
+    switch (zip_tile(a.K)) {
+#define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
+        ZIP_K_LIST(X)
+#undef X
+    }
+    return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", a.K);
+}
+
+extern "C" int imc_seqset_zip_info(imc_seqset* set, int K, int* ids_available, int* ids_used, int64_t* tokens, int* levels) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (ids_available) *ids_available = set->merges.size();
+    if (!ids_used && !tokens && !levels) return IMC_OK;
+    ZipPlan plan;
+    int rc = zip_plan(K, set->nsym, set->merges.size(), &plan);
+    if (rc) return rc;
+    if (ids_used) *ids_used = plan.M;
+    if (levels) *levels = (int)zip_levels(set->merges, plan.M).level_start.size() - 1;
+    if (tokens) {
+        std::vector<long long> len(set->merges.size(), 1);
+        for (int id = std::max(plan.M, set->nsym); id < set->merges.size(); ++id) {
+            const auto& pr = set->merges.pairs[id - set->nsym];
+            len[id] = len[pr[0]] + len[pr[1]];
+        }
+        long long total = 0;
+        for (const auto& t : set->tok_full) for (uint8_t x : t) total += len[x];
+        *tokens = total;
+    }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_zip_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs) {
+    if (!set || !pairs_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (capacity_pairs < (int)set->merges.pairs.size()) return fail(IMC_ERR_INVALID, "capacity %d < %zu pairs", capacity_pairs, set->merges.pairs.size());
+    for (size_t i = 0; i < set->merges.pairs.size(); ++i) { pairs_out[2 * i] = set->merges.pairs[i][0]; pairs_out[2 * i + 1] = set->merges.pairs[i][1]; }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_t* out, int64_t capacity, int64_t* ntokens) {
+    if (!set || !ntokens) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (chunk < 0 || chunk >= set->n_chunks) return fail(IMC_ERR_INVALID, "chunk %d out of range", chunk);
+    if (ids < set->nsym || ids > set->merges.size()) return fail(IMC_ERR_INVALID, "ids must be in [%d, %d]", set->nsym, set->merges.size());
+    const int k = set->stream_of_chunk[chunk];
+    if (k < 0) { *ntokens = 0; return IMC_OK; }
+    std::vector<uint8_t> tok;
+    zip_expand(set->merges, set->tok_full[k], ids, tok);
+    *ntokens = (int64_t)tok.size();
+    if (out) {
+        if (capacity < (int64_t)tok.size()) return fail(IMC_ERR_INVALID, "capacity %lld < %zu tokens", (long long)capacity, tok.size());
+        if (!tok.empty()) memcpy(out, tok.data(), tok.size());
+    }
+    return IMC_OK;
+}
+

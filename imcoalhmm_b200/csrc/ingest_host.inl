@@ -23,6 +23,38 @@ extern "C" int imc_seq_from_pair(const char* seq1, const char* seq2, int64_t L, 
     return seq_finish(s, out);
 }
 
+// Triplet / quartet columns (scripts/prepare-alignments.py:113-190): with every base in ACGT the symbol is
+// i1 + 4 i2 + 16 i3 (+ 32 i4 for quartets -- the script's own weight, reproduced as it is, so clean quartet columns
+// reach 159 and 128 is ambiguous: NSYM = 160 there), otherwise 64 (128).
+extern "C" int imc_seq_from_columns(const char* const* seqs, int n_seqs, int64_t L, imc_seq** out) {
+    if (!out || !seqs || L < 0) return fail(IMC_ERR_INVALID, "bad arguments");
+    if (n_seqs == 2) return imc_seq_from_pair(seqs[0], seqs[1], L, out);
+    if (n_seqs != 3 && n_seqs != 4) return fail(IMC_ERR_INVALID, "alignments of 2, 3 or 4 sequences are supported, not %d", n_seqs);
+    for (int k = 0; k < n_seqs; ++k) if (L > 0 && !seqs[k]) return fail(IMC_ERR_INVALID, "sequence %d is NULL", k);
+    static const struct Table { uint8_t code[256]; Table() {
+        for (int i = 0; i < 256; ++i) code[i] = 4;
+        code[(int)'A'] = code[(int)'a'] = 0; code[(int)'C'] = code[(int)'c'] = 1;
+        code[(int)'G'] = code[(int)'g'] = 2; code[(int)'T'] = code[(int)'t'] = 3;
+    } } tab;
+    static const int weight[4] = {1, 4, 16, 32};
+    const int missing = n_seqs == 3 ? 64 : 128;
+    imc_seq* s = new (std::nothrow) imc_seq;
+    if (!s) return fail(IMC_ERR_NOMEM, "out of memory");
+    s->nsym = n_seqs == 3 ? 65 : 160;
+    try { s->sym.resize((size_t)L); } catch (...) { delete s; return fail(IMC_ERR_NOMEM, "out of memory for %lld symbols", (long long)L); }
+    for (int64_t t = 0; t < L; ++t) {
+        int v = 0;
+        bool clean = true;
+        for (int k = 0; k < n_seqs; ++k) {
+            const uint8_t c = tab.code[(unsigned char)seqs[k][t]];
+            clean = clean && c < 4;
+            v += weight[k] * (c & 3);
+        }
+        s->sym[(size_t)t] = (uint8_t)(clean ? v : missing);
+    }
+    return seq_finish(s, out);
+}
+
 // FASTA: '>' starts a record, its name is the text up to the first whitespace; sequence lines are concatenated.
 static int read_fasta(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
     FILE* f = fopen(path, "rb");
@@ -72,6 +104,26 @@ extern "C" int imc_seq_from_fasta(const char* path, const char* name1, const cha
     if (seqs[i1].size() != seqs[i2].size())
         return fail(IMC_ERR_INVALID, "aligned sequences differ in length (%zu vs %zu)", seqs[i1].size(), seqs[i2].size());
     return imc_seq_from_pair(seqs[i1].data(), seqs[i2].data(), (int64_t)seqs[i1].size(), out);
+}
+
+extern "C" int imc_seq_from_fasta_n(const char* path, const char* const* record_names, int n_names, imc_seq** out) {
+    if (!path || !out || !record_names) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (n_names < 2 || n_names > 4) return fail(IMC_ERR_INVALID, "2, 3 or 4 record names are needed, got %d", n_names);
+    std::vector<std::string> names, seqs;
+    int rc = read_fasta(path, names, seqs);
+    if (rc) return rc;
+    const char* cols[4];
+    size_t len = 0;
+    for (int k = 0; k < n_names; ++k) {
+        int found = -1;
+        for (size_t i = 0; i < names.size(); ++i) if (record_names[k] && names[i] == record_names[k]) found = (int)i;
+        if (found < 0) return fail(IMC_ERR_INVALID, "record '%s' not found in '%s'", record_names[k] ? record_names[k] : "(null)", path);
+        if (k > 0 && seqs[found].size() != len)
+            return fail(IMC_ERR_INVALID, "aligned sequences differ in length (%zu vs %zu)", len, seqs[found].size());
+        len = seqs[found].size();
+        cols[k] = seqs[found].data();
+    }
+    return imc_seq_from_columns(cols, n_names, (int64_t)len, out);
 }
 
 // Binary container: "IMCSEQ1\0", int32 nsym, int32 bits per symbol (2 or 8), int64 L, packed symbols (little endian,

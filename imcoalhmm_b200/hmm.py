@@ -220,12 +220,36 @@ class Forwarder(object):
         return self
 
     @classmethod
-    def from_fasta(cls, path, names=None):
-        """The two named records of a FASTA alignment (or its only two) as one pairwise Forwarder."""
+    def from_sequences(cls, *sequences):
+        """2, 3 or 4 aligned sequences -> one symbol per column (prepare-alignments.py:77-190): pairs 0/1/2, triplets
+        i1 + 4 i2 + 16 i3 or 64, quartets i1 + 4 i2 + 16 i3 + 32 i4 or 128 (the script's weights: NSYM = 160)."""
+        seqs = [s.encode("ascii", "replace") if isinstance(s, str) else bytes(s) for s in sequences]
+        if len({len(s) for s in seqs}) > 1:
+            raise ValueError("aligned sequences differ in length")
+        arr = (ctypes.c_char_p * len(seqs))(*seqs)
         self = cls.__new__(cls)
         h = _lib.c_vp()
-        n1, n2 = (None, None) if names is None else (str(names[0]).encode(), str(names[1]).encode())
+        check(_lib.load().imc_seq_from_columns(arr, len(seqs), len(seqs[0]) if seqs else 0, ctypes.byref(h)))
+        self._finish(_Seq(h), {2: 3, 3: 65, 4: 160}[len(seqs)])
+        return self
+
+    @classmethod
+    def from_fasta(cls, path, names=None):
+        """The named records of a FASTA alignment (two, three or four; or its only two) as one Forwarder."""
+        self = cls.__new__(cls)
+        h = _lib.c_vp()
         lib = _lib.load()
+        if names is not None and len(names) != 2:
+            arr = (ctypes.c_char_p * len(names))(*[str(n).encode() for n in names])
+            rc = lib.imc_seq_from_fasta_n(os.fsencode(path), arr, len(names), ctypes.byref(h))
+            if rc == -5 and not os.path.exists(path):
+                raise IOError(lib.imc_last_error().decode())
+            if rc in (-5, -1):
+                raise ValueError(lib.imc_last_error().decode())
+            check(rc)
+            self._finish(_Seq(h), {3: 65, 4: 160}[len(names)])
+            return self
+        n1, n2 = (None, None) if names is None else (str(names[0]).encode(), str(names[1]).encode())
         rc = lib.imc_seq_from_fasta(os.fsencode(path), n1, n2, ctypes.byref(h))
         if rc == -5 and not os.path.exists(path):
             raise IOError(lib.imc_last_error().decode())

@@ -56,6 +56,11 @@ int imc_seq_from_file(const char* path, int nsym, imc_seq** out);
  * named records (record name = header text up to the first blank), or the only two when both names are NULL. */
 int imc_seq_from_pair(const char* seq1, const char* seq2, int64_t L, imc_seq** out);
 int imc_seq_from_fasta(const char* path, const char* name1, const char* name2, imc_seq** out);
+/* 2, 3 or 4 aligned sequences: pairs as above; triplets i1 + 4 i2 + 16 i3 with 64 for any base outside ACGT (NSYM = 65),
+ * quartets i1 + 4 i2 + 16 i3 + 32 i4 with 128 -- prepare-alignments.py:113-190, weights as in the script (clean quartet
+ * columns therefore reach 159 and 128 is ambiguous; NSYM = 160). */
+int imc_seq_from_columns(const char* const* seqs, int n_seqs, int64_t L, imc_seq** out);
+int imc_seq_from_fasta_n(const char* path, const char* const* record_names, int n_names, imc_seq** out);
 /* Binary container for a symbol sequence (2 bits per symbol for NSYM <= 4): 16x smaller than the text format. */
 int imc_seq_save(const imc_seq* seq, const char* path);
 int imc_seq_load(const char* path, imc_seq** out);

@@ -77,3 +77,30 @@ def test_reference_example_alignment_matches_committed_fixture():
     import imcoalhmm_b200 as m
     f = m.Forwarder.from_fasta("/root/reference/examples/example_data.fa", names=("hg18", "pantro2"))
     assert np.array_equal(f._seq.symbols(), example_symbols())
+
+
+def test_triplet_and_quartet_columns_bit_exact(tmp_path):
+    """prepare-alignments.py:113-190: i1 + 4 i2 + 16 i3 (+ 32 i4, the script's own weight) or 64 / 128 for unclean columns."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(1)
+    nuc = {"A": 0, "C": 1, "G": 2, "T": 3}
+    seqs = ["".join(rng.choice(list("ACGTacgtN-"), size=3000, p=[.22, .22, .22, .22, .02, .02, .02, .02, .02, .02])) for _ in range(4)]
+
+    def rule(cols, weights, missing):
+        out = []
+        for bases in zip(*cols):
+            up = [b.upper() for b in bases]
+            out.append(sum(w * nuc[b] for w, b in zip(weights, up)) if all(b in nuc for b in up) else missing)
+        return np.array(out, dtype=np.uint8)
+    f3 = m.Forwarder.from_sequences(*seqs[:3])
+    assert f3.NSYM == 65 and np.array_equal(f3._seq.symbols(), rule(seqs[:3], (1, 4, 16), 64))
+    f4 = m.Forwarder.from_sequences(*seqs)
+    assert f4.NSYM == 160 and np.array_equal(f4._seq.symbols(), rule(seqs, (1, 4, 16, 32), 128))
+    f2 = m.Forwarder.from_sequences(seqs[0], seqs[1])
+    assert f2.NSYM == 3 and np.array_equal(f2._seq.symbols(), python_rule(seqs[0], seqs[1]))
+    p = tmp_path / "t.fa"
+    p.write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    g3 = m.Forwarder.from_fasta(str(p), names=("s2", "s0", "s3"))
+    assert np.array_equal(g3._seq.symbols(), rule([seqs[2], seqs[0], seqs[3]], (1, 4, 16), 64))
+    with pytest.raises(ValueError):
+        m.Forwarder.from_sequences("ACGT", "ACG", "ACGT")

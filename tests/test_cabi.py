@@ -106,3 +106,33 @@ def test_legacy_matrix_objects_are_accepted():
     a = _hmm_arrays(Matrix(pi), Matrix(T), Matrix(E), batched=False)
     b = _hmm_arrays(pi, T, E, batched=False)
     assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3:] == b[3:] == (1, 4, 3)
+
+
+def test_options_are_validated_on_the_host():
+    import imcoalhmm_b200 as m
+    for key, good, bad in (("forward_kernel", 4, 5), ("zip_lanes", 32, 16), ("zip_ctas_per_sm", 2, 3), ("zip_max_entries", 256, 257),
+                           ("zip_segment_tokens", -1, -2), ("dmma_mtiles", 4, 3)):
+        m.set_option(key, good)
+        assert m.get_option(key) == good
+        with pytest.raises(m.IMCError):
+            m.set_option(key, bad)
+        m.set_option(key, 0)
+        assert m.get_option(key) == 0
+    with pytest.raises(m.IMCError):
+        m.set_option("no_such_option", 1)
+    with pytest.raises(m.IMCError):
+        m.get_option("no_such_option")
+
+
+def test_forward_without_a_gpu_fails_loudly(have_gpu):
+    """No CPU fallback: on a box without a usable device every forward call raises instead of computing on the host."""
+    import imcoalhmm_b200 as m
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    f = m.Forwarder.from_symbols(np.array([0, 1, 2, 0], dtype=np.int32), 3)
+    K = 4
+    with pytest.raises(m.IMCError) as e:
+        f.forward(np.full(K, 0.25), np.full((K, K), 0.25), np.full((K, 3), 1.0 / 3))
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(m.IMCError):
+        m.IsolationModel(4).build_hidden_markov_model(np.array([1e-3, 1000.0, 0.4]))

@@ -64,3 +64,34 @@ def test_full_size_oracle_spot_check(full_c2):
     got = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in sub]).forward_batch(pis[:4], Ts[:4], Es[:4])
     want, _ = F.forward_batch([c.astype(np.int32) for c in sub], pis[:4], Ts[:4], Es[:4])
     np.testing.assert_allclose(got, want, rtol=1e-11)
+
+
+def test_full_size_im_model_shard():
+    """configs[2] per-GPU shard (IM model K=10+10, 125 x 1 Mbp) on 256 parameter points: the compressed kernel (4 lanes per
+    chain), the per-site DMMA kernel that walks all 1.25e8 sites, chunk additivity over independently preprocessed halves,
+    and the warp-per-chain route of single-point calls must all agree."""
+    import bench
+    import imcoalhmm_b200 as m
+    wl = bench.WORKLOADS["c3_1gpu"]
+    model = m.IsolationMigrationModel(10, 10)
+    thetas = bench.thetas_around(wl["default"], 256)
+    pis, Ts, Es, st = model.build_hidden_markov_models(thetas)
+    assert (st == 0).all()
+    chunks = bench.make_chunks(wl, pis, Ts, Es, range(wl["chunks"]))
+    mk = lambda cs: m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in cs])
+    whole_set = mk(chunks)
+    whole = whole_set.forward_batch(pis, Ts, Es)
+    assert m.last_forward_kernel() == "zip" and np.isfinite(whole).all()
+    halves = mk(chunks[:60]).forward_batch(pis, Ts, Es) + mk(chunks[60:]).forward_batch(pis, Ts, Es)
+    np.testing.assert_allclose(halves, whole, rtol=1e-12)
+    m.set_option("forward_kernel", 3)
+    try:
+        plain = whole_set.forward_batch(pis[:64], Ts[:64], Es[:64])
+        assert m.last_forward_kernel() == "dmma"
+    finally:
+        m.set_option("forward_kernel", 0)
+    np.testing.assert_allclose(plain, whole[:64], rtol=1e-11)
+    one = whole_set.forward(pis[5], Ts[5], Es[5])
+    assert m.last_forward_kernel() in ("zip-warp", "zip-segmented")
+    assert one == pytest.approx(whole[5], rel=1e-12)
+    np.testing.assert_allclose(model.batched_log_likelihood(thetas[:32], whole_set), whole[:32], rtol=1e-12)

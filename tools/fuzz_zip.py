@@ -37,7 +37,13 @@ for trial in range(trials):
     seg = int(rng.choice([0, 0, -1, 16, 64, 700]))
     cap = int(rng.choice([0, 0, nsym, nsym + 1, 9, 40]))
     cap = cap if cap == 0 or cap >= nsym else nsym
-    fk = int(rng.choice([4, 4, 4, 0]))                       # mostly the zip kernel forced, sometimes the automatic choice
+    fk = int(rng.choice([4, 4, 4, 0, 1, 2, 3]))              # mostly the zip kernel; also the automatic choice and the per-site kernels
+    if fk in (1, 2, 3) and nsym > 3:
+        fk = 4                                               # the packed 2-bit layout of the per-site kernels holds 3 symbols
+    if fk == 2 and (K % 2 or K > 12):
+        fk = 1
+    if fk == 3 and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
+        fk = 1
     for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap)):
         m.set_option(k, v)
     got = fset.forward_batch(pis, Ts, Es)

@@ -549,35 +549,30 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     const int nunits = (a.nchunks + C::CPW - 1) / C::CPW;
     int primary = blockIdx.x;          // next point of this CTA's own share
     int scan = (int)(((long long)blockIdx.x * 7919) % a.N);   // where the search for points to help starts
-    if (tid == 0) s_point[1] = 0x7fffffff;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_point + 2);
     for (;;) {
-        // ---- choose a point: own share first, then any point with unclaimed quads.  s_point[0] = point, -1 = none
-        // left anywhere, -2 = own point already finished by helpers.  All decisions go through shared memory so
-        // that they are uniform over the CTA.
+        // ---- choose a point: own share first, then the point with the MOST unclaimed warp-loads (ties: the first one
+        // after this CTA's own scan start, so that helpers spread out).  s_point[0] = point, -1 = none left anywhere,
+        // -2 = own point already finished by helpers.  All decisions go through shared memory so that they are uniform
+        // over the CTA.
         __syncthreads();               // everybody is done with the previous point's dictionary and s_point[0]
         if (primary < a.N) {
             if (tid == 0) s_point[0] = *((volatile int*)(a.point_next + primary)) < nunits ? primary : -2;
             primary += gridDim.x;
         } else {
-            if (tid == 0) s_point[0] = -1;
-            for (int r0 = 0; r0 < a.N; r0 += THREADS) {
-                __syncthreads();       // s_point[1] == INT_MAX here
-                const int idx = r0 + tid;
-                if (idx < a.N && *((volatile int*)(a.point_next + (scan + idx) % a.N)) < nunits) atomicMin(s_point + 1, idx);
-                __syncthreads();
-                const int best = s_point[1];
-                if (best != 0x7fffffff) {
-                    __syncthreads();   // everyone has read `best`
-                    if (tid == 0) { s_point[0] = (scan + best) % a.N; s_point[1] = 0x7fffffff; }
-                    break;
-                }
+            if (tid == 0) { s_point[0] = -1; *s_best = 0ull; }
+            __syncthreads();
+            for (int idx = tid; idx < a.N; idx += THREADS) {
+                const int left = nunits - *((volatile int*)(a.point_next + (scan + idx) % a.N));
+                if (left > 0) atomicMax(s_best, ((unsigned long long)left << 32) | (0xffffffffu - (unsigned)idx));
             }
+            __syncthreads();
+            if (tid == 0 && *s_best != 0ull) s_point[0] = (scan + (int)(0xffffffffu - (unsigned)(*s_best & 0xffffffffull))) % a.N;
         }
         __syncthreads();
         const int n = s_point[0];
         if (n == -1) break;
         if (n == -2) continue;
-        if (primary >= a.N) scan = (n + 1) % a.N;
         zip_build_dictionary<C, THREADS>(a, n, dict, sE, spi, dexp);
         for (; warp < a.active_warps;) {
             int unit = 0;

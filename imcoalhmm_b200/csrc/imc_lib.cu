@@ -214,16 +214,17 @@ extern "C" int imc_seq_from_file(const char* path, int nsym, imc_seq** out) {
     // whitespace-separated base-10 integers (python: map(int, text.split()), hmm.py:13-14)
     std::vector<char> buf(1 << 20);
     long long cur = 0;
-    bool in_num = false, neg = false;
+    bool in_num = false, neg = false, digits = false;
     int rc = IMC_OK;
     size_t got;
     long long pos = 0;
     auto flush = [&]() -> int {
         if (!in_num) return IMC_OK;
+        if (!digits) return fail(IMC_ERR_IO, "token %zu of '%s' is a sign without digits", s->sym.size(), path);
         const long long v = neg ? -cur : cur;
         if (v < 0 || v >= nsym) return fail(IMC_ERR_INVALID, "symbol %lld (token %zu) in '%s' is outside [0, %d)", v, s->sym.size(), path, nsym);
         s->sym.push_back((uint8_t)v);
-        in_num = false; neg = false; cur = 0;
+        in_num = false; neg = false; digits = false; cur = 0;
         return IMC_OK;
     };
     while (rc == IMC_OK && (got = fread(buf.data(), 1, buf.size(), f)) > 0) {
@@ -232,7 +233,7 @@ extern "C" int imc_seq_from_file(const char* path, int nsym, imc_seq** out) {
             if (ch >= '0' && ch <= '9') {
                 cur = cur * 10 + (ch - '0');
                 if (cur > 1000000) cur = 1000000;  // saturate; rejected by the range check
-                in_num = true;
+                in_num = true; digits = true;
             } else if (ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\f' || ch == '\v') {
                 rc = flush();
             } else if ((ch == '-' || ch == '+') && !in_num) {

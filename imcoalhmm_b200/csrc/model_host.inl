@@ -256,7 +256,7 @@ extern "C" int imc_model_info(const imc_model* m, int* K, int* P) {
 
 extern "C" int imc_model_destroy(imc_model* m) {
     if (!m) return IMC_OK;
-    if (m->uploaded && g_ctx.pid == getpid()) {
+    if (g_ctx.pid == getpid()) {      // buffers may exist before the static tables were uploaded
         for (DeviceBuf* b : {&m->d_static, &m->d_theta, &m->d_params, &m->d_scratch, &m->d_status, &m->d_pbuf,
                              &m->d_prebuf, &m->d_pi, &m->d_T, &m->d_E, &m->d_out}) b->release();
     }

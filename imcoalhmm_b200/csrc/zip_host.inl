@@ -81,7 +81,12 @@ static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_overrid
 }
 
 // token streams over the first M dictionary ids, level-ordered, on the device (cached per M)
+static int zip_device_build(imc_seqset* set, int M, ZipDevice** out);
 static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
+    try { return zip_device_build(set, M, out); }
+    catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams"); }
+}
+static int zip_device_build(imc_seqset* set, int M, ZipDevice** out) {
     for (ZipDevice* z : set->zip_dev) if (z->M == M) { *out = z; return IMC_OK; }
     const int ns = (int)set->streams.size();
     ZipLevels zl = zip_levels(set->merges, M);
@@ -118,7 +123,7 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
     z->max_ntok = ns ? chunks[0].ntok : 0;
-    z->host_chunks = chunks;
+    z->host_chunks.swap(chunks);      // no copy, cannot throw
     int rc;
     if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
         (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
@@ -128,7 +133,7 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
     }
     cudaError_t e = cudaSuccess;
     if (!flat.empty()) e = cudaMemcpy(z->tokens.p, flat.data(), flat.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && ns) e = cudaMemcpy(z->chunks.p, chunks.data(), sizeof(ZipChunk) * ns, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ns) e = cudaMemcpy(z->chunks.p, z->host_chunks.data(), sizeof(ZipChunk) * ns, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !zl.pairs.empty()) e = cudaMemcpy(z->pairs.p, zl.pairs.data(), zl.pairs.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(z->levels.p, zl.level_start.data(), sizeof(int) * zl.level_start.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -142,7 +147,12 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
 }
 
 // chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen)
+static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out);
 static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
+    try { return zip_split_build(z, K, seglen, out); }
+    catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while cutting chunks into segments"); }
+}
+static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
     for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
     std::vector<ZipChunk> chains;
     std::vector<ZipFoldItem> items1, items2;

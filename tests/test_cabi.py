@@ -44,6 +44,11 @@ def test_host_side_sequence_handling_without_gpu(tmp_path):
     bad.write_text("0 1 x 2")
     with pytest.raises(ValueError):
         m.Forwarder(str(bad), 3)
+    bad.write_text("0 1 - 2")                       # a sign without digits: int("-") raises in the reference (hmm.py:14)
+    with pytest.raises(ValueError):
+        m.Forwarder(str(bad), 3)
+    bad.write_text("0 +1 2\n")                      # int("+1") == 1
+    assert m.Forwarder(str(bad), 3).new_obs.tolist() == [0, 1, 2]
     bad.write_text("0 1 3 2")                       # symbol outside [0, NSYM)
     with pytest.raises(ValueError):
         m.Forwarder(str(bad), 3)

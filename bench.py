@@ -234,6 +234,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs)")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl", "torch"],
+                    help="N > 1: all-reduce inside the library's reduction kernel over peer memory (falls back to its "
+                         "ncclAllReduce where the mailboxes cannot be mapped), the library's ncclAllReduce, or "
+                         "torch.distributed.all_reduce on the partial sums")
     ap.add_argument("--forward-kernel", type=int, default=0,
                     help="0 auto (zip: compressed token streams), 2 lane-pair DFMA, 3 DMMA (2/3 walk every site)")
     args = ap.parse_args()
@@ -284,6 +288,20 @@ def main():
             os.close(saved)
     m._lib.check(m._lib.load().imc_init(local_rank))
     dev = torch.device("cuda", local_rank)
+    lib_comm = False
+    if world > 1 and args.collective != "torch":
+        # the library's own communicator: rank 0 draws the id, torch.distributed carries it to the other ranks
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(m._lib.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        m.set_option("comm_fused", 1 if args.collective == "fused" else 0)
+        m._lib.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        lib_comm = True
+        config["collective"] = ("all-reduce fused into the chain-reduction kernel (peer-to-peer stores over NVLink)"
+                                if m._lib.comm_info()["fused"] else "ncclAllReduce issued by the library")
+    elif world > 1:
+        config["collective"] = "torch.distributed.all_reduce (NCCL)"
 
     m.set_option("forward_kernel", args.forward_kernel)
     model = getattr(m, wl["ctor"][0])(*wl["ctor"][1])
@@ -309,8 +327,8 @@ def main():
     def step():
         # theta -> (pi,T,E) -> logL on the device: 3 model-build kernels, forward, chunk reduction, status fix-up
         model.batched_log_likelihood_device(d_theta.data_ptr(), fset, d_out.data_ptr(), N, 0, stream.cuda_stream)
-        if dist is not None:
-            dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods
+        if dist is not None and not lib_comm:
+            dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods (lib_comm: done inside the call)
 
     peak_dfma, peak_dmma = m.measure_fp64_peak()
     sampler = ClockSampler(local_rank)       # samples nvidia-smi every ~100 ms from the warm-up steps to the end of the timed region
@@ -343,6 +361,7 @@ def main():
 
     # ---- kernel-only time of the dominant kernel (forward kernel without the reduce / all-reduce) ----
     kt = []
+    m.set_option("comm_enabled", 0)          # this rank's kernel alone
     for _ in range(min(3, args.steps)):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -353,6 +372,7 @@ def main():
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b) * 1e-3)
     t_kernel = float(np.mean(kt))
+    m.set_option("comm_enabled", 1)
 
     # ---- end to end through the host API (Model.batched_log_likelihood -> imc_loglik_batch): pinned host theta in,
     # host logL + status out, every step; model build and forward on the device in between ----
@@ -367,7 +387,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         np_out = model.batched_log_likelihood(np_theta, fset)   # synchronous: returns with logL on the host
-        if dist is not None:
+        if dist is not None and not lib_comm:
             tmp = torch.from_numpy(np_out).to(dev)
             dist.all_reduce(tmp)
             np_out[:] = tmp.cpu().numpy()
@@ -378,6 +398,8 @@ def main():
         t_e2e = float(tt.item())
     h2d = thetas.nbytes
     d2h = N * 8 + N * 4
+    if lib_comm:
+        m._lib.comm_destroy()      # collective; what follows (parity gate, CPU baseline) runs on rank 0 alone
     if world == 1:
         assert np.allclose(np_out, logl_dev, rtol=1e-12), "host API and device API disagree"
 

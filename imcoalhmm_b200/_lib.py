@@ -59,6 +59,7 @@ _SIGNATURES = {
     "imc_comm_unique_id": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "imc_comm_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp]),
     "imc_comm_destroy": (ctypes.c_int, []),
+    "imc_comm_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "imc_model_create": (ctypes.c_int, [ctypes.c_int, c_i32p, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "imc_model_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "imc_model_destroy": (ctypes.c_int, [c_vp]),
@@ -133,6 +134,13 @@ def comm_init(nranks, rank, unique_id=None):
 
 def comm_destroy():
     check(load().imc_comm_destroy())
+
+
+def comm_info():
+    """dict(nranks, rank, fused): fused = the all-reduce runs inside the reduction kernel over peer memory (NVLink)."""
+    n, r, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(load().imc_comm_info(ctypes.byref(n), ctypes.byref(r), ctypes.byref(f)))
+    return {"nranks": n.value, "rank": r.value, "fused": bool(f.value)}
 
 
 def kernel_launches():

@@ -544,6 +544,66 @@ __global__ void reduce_chains_kernel(const double* chain_out, int nstreams, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same reduction fused with the all-reduce over ranks (one process per GPU, chunks sharded): every block
+// pushes its point's partial sum straight into the mailbox of EVERY rank with peer-to-peer stores over NVLink; the last
+// block of the grid to deliver raises this rank's flag in all mailboxes, waits for the other ranks' flags and adds the
+// rows up in rank order (bitwise the same result on every rank).  Mailbox of a rank: double val[2][nranks][nmax] (two
+// epochs, so that a rank that runs ahead never overwrites rows a slower rank is still reading) followed by one
+// 128-byte flag line per source rank holding the epoch it has delivered.  No NCCL call, no extra launch.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 32;
+struct PeerReduceArgs {
+    int nranks, rank, nmax;
+    unsigned epoch;                 // 1, 2, ... one per collective call, the same sequence on every rank
+    double* box[MAX_PEERS];         // val array of rank r's mailbox as mapped into this process
+    unsigned* flag[MAX_PEERS];      // flag lines of rank r's mailbox: flag[r][32 * source]
+    unsigned* counter;              // local: blocks of this launch that have delivered (left at 0)
+};
+
+__global__ void __launch_bounds__(256) reduce_chains_peer_kernel(const double* chain_out, int nstreams, double* out, PeerReduceArgs pa) {
+    __shared__ double sh[256];
+    __shared__ int s_last;
+    const int n = blockIdx.x, tid = threadIdx.x, N = gridDim.x;
+    const double* src = chain_out + (size_t)n * nstreams;
+    double acc = 0.0;
+    for (int s = tid; s < nstreams; s += 256) acc += src[s];
+    sh[tid] = acc;
+    __syncthreads();
+    for (int m = 128; m >= 1; m >>= 1) {
+        if (tid < m) sh[tid] += sh[tid + m];
+        __syncthreads();
+    }
+    const size_t row = ((size_t)(pa.epoch & 1u) * pa.nranks) * pa.nmax;
+    if (tid == 0) {
+        const double v = sh[0];
+        for (int r = 0; r < pa.nranks; ++r)
+            *((volatile double*)(pa.box[r] + row + (size_t)pa.rank * pa.nmax + n)) = v;
+        __threadfence_system();                                   // the rows are out before this block counts as delivered
+        s_last = atomicAdd(pa.counter, 1u) == (unsigned)(N - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) {
+        __threadfence_system();                                   // every block's rows (seen through the counter) before the flag
+        for (int r = 0; r < pa.nranks; ++r)
+            if (r != pa.rank) *((volatile unsigned*)(pa.flag[r] + 32 * pa.rank)) = pa.epoch;
+    }
+    for (int r = 0; r < pa.nranks; ++r) {                         // every thread waits for every source itself
+        if (r == pa.rank) continue;
+        const volatile unsigned* f = pa.flag[pa.rank] + 32 * r;
+        while ((int)(*f - pa.epoch) < 0) __nanosleep(64);
+    }
+    __threadfence_system();
+    const double* mine = pa.box[pa.rank] + row;
+    for (int i = tid; i < N; i += 256) {
+        double s = 0.0;
+        for (int r = 0; r < pa.nranks; ++r) s += *((const volatile double*)(mine + (size_t)r * pa.nmax + i));
+        out[i] = s;
+    }
+    if (tid == 0) *pa.counter = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak probes (the roofline denominator is measured in the same run: MEASURED_PEAKS.json has no FP64 entry)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) peak_dfma_kernel(double* out, int iters, double a, double b) {

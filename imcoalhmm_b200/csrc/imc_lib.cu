@@ -61,6 +61,8 @@ struct Context {
     long long opt_zip_lanes = 0;       // lanes per chain in the zip kernel: 8, 4 or 0 = auto
     long long opt_zip_segment_tokens = 0;  // tokens per segment in segmented mode: 0 = auto, -1 = never, > 0 = forced
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
+    long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
+    long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
 };
 static Context g_ctx;
 
@@ -487,6 +489,8 @@ static int launch_generic(const FwdArgs& a, cudaStream_t st) {
     return IMC_OK;
 }
 
+static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out, cudaStream_t st);   // comm_host.inl
+
 static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
                              double* d_out, cudaStream_t st) {
     if (!set) return fail(IMC_ERR_INVALID, "NULL set");
@@ -498,10 +502,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
     int rc = ensure_device();
     if (rc) return rc;
     const int ns = (int)set->streams.size();
-    if (ns == 0) {   // only empty chunks: logL = 0 for every point
-        CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)N, st));
-        return IMC_OK;
-    }
+    if (ns == 0) return launch_chain_reduce(nullptr, 0, N, d_out, st);   // only empty chunks here: this rank adds 0 to every point
     if ((rc = set->d_chain.reserve(sizeof(double) * (size_t)N * ns))) return rc;
 
     int which = (int)g_ctx.opt_forward_kernel;
@@ -622,10 +623,8 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
             CUDA_TRY(cudaGetLastError());
             g_launches += 1;
         }
-        reduce_chains_kernel<<<N, 256, 0, st>>>(za.chain_out, ns, d_out);
-        CUDA_TRY(cudaGetLastError());
-        g_launches += 2;
-        return IMC_OK;
+        g_launches += 1;
+        return launch_chain_reduce(za.chain_out, ns, N, d_out, st);
     }
     if (!set->packable)
         return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols run on the zip kernel only (nsym = %d, K = %d)", set->nsym, K);
@@ -676,10 +675,8 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
     }
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
-    reduce_chains_kernel<<<N, 256, 0, st>>>(a.chain_out, ns, d_out);
-    CUDA_TRY(cudaGetLastError());
-    g_launches += 2;
-    return IMC_OK;
+    g_launches += 1;
+    return launch_chain_reduce(a.chain_out, ns, N, d_out, st);
 }
 
 #include "comm_host.inl"
@@ -737,6 +734,8 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_segment_tokens")) { if (value < -1) return fail(IMC_ERR_INVALID, "zip_segment_tokens must be >= -1"); g_ctx.opt_zip_segment_tokens = value; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8 && value != 32) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4, 8 or 32"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
+    if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
+    if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int imc_get_option(const char* key, int64_t* value_out) {
@@ -748,6 +747,8 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_segment_tokens")) { *value_out = g_ctx.opt_zip_segment_tokens; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { *value_out = g_ctx.opt_zip_lanes; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
+    if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
+    if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }

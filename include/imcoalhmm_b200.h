@@ -111,14 +111,25 @@ int imc_forward_batch_dev(imc_seqset* set, int N, int K, int S, const double* d_
 
 /* ---- multi-GPU (one process per GPU): chunks are sharded over the ranks, every rank scores the same parameter batch on
  * its own sequence set, and once a communicator exists every forward / loglik entry point above and below returns the SUM
- * over ranks -- one ncclAllReduce of float64[N] per batch, the only collective of the path (likelihood.py:33 sums over
+ * over ranks -- one all-reduce of float64[N] per batch, the only collective of the path (likelihood.py:33 sums over
  * forwarders; here the forwarders live on different GPUs).  Rank 0 draws the id and hands its bytes to the other ranks by
  * any means (file, pipe, MPI, torch.distributed); all ranks then call imc_comm_init after imc_init(device).  NCCL is
- * loaded with dlopen at that point (no link-time dependency). */
+ * loaded with dlopen at that point (no link-time dependency) and used for the bootstrap.
+ *
+ * On one node the all-reduce is FUSED into the kernel that sums a rank's chains: imc_comm_init maps a small mailbox of
+ * every rank into every other rank (CUDA IPC), the reduction kernel stores each point's partial sum into all mailboxes
+ * with peer-to-peer writes over NVLink, and its last block adds the rows up in rank order (the same bits on every rank;
+ * no extra launch, no NCCL call per batch).  Where the mailboxes cannot be mapped (ranks on different nodes, IPC not
+ * permitted) or a batch has more than 65536 points, the sum is one ncclAllReduce instead; imc_comm_info tells which.
+ * All ranks must issue the same sequence of forward / loglik calls (as with any collective), set the options
+ * "comm_fused" (default 1; 0 = always NCCL; read by imc_comm_init) and "comm_enabled" (default 1; 0 = calls return this
+ * rank's partial sums) identically, and call imc_comm_destroy together. */
 #define IMC_COMM_ID_BYTES 128
 int imc_comm_unique_id(void* id_out, int capacity);
 int imc_comm_init(int nranks, int rank, const void* nccl_id);
 int imc_comm_destroy(void);
+/* any pointer may be NULL; *fused = 1 when the peer-memory kernel performs the all-reduce */
+int imc_comm_info(int* nranks, int* rank, int* fused);
 
 /* ---- batched model build: theta -> (pi, T, E) on the GPU ----------------------------------------------
  * Replaces Model.build_hidden_markov_model (model.py:44-49) and everything under it (state_spaces.py, CTMC.py,

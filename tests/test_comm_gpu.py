@@ -11,11 +11,7 @@ from conftest import golden_model, example_symbols
 pytestmark = pytest.mark.gpu
 
 
-def _rank(rank, world, tmp, lengths):
-    import imcoalhmm_b200 as m
-    lib = m._lib.load()
-    m._lib.check(lib.imc_init(rank))
-    idfile = os.path.join(tmp, "nccl_id")
+def _connect(m, rank, world, idfile):
     if rank == 0:
         uid = m._lib.comm_unique_id()
         with open(idfile + ".tmp", "wb") as f:
@@ -28,16 +24,39 @@ def _rank(rank, world, tmp, lengths):
             time.sleep(0.1)
         uid = open(idfile, "rb").read()
     m._lib.comm_init(world, rank, uid)
+
+
+def _rank(rank, world, tmp, lengths):
+    import imcoalhmm_b200 as m
+    lib = m._lib.load()
+    m._lib.check(lib.imc_init(rank))
     theta, pis, Ts, Es = golden_model("isolation_k10")
     obs = example_symbols()
     cuts = np.concatenate([[0], np.cumsum(lengths)])
     mine = [obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths)) if c % world == rank]
     fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in mine])
-    a = fset.forward_batch(pis[:6], Ts[:6], Es[:6])                       # host arrays in, summed over ranks
-    b = m.IsolationModel(10).batched_log_likelihood(theta[:6], fset)      # fused theta -> logL, summed over ranks
-    c = fset.forward(pis[2], Ts[2], Es[2])                                # chain-scarce single point
-    np.save(os.path.join(tmp, "out%d.npy" % rank), np.concatenate([a, b, [c]]))
-    m._lib.comm_destroy()
+    # a rank whose shard holds nothing but an empty chunk still takes part in the sum
+    lonely = fset if rank == 0 else m.ForwarderSet([m.Forwarder.from_symbols(np.zeros(0, dtype=np.int32), 3)])
+    model = m.IsolationModel(10)
+    results, fused = [], []
+    for phase in range(2):      # 0: all-reduce fused into the reduction kernel over peer memory; 1: ncclAllReduce
+        m.set_option("comm_fused", 1 - phase)
+        _connect(m, rank, world, os.path.join(tmp, "nccl_id%d" % phase))
+        fused.append(m._lib.comm_info()["fused"])
+        assert m._lib.comm_info()["nranks"] == world and m._lib.comm_info()["rank"] == rank
+        for rep in range(3):    # several epochs through the two mailbox halves
+            a = fset.forward_batch(pis[:6], Ts[:6], Es[:6])                   # host arrays in, summed over ranks
+        b = model.batched_log_likelihood(theta[:6], fset)                     # fused theta -> logL, summed over ranks
+        c = fset.forward(pis[2], Ts[2], Es[2])                                # chain-scarce single point
+        d = lonely.forward_batch(pis[:6], Ts[:6], Es[:6])                     # rank 0's shard only
+        m.set_option("comm_enabled", 0)
+        e = fset.forward_batch(pis[:6], Ts[:6], Es[:6])                       # this rank's partial sums
+        m.set_option("comm_enabled", 1)
+        results.append(np.concatenate([a, b, [c], d, e]))
+        m._lib.comm_destroy()
+    assert m._lib.comm_info() == {"nranks": 1, "rank": 0, "fused": False}
+    np.save(os.path.join(tmp, "out%d.npy" % rank), np.stack(results))
+    np.save(os.path.join(tmp, "fused%d.npy" % rank), np.array(fused))
 
 
 def test_native_allreduce_sums_over_two_gpus(tmp_path):
@@ -61,8 +80,20 @@ def test_native_allreduce_sums_over_two_gpus(tmp_path):
     obs = example_symbols().astype(np.int32)
     cuts = np.concatenate([[0], np.cumsum(lengths)])
     want, _ = F.forward_batch([obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths))], pis[:6], Ts[:6], Es[:6])
+    chunks = [obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths))]
+    want0, _ = F.forward_batch(chunks[0::2], pis[:6], Ts[:6], Es[:6])
+    want1, _ = F.forward_batch(chunks[1::2], pis[:6], Ts[:6], Es[:6])
+    outs = [np.load(tmp_path / ("out%d.npy" % r)) for r in range(2)]
+    fused = [np.load(tmp_path / ("fused%d.npy" % r)) for r in range(2)]
+    assert fused[0].tolist() == fused[1].tolist() and not fused[0][1]      # phase 1 is NCCL; phase 0 is fused where IPC works
     for r in range(2):
-        got = np.load(tmp_path / ("out%d.npy" % r))
-        np.testing.assert_allclose(got[:6], want, rtol=1e-11)
-        np.testing.assert_allclose(got[6:12], want, rtol=1e-9)      # GPU-built (pi,T,E) vs reference-built fixture
-        assert got[12] == pytest.approx(want[2], rel=1e-11)
+        for phase in range(2):
+            got = outs[r][phase]
+            np.testing.assert_allclose(got[:6], want, rtol=1e-11)
+            np.testing.assert_allclose(got[6:12], want, rtol=1e-9)      # GPU-built (pi,T,E) vs reference-built fixture
+            assert got[12] == pytest.approx(want[2], rel=1e-11)
+            np.testing.assert_allclose(got[13:19], want0, rtol=1e-11)
+            np.testing.assert_allclose(got[19:25], want1 if r else want0, rtol=1e-11)
+        np.testing.assert_array_equal(outs[r][0], outs[r][1])             # both collectives add the same two numbers
+    np.testing.assert_array_equal(outs[0][:, :19], outs[1][:, :19])       # and every rank holds the same bits
+    print("fused all-reduce used:", bool(fused[0][0]))

@@ -61,6 +61,7 @@ struct Context {
     long long opt_zip_lanes = 0;       // lanes per chain in the zip kernel: 8, 4 or 0 = auto
     long long opt_zip_segment_tokens = 0;  // tokens per segment in segmented mode: 0 = auto, -1 = never, > 0 = forced
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
+    long long opt_zip_pipeline = 0;    // pieces per chunk in pipelined mode: 0 = auto, 1 = off, >= 2 forced
     long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
     long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
 };
@@ -148,7 +149,7 @@ struct imc_seqset {
     std::vector<int> stream_of_chunk;             // chunk index as given to imc_seqset_create -> stream (-1: empty chunk)
     // device side (lazy)
     bool uploaded = false;
-    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext, d_vec;
+    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext, d_vec, d_prog;
     std::vector<ZipDevice*> zip_dev;      // one per dictionary size in use
 };
 
@@ -358,7 +359,7 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
     if (mine) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
         set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release(); set->d_pnext.release();
-        set->d_vec.release();
+        set->d_vec.release(); set->d_prog.release();
     }
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
@@ -601,6 +602,32 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                 else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
             }
         }
+        za.nseg = 1; za.seglen = 0; za.carry = nullptr; za.carry_stride = 0; za.progress = nullptr;
+        if (!split) {
+            // ---- few work units per warp: walk every chunk in pieces that are separate, ordered work units (pipelined
+            // mode of zip_run_unit), so that the end of the launch is not a wait for whole-chunk stragglers.  Config 2 has
+            // 2.7 warp-loads per warp: SMs were idle 9 % of the launch.
+            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+            const int cpw = 32 / plan.lanes, nquads = (ns + cpw - 1) / cpw;
+            const double waves = (double)N * nquads / ((double)sms * plan.ctas_per_sm * (plan.threads / 32));
+            long long nseg = 1;
+            if (g_ctx.opt_zip_pipeline >= 2) nseg = g_ctx.opt_zip_pipeline;
+            else if (g_ctx.opt_zip_pipeline == 0 && waves >= 1.0 && waves < 40.0) nseg = (long long)std::ceil(40.0 / waves);
+            nseg = std::min<long long>({nseg, 32, z->max_ntok / 256});
+            if (nseg >= 2) {
+                const int seglen = (int)(((z->max_ntok + nseg - 1) / nseg + 15) / 16 * 16);
+                nseg = (z->max_ntok + seglen - 1) / seglen;
+                if (nseg >= 2) {
+                    const int cstride = zip_tile(K) + 4;
+                    if ((rc = set->d_vec.reserve(sizeof(double) * (size_t)N * ns * cstride))) return rc;
+                    if ((rc = set->d_prog.reserve(sizeof(int) * (size_t)N * ns))) return rc;
+                    CUDA_TRY(cudaMemsetAsync(set->d_prog.p, 0, sizeof(int) * (size_t)N * ns, st));
+                    za.nseg = (int)nseg; za.seglen = seglen;
+                    za.carry = (double*)set->d_vec.p; za.carry_stride = cstride;
+                    za.progress = (int*)set->d_prog.p;
+                }
+            }
+        }
         if (split) {
             za.chunks = (const ZipChunk*)split->chunks.p;
             za.nchunks = split->nchains;
@@ -734,6 +761,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_segment_tokens")) { if (value < -1) return fail(IMC_ERR_INVALID, "zip_segment_tokens must be >= -1"); g_ctx.opt_zip_segment_tokens = value; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8 && value != 32) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4, 8 or 32"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
+    if (!strcmp(key, "zip_pipeline")) { if (value < 0 || value > 32) return fail(IMC_ERR_INVALID, "zip_pipeline must be in [0, 32]"); g_ctx.opt_zip_pipeline = value; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
@@ -747,6 +775,7 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_segment_tokens")) { *value_out = g_ctx.opt_zip_segment_tokens; return IMC_OK; }
     if (!strcmp(key, "zip_lanes")) { *value_out = g_ctx.opt_zip_lanes; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
+    if (!strcmp(key, "zip_pipeline")) { *value_out = g_ctx.opt_zip_pipeline; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);

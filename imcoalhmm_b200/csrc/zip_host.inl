@@ -249,7 +249,7 @@ static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaSt
 
 static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
     // persistent CTAs: one per resident slot, but never more than there are (point, warp-load of quads) units
-    const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw, nw = p.threads / 32;
+    const int cpw = 32 / p.lanes, nunits = (a.nchunks + cpw - 1) / cpw * (a.nseg > 1 ? a.nseg : 1), nw = p.threads / 32;
     (void)nw;
     const long long units = (long long)a.N * nunits;     // scarce work spreads one warp-load per CTA over the SMs
     const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;

@@ -46,6 +46,13 @@ struct ZipArgs {
     int active_warps;            // warps per CTA that claim work (scarce work is spread over the SMs, one chain group per warp)
     double* vec_out;             // segmented mode: [N][nchunks][vec_stride] final vector (K doubles, unnormalised) + exponent
     int vec_stride;
+    // pipelined mode (nseg > 1): every chunk is walked in nseg pieces of seglen tokens that are separate work units; a
+    // piece starts from the state its predecessor left in `carry` once `progress` says so.  Same arithmetic, same bits,
+    // but work units nseg times smaller, so the SMs run dry together at the end of a launch with few units per warp.
+    int nseg, seglen;
+    double* carry;               // [N][nchunks][carry_stride]: state registers of the chain's lanes, exponent, flags
+    int carry_stride;
+    int* progress;               // [N][nchunks] pieces completed (zeroed before the launch)
 };
 
 // Segmented mode (chain-scarce calls: few chunks x few points).  A long chunk is cut into segments of `seglen` tokens.
@@ -440,25 +447,48 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
                                              const double* spi, const long long* dexp, const typename C::Lane& L) {
     constexpr int KP = C::KP;
     const int K = a.K, S = a.S;
-    const int ci = unit * C::CPW + L.grp;
+    int seg = 0, quad = unit;
+    if (a.nseg > 1) {          // pipelined mode: units are numbered piece-major, so a chunk's pieces are claimed in order
+        const int nquads = (a.nchunks + C::CPW - 1) / C::CPW;
+        seg = unit / nquads;
+        quad = unit - seg * nquads;
+    }
+    const int ci = quad * C::CPW + L.grp;
     const bool have = ci < a.nchunks;
-    const ZipChunk ch = a.chunks[have ? ci : unit * C::CPW];
-    const int nt = have ? ch.ntok : 0;
-    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off);
+    const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
+    const int tok0 = seg * a.seglen;
+    const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
+    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + tok0);
     int maxnt = nt;
 #pragma unroll
     for (int m = 16; m >= C::G; m >>= 1) maxnt = max(maxnt, __shfl_xor_sync(0xffffffffu, maxnt, m));
 
     double al[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int st = C::state_of(L, k);
-        if (ch.first_sym >= 0) al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
-        else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
-    }
     long long scale = 0;       // exponents taken out by zip_rescale (the same in every lane of the chain)
     long long tscale = 0;      // exponents of the dictionary matrices applied (GROUP4: partial sum per lane pair)
     bool dead = false, isnan = false;
+    double* carry = a.carry + ((size_t)n * a.nchunks + (have ? ci : 0)) * a.carry_stride;
+    int* prog = a.progress + (size_t)n * a.nchunks + (have ? ci : 0);
+    if (seg == 0) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int st = C::state_of(L, k);
+            if (ch.first_sym >= 0) al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
+            else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
+        }
+    } else if (have) {         // every lane of the chain waits for the predecessor piece itself, then reads what it left
+        while (*((volatile int*)prog) < seg) __nanosleep(200);
+        __threadfence();
+#pragma unroll
+        for (int k = 0; k < KP; ++k) al[k] = __ldcg(carry + k);
+        scale = (long long)__ldcg(carry + KP);
+        const int fl = (int)__ldcg(carry + KP + 1);
+        dead = fl & 1;
+        isnan = fl & 2;
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) al[k] = 0.0;
+    }
     int buf = 0;
     uint4 cur = make_uint4(0, 0, 0, 0);
     if (nt > 0) cur = tp[0];
@@ -505,6 +535,17 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
         tscale += __shfl_xor_sync(0xffffffffu, tscale, 4);
     }
     scale += tscale;
+    if (a.nseg > 1 && seg < a.nseg - 1) {       // hand the state on to the next piece (the same lane group of some warp)
+        if (have && L.writer()) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) __stcg(carry + k, al[k]);
+            __stcg(carry + KP, (double)scale);
+            __stcg(carry + KP + 1, (double)((dead ? 1 : 0) | (isnan ? 2 : 0)));
+            __threadfence();
+            *((volatile int*)prog) = seg + 1;
+        }
+        return;
+    }
     double sum = 0.0;
 #pragma unroll
     for (int k = 0; k < KP; ++k) sum += al[k];
@@ -546,7 +587,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const typename C::Lane L(lane, warp, sbuf);
     for (int x = tid; x < (THREADS / 32) * C::SBUF_PER_WARP; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
-    const int nunits = (a.nchunks + C::CPW - 1) / C::CPW;
+    const int nunits = (a.nchunks + C::CPW - 1) / C::CPW * (a.nseg > 1 ? a.nseg : 1);
     int primary = blockIdx.x;          // next point of this CTA's own share
     int scan = (int)(((long long)blockIdx.x * 7919) % a.N);   // where the search for points to help starts
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_point + 2);

@@ -177,6 +177,11 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       are cut into segments of this many tokens whose K x K transfer matrices are computed
  *                       column by column in parallel and folded afterwards.  0 = auto, -1 = never, > 0 = forced length.
  * key "zip_max_entries": cap on the dictionary ids used (0 = as many as fit).
+ * key "zip_pipeline":   pipelined mode of the zip kernel for launches with few work units per warp: every chunk is walked
+ *                       in this many pieces that are separate, ordered work units (a piece starts from the state its
+ *                       predecessor left in global memory), so that the SMs finish together; bit-identical results.
+ *                       0 = auto (about 40 units per warp), 1 = off, 2..32 = forced.
+ * key "comm_fused", "comm_enabled": see the multi-GPU section above.
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
  *                       of T where E[:,s0] > 0; 0 (default; measured faster on B200) = always multiply by the emission row. */

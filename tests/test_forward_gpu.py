@@ -25,6 +25,7 @@ def _reset_options():
     m.set_option("zip_max_entries", 0)
     m.set_option("zip_lanes", 0)
     m.set_option("zip_segment_tokens", 0)
+    m.set_option("zip_pipeline", 0)
 
 
 def oracle_batch(chunks, pis, Ts, Es):
@@ -277,6 +278,39 @@ def test_zip_kernel_work_stealing_many_points():
         got = s.forward_batch(*big)
         np.testing.assert_allclose(got, np.tile(want16, reps), rtol=RTOL)
         np.testing.assert_allclose(s.forward_batch(pis[:3], Ts[:3], Es[:3]), want16[:3], rtol=RTOL)
+
+
+@pytest.mark.parametrize("model,lanes", [("isolation_k10", 8), ("im_k10_10", 4), ("im_k10_10", 32), ("isolation_k4", 8)])
+def test_zip_pipelined_pieces_are_bit_identical(model, lanes):
+    """Pipelined mode: a chunk is walked in pieces that are separate, ordered work units handing their state on through
+    global memory.  Same operations in the same order, so the result must not change by a single bit -- ragged chunks,
+    chunks shorter than a piece, a chain that dies half way, more points than CTAs."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(5)
+    _, pis, Ts, Es = golden_model(model)
+    chunks = [rng.choice(3, size=int(n), p=[0.6, 0.3, 0.1]).astype(np.uint8) for n in rng.integers(1, 20000, size=37)]
+    chunks.append(rng.choice(3, size=30000, p=[0.6, 0.3, 0.1]).astype(np.uint8))
+    Es = Es.copy()
+    P, dead = pis.shape[0], pis.shape[0] - 1
+    Es[dead, :, 1] = 0.0                                     # last point: symbol 1 is impossible -> -inf, carried across pieces
+    want = oracle_batch(chunks, pis, Ts, Es)
+    assert np.isfinite(want[:dead]).all()                    # (the oracle's plain recursion gives 0/0 = nan for the dead point)
+    s = make_set(chunks)
+    reps = 320 // P                                          # 320 points > 148 or 296 CTAs
+    big = [np.tile(x, (reps,) + (1,) * (x.ndim - 1)) for x in (pis, Ts, Es)]
+    m.set_option("forward_kernel", 4)                        # (these symbols hardly compress: auto would pick a per-site kernel)
+    m.set_option("zip_lanes", lanes)
+    m.set_option("zip_segment_tokens", -1)
+    m.set_option("zip_pipeline", 1)
+    base = s.forward_batch(*big)
+    assert m.last_forward_kernel() in ("zip", "zip-warp")
+    base2 = base.reshape(reps, P)
+    np.testing.assert_allclose(base2[:, :dead], np.tile(want[:dead], (reps, 1)), rtol=RTOL)
+    assert np.isneginf(base2[:, dead]).all()
+    for pieces in (2, 5, 32, 0):
+        m.set_option("zip_pipeline", pieces)
+        np.testing.assert_array_equal(s.forward_batch(*big), base)
+        np.testing.assert_array_equal(s.forward_batch(pis[:3], Ts[:3], Es[:3]), base[:3])
 
 
 @pytest.mark.parametrize("model", ["isolation_k10", "im_k10_10", "isolation_k4"])

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0)
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes")
+    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces]")
     ap.add_argument("--plain", action="store_true", help="also time the uncompressed kernel")
     ap.add_argument("--check", type=int, default=2, help="chunks to check against the oracle")
     args = ap.parse_args()
@@ -66,7 +66,10 @@ def main():
 
     ref = None
     for spec in args.sweep.split(","):
-        ctas, cap, lanes = map(int, spec.split(":"))
+        f = list(map(int, spec.split(":")))
+        ctas, cap, lanes = f[:3]
+        pipe = f[3] if len(f) > 3 else 0
+        m.set_option("zip_pipeline", pipe)
         m.set_option("forward_kernel", 4)
         m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)
@@ -74,7 +77,7 @@ def main():
         info = fset.zip_info(K)
         m.set_option("zip_ctas_per_sm", ctas)   # zip_info reports the plan in effect
         info = fset.zip_info(K)
-        out = timed("zip lanes=%d ctas=%d cap=%d M=%d tok=%d" % (lanes, ctas, cap, info["ids_used"], info["tokens"]))
+        out = timed("zip lanes=%d ctas=%d cap=%d pipe=%d M=%d tok=%d" % (lanes, ctas, cap, pipe, info["ids_used"], info["tokens"]))
         if ref is None:
             ref = out
         else:

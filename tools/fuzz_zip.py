@@ -37,6 +37,7 @@ for trial in range(trials):
     seg = int(rng.choice([0, 0, -1, 16, 64, 700]))
     cap = int(rng.choice([0, 0, nsym, nsym + 1, 9, 40]))
     cap = cap if cap == 0 or cap >= nsym else nsym
+    pipe = int(rng.choice([0, 0, 1, 2, 3, 7, 32]))           # pipelined pieces (needs >= 256 tokens per piece to engage)
     fk = int(rng.choice([4, 4, 4, 0, 1, 2, 3]))              # mostly the zip kernel; also the automatic choice and the per-site kernels
     if fk in (1, 2, 3) and nsym > 3:
         fk = 4                                               # the packed 2-bit layout of the per-site kernels holds 3 symbols
@@ -44,7 +45,8 @@ for trial in range(trials):
         fk = 1
     if fk == 3 and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
         fk = 1
-    for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap)):
+    for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap),
+                 ("zip_pipeline", pipe)):
         m.set_option(k, v)
     got = fset.forward_batch(pis, Ts, Es)
     # the oracle's plain forward divides by the zero scale of an impossible observation and returns NaN where the
@@ -57,7 +59,7 @@ for trial in range(trials):
     ok = bool(same_inf.all()) and err < 1e-10 and bool((np.isfinite(got) == np.isfinite(want)).all())
     worst = max(worst, err)
     if not ok:
-        print("MISMATCH trial %d: K=%d N=%d C=%d nsym=%d lanes=%d ctas=%d seg=%d cap=%d kernel=%s err=%.3e\n got %s\nwant %s"
-              % (trial, K, N, C, nsym, lanes, ctas, seg, cap, m.last_forward_kernel(), err, got[:4], want[:4]))
+        print("MISMATCH trial %d: K=%d N=%d C=%d nsym=%d lanes=%d ctas=%d seg=%d cap=%d pipe=%d kernel=%s err=%.3e\n got %s\nwant %s"
+              % (trial, K, N, C, nsym, lanes, ctas, seg, cap, pipe, m.last_forward_kernel(), err, got[:4], want[:4]))
         sys.exit(1)
 print("fuzz ok: %d trials, worst relative error %.2e" % (trials, worst))

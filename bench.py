@@ -134,38 +134,69 @@ def make_chunks(wl, pis, Ts, Es, chunk_ids):
 
 # ---------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of GPU `index` sampled from the warm-up steps to the end of the timed region: NVML
+    (what nvidia-smi reads) every ~5 ms in-process, or an `nvidia-smi --query-gpu` call every ~50 ms where pynvml is
+    not usable."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self._stop_evt = index, threading.Event()
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._handle
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if bits & int(bit):
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 7:
+            if f[0].replace(".", "").isdigit():
+                self.sm.append(float(f[0]))
+            if f[1].replace(".", "").isdigit():
+                self.mx.append(float(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._stop_evt.wait(0.05)
+                if self._nvml is not None:
+                    self._nvml, self.source = None, "nvidia-smi"     # fall back for the rest of the run
+            self._stop_evt.wait(0.005 if self._nvml is not None else 0.05)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------- CPU arm

@@ -322,12 +322,8 @@ def main():
     lib_comm = False
     if world > 1 and args.collective != "torch":
         # the library's own communicator: rank 0 draws the id, torch.distributed carries it to the other ranks
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(m._lib.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        m.set_option("comm_fused", 1 if args.collective == "fused" else 0)
-        m._lib.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        from imcoalhmm_b200.sharding import init_library_comm
+        init_library_comm(dev, fused=(args.collective == "fused"))
         lib_comm = True
         config["collective"] = ("all-reduce fused into the chain-reduction kernel (peer-to-peer stores over NVLink)"
                                 if m._lib.comm_info()["fused"] else "ncclAllReduce issued by the library")

@@ -31,20 +31,45 @@ def partition_chunks(lengths, world_size):
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
+def init_library_comm(device, fused=True, process_group=None):
+    """Give the library its own communicator from an initialised torch.distributed group: rank 0 draws the id, a
+    broadcast carries it to the other ranks, every rank calls imc_comm_init.  From then on every forward / likelihood
+    call of this process returns the SUM over ranks -- on one node inside the chain-reduction kernel over peer memory
+    (`comm_info()["fused"]`), else by one ncclAllReduce -- and ShardedLikelihood must not all-reduce again
+    (`summed_by_library=True`).  Call `_lib.comm_destroy()` on all ranks together when done.  Returns comm_info()."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib, set_option
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    if world == 1:
+        return _lib.comm_info()
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(_lib.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0, group=process_group)
+    set_option("comm_fused", 1 if fused else 0)
+    _lib.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    return _lib.comm_info()
+
+
 class ShardedLikelihood(object):
     """Likelihood over chunks sharded across ranks.
 
     local_scorer(thetas) -> tensor float64[N] of this rank's partial log-likelihoods, on the device the process
-    group communicates on (cuda for nccl, cpu for gloo).  `batched` all-reduces it (sum) and returns the tensor.
+    group communicates on (cuda for nccl, cpu for gloo).  `batched` all-reduces it (sum) and returns the tensor --
+    unless the scorer's result is already the sum over ranks (`summed_by_library`: init_library_comm was called).
     """
 
-    def __init__(self, local_scorer, process_group=None):
+    def __init__(self, local_scorer, process_group=None, summed_by_library=False):
         self.local_scorer = local_scorer
         self.process_group = process_group
+        self.summed_by_library = summed_by_library
 
     def batched(self, thetas):
         import torch.distributed as dist
         part = self.local_scorer(thetas)
+        if self.summed_by_library:
+            return part
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.process_group)   # the only collective
         return part

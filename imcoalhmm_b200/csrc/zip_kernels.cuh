@@ -13,7 +13,9 @@
 // of a warp are using.  The new state is exchanged through a small shared-memory buffer (one STS.64 per owned row, K/2
 // broadcast LDS.128 back), after which every lane holds all of alpha again.  The bound is the shared-memory pipe: 8 K^2
 // bytes of matrix per chain-step against 128 B/clk/SM, i.e. at most 1/4 of the FP64 rate -- times the compression ratio
-// (50-150x on the benchmark alignments).  DESIGN.md section 4.1 has the measurements behind every choice made here.
+// (50-150x on the benchmark alignments).  Launches with few work units per warp walk every chunk in ordered pieces that
+// hand their state on through global memory (ZipArgs::nseg, bit-identical), chain-scarce calls use one warp per chain or
+// the segmented (scan) form below.  DESIGN.md section 4.1 has the measurements behind every choice made here.
 #pragma once
 #include "forward_kernels.cuh"
 

@@ -479,6 +479,16 @@ def main():
             roofline["traffic_source"] = "%s, ncu --set full: %s" % (tr["kernel"], tr["source"])
     except (OSError, ValueError):
         pass
+    # the HBM view, for completeness: DRAM bytes of the dominant kernel (ncu) / kernel time against the measured copy bandwidth
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, ValueError, KeyError):
+        hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+    if roofline.get("traffic"):
+        ach = roofline["traffic"] / t_kernel / 1e9
+        roofline["hbm_view"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                "peak_source": hbm_src, "note": "not the bound: the working set lives in shared memory and registers"}
     line = {
         "metric": "forward sites*param-points/sec", "value": value, "unit": "sites*points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,

@@ -332,13 +332,18 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
     int nmax = 4;
     for (int s : m->interval_space) nmax = std::max(nmax, host_space(s).n);
     const size_t smem_expm = sizeof(double) * 3 * (size_t)nmax * nmax;
-    static size_t expm_attr = 0;
-    if (smem_expm > expm_attr) {
-        CUDA_TRY(cudaFuncSetAttribute(model_expm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_expm));
-        expm_attr = smem_expm;
+    if (nmax <= 16) {       // isolation-type models: the lean instantiation (no tensor-path code, 8 CTAs per SM)
+        model_expm_kernel<true><<<dim3(K, N), 256, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
+                                                                    (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
+    } else {
+        static size_t expm_attr = 0;
+        if (smem_expm > expm_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(model_expm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_expm));
+            expm_attr = smem_expm;
+        }
+        model_expm_kernel<false><<<dim3(K, N), 256, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
+                                                                     (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
     }
-    model_expm_kernel<<<dim3(K, N), 256, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
-                                                          (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
     CUDA_TRY(cudaGetLastError());
     const size_t smem_chain = sizeof(double) * (2 * MAX_STATES + (size_t)K * K + 2 * (size_t)K * MAX_L + 128);
     static size_t chain_attr = 0;

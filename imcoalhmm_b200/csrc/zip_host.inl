@@ -19,6 +19,9 @@ static int zip_tile(int K) {
 static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
 
 struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
+#ifndef IMC_ZIP8_THREADS
+#define IMC_ZIP8_THREADS 512     // threads of the single-CTA-per-SM shape with 8 lanes per chain, K <= 24 (experiment builds: 640, 768)
+#endif
 static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM (1 KB per resident CTA is reserved on top)
 
 // Launch shapes (all persistent, see zip_forward_kernel):
@@ -46,7 +49,7 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
         want_ctas = 1;
     } else if (p.lanes == 8) {
         using C = ZipCfg8<K>;
-        t1 = K <= 24 ? 512 : 256;
+        t1 = K <= 24 ? IMC_ZIP8_THREADS : 256;
         m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
         m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
     } else {
@@ -241,7 +244,7 @@ static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaSt
     }
     if constexpr (K <= 24) {
         if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2>(a, p, grid, st);
-        return launch_zip_k<ZipCfg8<K>, 512, 1>(a, p, grid, st);
+        return launch_zip_k<ZipCfg8<K>, IMC_ZIP8_THREADS, 1>(a, p, grid, st);
     } else {
         return launch_zip_k<ZipCfg8<K>, 256, 1>(a, p, grid, st);
     }

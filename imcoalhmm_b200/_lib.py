@@ -37,6 +37,8 @@ _SIGNATURES = {
     "imc_seq_from_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "imc_seq_from_columns": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int64, ctypes.POINTER(c_vp)]),
     "imc_seq_from_fasta_n": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seq_from_alignment": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
+                                              ctypes.POINTER(c_vp)]),
     "imc_seq_save": (ctypes.c_int, [c_vp, ctypes.c_char_p]),
     "imc_seq_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "imc_seq_length": (ctypes.c_int, [c_vp, c_i64p]),

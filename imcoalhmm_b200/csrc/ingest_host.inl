@@ -87,6 +87,141 @@ static int read_fasta(const char* path, std::vector<std::string>& names, std::ve
     return IMC_OK;
 }
 
+// PHYLIP (the other common input of scripts/prepare-alignments.py, whose <input format> argument is handed to BioPython):
+// header "ntaxa nsites", then either interleaved blocks (first block: name + data per taxon; later blocks: data only, same
+// order) or, sequential, each taxon's name followed by all of its data over as many lines as it takes.  Strict names
+// occupy the first 10 columns of the line; relaxed names end at the first blank.  Blanks inside the data are ignored;
+// '.' (match-first-row shorthand) is rejected, as BioPython does.
+static int read_phylip(const char* path, bool sequential, bool relaxed, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
+    std::string text;
+    std::vector<char> buf(1 << 20);
+    size_t got;
+    try {
+        while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) text.append(buf.data(), got);
+    } catch (...) { fclose(f); return fail(IMC_ERR_NOMEM, "out of memory reading '%s'", path); }
+    fclose(f);
+    std::vector<std::pair<size_t, size_t>> lines;      // non-blank lines as (begin, end)
+    for (size_t b = 0; b < text.size();) {
+        size_t e = text.find('\n', b);
+        if (e == std::string::npos) e = text.size();
+        size_t e2 = e;
+        while (e2 > b && (text[e2 - 1] == '\r' || text[e2 - 1] == ' ' || text[e2 - 1] == '\t')) --e2;
+        bool blank = true;
+        for (size_t i = b; i < e2; ++i) if (text[i] != ' ' && text[i] != '\t') { blank = false; break; }
+        if (!blank) lines.emplace_back(b, e2);
+        b = e + 1;
+    }
+    if (lines.empty()) return fail(IMC_ERR_IO, "'%s' is empty", path);
+    long long ntaxa = 0, nsites = 0;
+    {
+        const std::string head = text.substr(lines[0].first, lines[0].second - lines[0].first);
+        char extra;
+        if (sscanf(head.c_str(), " %lld %lld %c", &ntaxa, &nsites, &extra) != 2 || ntaxa < 1 || nsites < 0)
+            return fail(IMC_ERR_IO, "'%s' does not start with a PHYLIP header (taxa, sites)", path);
+    }
+    names.assign((size_t)ntaxa, std::string());
+    seqs.assign((size_t)ntaxa, std::string());
+    auto add_data = [&](std::string& dst, size_t b, size_t e) -> int {
+        for (size_t i = b; i < e; ++i) {
+            const char ch = text[i];
+            if (ch == ' ' || ch == '\t') continue;
+            if (ch == '.') return fail(IMC_ERR_IO, "'%s' uses '.' match characters, which are not supported", path);
+            dst.push_back(ch);
+        }
+        return IMC_OK;
+    };
+    auto split_name = [&](size_t b, size_t e, std::string& name) -> size_t {      // returns where the data starts
+        size_t i = b;
+        if (relaxed) {
+            while (i < e && (text[i] == ' ' || text[i] == '\t')) ++i;
+            const size_t nb = i;
+            while (i < e && text[i] != ' ' && text[i] != '\t') ++i;
+            name = text.substr(nb, i - nb);
+            return i;
+        }
+        const size_t ne = std::min(e, b + 10);
+        name = text.substr(b, ne - b);
+        while (!name.empty() && (name.back() == ' ' || name.back() == '\t')) name.pop_back();
+        size_t lead = 0;
+        while (lead < name.size() && (name[lead] == ' ' || name[lead] == '\t')) ++lead;
+        name.erase(0, lead);
+        return ne;
+    };
+    size_t li = 1;
+    int rc;
+    try {
+        if (sequential) {
+            for (long long t = 0; t < ntaxa; ++t) {
+                if (li >= lines.size()) return fail(IMC_ERR_IO, "'%s' ends before taxon %lld", path, t + 1);
+                size_t ds = split_name(lines[li].first, lines[li].second, names[(size_t)t]);
+                if ((rc = add_data(seqs[(size_t)t], ds, lines[li].second))) return rc;
+                ++li;
+                while ((long long)seqs[(size_t)t].size() < nsites && li < lines.size()) {
+                    if ((rc = add_data(seqs[(size_t)t], lines[li].first, lines[li].second))) return rc;
+                    ++li;
+                }
+            }
+        } else {
+            for (long long t = 0; t < ntaxa; ++t, ++li) {
+                if (li >= lines.size()) return fail(IMC_ERR_IO, "'%s' ends before taxon %lld", path, t + 1);
+                size_t ds = split_name(lines[li].first, lines[li].second, names[(size_t)t]);
+                if ((rc = add_data(seqs[(size_t)t], ds, lines[li].second))) return rc;
+            }
+            while (li < lines.size()) {
+                for (long long t = 0; t < ntaxa; ++t, ++li) {
+                    if (li >= lines.size()) return fail(IMC_ERR_IO, "'%s': the last interleaved block is incomplete", path);
+                    if ((rc = add_data(seqs[(size_t)t], lines[li].first, lines[li].second))) return rc;
+                }
+            }
+        }
+    } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of memory reading '%s'", path); }
+    if (li < lines.size()) return fail(IMC_ERR_IO, "'%s' holds data beyond the %lld x %lld announced in its header", path, ntaxa, nsites);
+    for (long long t = 0; t < ntaxa; ++t)
+        if ((long long)seqs[(size_t)t].size() != nsites)
+            return fail(IMC_ERR_IO, "taxon '%s' of '%s' has %zu sites, the header says %lld", names[(size_t)t].c_str(), path,
+                        seqs[(size_t)t].size(), nsites);
+    return IMC_OK;
+}
+
+// format: "fasta", "phylip" (interleaved, 10-column names), "phylip-relaxed" (interleaved, names end at the first blank),
+// "phylip-sequential" -- BioPython's names for them (prepare-alignments.py:41,66)
+static int read_alignment(const char* path, const char* format, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+    if (!format || !strcmp(format, "fasta")) return read_fasta(path, names, seqs);
+    if (!strcmp(format, "phylip")) return read_phylip(path, false, false, names, seqs);
+    if (!strcmp(format, "phylip-relaxed")) return read_phylip(path, false, true, names, seqs);
+    if (!strcmp(format, "phylip-sequential")) return read_phylip(path, true, false, names, seqs);
+    return fail(IMC_ERR_UNSUPPORTED, "alignment format '%s' is not supported (fasta, phylip, phylip-relaxed, phylip-sequential)", format);
+}
+
+extern "C" int imc_seq_from_alignment(const char* path, const char* format, const char* const* record_names, int n_names, imc_seq** out) {
+    if (!path || !out) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (n_names != 0 && (n_names < 2 || n_names > 4 || !record_names)) return fail(IMC_ERR_INVALID, "0 (the only two records), 2, 3 or 4 record names are needed");
+    std::vector<std::string> names, seqs;
+    int rc = read_alignment(path, format, names, seqs);
+    if (rc) return rc;
+    const char* cols[4];
+    size_t len = 0;
+    if (n_names == 0) {
+        if (names.size() != 2) return fail(IMC_ERR_INVALID, "'%s' holds %zu records; name the ones to compare", path, names.size());
+        cols[0] = seqs[0].data(); cols[1] = seqs[1].data(); len = seqs[0].size(); n_names = 2;
+        if (seqs[1].size() != len) return fail(IMC_ERR_INVALID, "aligned sequences differ in length (%zu vs %zu)", len, seqs[1].size());
+    } else {
+        for (int k = 0; k < n_names; ++k) {
+            int found = -1;
+            for (size_t i = 0; i < names.size(); ++i) if (record_names[k] && names[i] == record_names[k]) found = (int)i;
+            if (found < 0) return fail(IMC_ERR_INVALID, "record '%s' not found in '%s'", record_names[k] ? record_names[k] : "(null)", path);
+            if (k > 0 && seqs[found].size() != len)
+                return fail(IMC_ERR_INVALID, "aligned sequences differ in length (%zu vs %zu)", len, seqs[found].size());
+            len = seqs[found].size();
+            cols[k] = seqs[found].data();
+        }
+    }
+    if (n_names == 2) return imc_seq_from_pair(cols[0], cols[1], (int64_t)len, out);
+    return imc_seq_from_columns(cols, n_names, (int64_t)len, out);
+}
+
 extern "C" int imc_seq_from_fasta(const char* path, const char* name1, const char* name2, imc_seq** out) {
     if (!path || !out) return fail(IMC_ERR_INVALID, "NULL argument");
     std::vector<std::string> names, seqs;

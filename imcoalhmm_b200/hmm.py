@@ -259,6 +259,24 @@ class Forwarder(object):
         self._finish(_Seq(h), 3)
         return self
 
+    @classmethod
+    def from_alignment(cls, path, fmt="fasta", names=None):
+        """The named records (two, three or four; or the only two) of an alignment file in format `fmt`: "fasta",
+        "phylip", "phylip-relaxed" or "phylip-sequential" -- the <input format> argument of scripts/prepare-alignments.py."""
+        self = cls.__new__(cls)
+        h = _lib.c_vp()
+        lib = _lib.load()
+        n = 0 if names is None else len(names)
+        arr = (ctypes.c_char_p * max(n, 1))(*[str(x).encode() for x in (names or [])]) if n else None
+        rc = lib.imc_seq_from_alignment(os.fsencode(path), str(fmt).encode(), arr, n, ctypes.byref(h))
+        if rc == -5 and not os.path.exists(path):
+            raise IOError(lib.imc_last_error().decode())
+        if rc in (-5, -1):
+            raise ValueError(lib.imc_last_error().decode())
+        check(rc)
+        self._finish(_Seq(h), {0: 3, 2: 3, 3: 65, 4: 160}[n])
+        return self
+
     def save(self, path):
         """Binary container (2 bits per symbol for NSYM <= 4); read it back with Forwarder.load."""
         check(_lib.load().imc_seq_save(self._seq.handle, os.fsencode(path)))

@@ -61,6 +61,10 @@ int imc_seq_from_fasta(const char* path, const char* name1, const char* name2, i
  * columns therefore reach 159 and 128 is ambiguous; NSYM = 160). */
 int imc_seq_from_columns(const char* const* seqs, int n_seqs, int64_t L, imc_seq** out);
 int imc_seq_from_fasta_n(const char* path, const char* const* record_names, int n_names, imc_seq** out);
+/* The same for any supported alignment format -- prepare-alignments.py:41,66 hands its <input format> argument to BioPython;
+ * here: "fasta" (or NULL), "phylip" (interleaved, names in the first 10 columns), "phylip-relaxed" (interleaved, names end at
+ * the first blank), "phylip-sequential".  n_names = 0 takes the only two records of the file, else 2, 3 or 4 named ones. */
+int imc_seq_from_alignment(const char* path, const char* format, const char* const* record_names, int n_names, imc_seq** out);
 /* Binary container for a symbol sequence (2 bits per symbol for NSYM <= 4): 16x smaller than the text format. */
 int imc_seq_save(const imc_seq* seq, const char* path);
 int imc_seq_load(const char* path, imc_seq** out);

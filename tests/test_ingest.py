@@ -104,3 +104,66 @@ def test_triplet_and_quartet_columns_bit_exact(tmp_path):
     assert np.array_equal(g3._seq.symbols(), rule([seqs[2], seqs[0], seqs[3]], (1, 4, 16), 64))
     with pytest.raises(ValueError):
         m.Forwarder.from_sequences("ACGT", "ACG", "ACGT")
+
+
+def _write_phylip(path, seqs, layout, width=50):
+    names = list(seqs)
+    L = len(seqs[names[0]])
+    with open(path, "w") as f:
+        f.write(" %d %d\n" % (len(names), L))
+        if layout == "sequential":                        # strict 10-column names, data over several lines per taxon
+            for n in names:
+                s = seqs[n]
+                f.write(n.ljust(10) + s[:width] + "\n")
+                for i in range(width, L, width):
+                    f.write(" ".join(s[j:j + 10] for j in range(i, min(i + width, L), 10)) + "\n")
+        else:
+            for b, i in enumerate(range(0, L, width)):
+                for n in names:
+                    chunk = " ".join(seqs[n][j:j + 10] for j in range(i, min(i + width, L), 10))
+                    if b == 0:
+                        f.write((n.ljust(10) if layout == "strict" else n + "  ") + chunk + "\r\n")
+                    else:
+                        f.write((" " * 10 if layout == "strict" else "") + chunk + "\n")
+                f.write("\n")
+
+
+def test_phylip_readers_match_fasta(tmp_path):
+    """prepare-alignments.py takes any BioPython format; the PHYLIP flavours give the same symbols as the FASTA reader."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(1)
+    seqs = {name: "".join(rng.choice(list("ACGTacgtN-"), size=1237, p=[.2, .2, .2, .2, .04, .04, .04, .04, .02, .02]))
+            for name in ("hg18", "pantro2", "gorilla", "orang")}
+    want2 = python_rule(seqs["hg18"], seqs["gorilla"])
+    for layout, fmt in (("strict", "phylip"), ("relaxed", "phylip-relaxed"), ("sequential", "phylip-sequential")):
+        p = tmp_path / (layout + ".phy")
+        _write_phylip(p, seqs, layout)
+        f = m.Forwarder.from_alignment(str(p), fmt, names=("hg18", "gorilla"))
+        assert f.NSYM == 3 and np.array_equal(f._seq.symbols(), want2), layout
+        q = m.Forwarder.from_alignment(str(p), fmt, names=("hg18", "pantro2", "gorilla", "orang"))
+        assert q.NSYM == 160 and len(q) == 1237
+        with pytest.raises(ValueError):
+            m.Forwarder.from_alignment(str(p), fmt)                     # four records: names are required
+        with pytest.raises(ValueError):
+            m.Forwarder.from_alignment(str(p), fmt, names=("hg18", "bonobo"))
+    fa = tmp_path / "four.fa"
+    with open(fa, "w") as f:
+        for n, s in seqs.items():
+            f.write(">%s\n%s\n" % (n, s))
+    q_fa = m.Forwarder.from_alignment(str(fa), "fasta", names=("hg18", "pantro2", "gorilla", "orang"))
+    assert np.array_equal(q_fa._seq.symbols(), q._seq.symbols())
+    assert np.array_equal(m.Forwarder.from_alignment(str(fa), names=("hg18", "gorilla"))._seq.symbols(), want2)
+    two = tmp_path / "two.phy"
+    two.write_text("2 5\nalpha     ACGTN\nbeta      ACCTA\n")
+    assert m.Forwarder.from_alignment(str(two), "phylip")._seq.symbols().tolist() == [0, 0, 1, 0, 2]
+    for bad in ("2 5\nalpha     ACGT\nbeta      ACCTA\n",           # a taxon shorter than the header says
+                "2 5\nalpha     ACGTN\n",                           # a taxon missing
+                "x y\nalpha     ACGTN\nbeta      ACCTA\n",          # no header
+                "2 5\nalpha     AC.TN\nbeta      ACCTA\n"):         # match characters
+        two.write_text(bad)
+        with pytest.raises(ValueError):
+            m.Forwarder.from_alignment(str(two), "phylip")
+    with pytest.raises(IOError):
+        m.Forwarder.from_alignment(str(tmp_path / "missing.phy"), "phylip")
+    with pytest.raises(m.IMCError):
+        m.Forwarder.from_alignment(str(fa), "nexus")

@@ -41,6 +41,8 @@ class Likelihood(object):
         """float64[N] of log-likelihoods for thetas[N, P]; invalid rows give -inf."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
         out = np.full(thetas.shape[0], -np.inf)
+        if self.forwarder_set is None:            # foreign forwarder objects: one reference-style call per point
+            return np.array([self(th) for th in thetas], dtype=np.float64)
         if hasattr(self.model, "batched_log_likelihood"):
             return self.model.batched_log_likelihood(thetas, self.forwarder_set)
         ok = np.array([bool(self.model.valid_parameters(th)) for th in thetas])

@@ -78,3 +78,23 @@ def test_sharded_sum_matches_single_process_gloo_world2():
     cuts = np.concatenate([[0], np.cumsum(lengths)])
     want, _ = F.forward_batch([obs[cuts[c]:cuts[c + 1]] for c in range(len(lengths))], pis[:6], Ts[:6], Es[:6])
     np.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+def test_library_comm_single_rank_is_a_no_op():
+    """init_library_comm with a world of one never touches NCCL or the GPU: comm_info reports one rank, nothing fused."""
+    import torch.distributed as dist
+    from imcoalhmm_b200 import _lib
+    from imcoalhmm_b200.sharding import init_library_comm, ShardedLikelihood
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        assert init_library_comm("cpu") == {"nranks": 1, "rank": 0, "fused": False}
+        import torch
+        part = torch.arange(4, dtype=torch.float64)
+        assert ShardedLikelihood(lambda th: part.clone()).batched(None).tolist() == part.tolist()
+        assert ShardedLikelihood(lambda th: part.clone(), summed_by_library=True).batched(None).tolist() == part.tolist()
+    finally:
+        dist.destroy_process_group()
+    _lib.comm_destroy()                      # harmless without a communicator
+    assert _lib.comm_info()["nranks"] == 1

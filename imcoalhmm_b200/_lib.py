@@ -53,6 +53,12 @@ _SIGNATURES = {
                                            c_i64p, ctypes.POINTER(ctypes.c_int)]),
     "imc_seqset_zip_pairs": (ctypes.c_int, [c_vp, c_u8p, ctypes.c_int]),
     "imc_seqset_zip_tokens": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_u8p, ctypes.c_int64, c_i64p]),
+    "imc_seqset_run_info": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_int), c_i64p, ctypes.POINTER(ctypes.c_int)]),
+    "imc_seqset_run_pairs": (ctypes.c_int, [c_vp, c_u8p, ctypes.c_int]),
+    "imc_seqset_run_tokens": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int64,
+                                             c_i64p, ctypes.POINTER(ctypes.c_int)]),
+    "imc_seqset_spectral_counts": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "imc_forward": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
     "imc_forward_batch": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f64p, c_f64p, c_f64p,
                                          c_f64p]),

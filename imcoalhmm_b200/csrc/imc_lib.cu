@@ -62,6 +62,8 @@ struct Context {
     long long opt_zip_segment_tokens = 0;  // tokens per segment in segmented mode: 0 = auto, -1 = never, > 0 = forced
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
     long long opt_zip_pipeline = 0;    // pieces per chunk in pipelined mode: 0 = auto, 1 = off, >= 2 forced
+    long long opt_zip_spectral = 0;    // spectral form of the zip kernel (run tokens): 0 = auto, 1 = always, 2 = never
+    long long opt_zip_spectral_force_bad = 0;   // test switch: zip_spectral_kernel declares every point unfit (plain-form pass serves them)
     long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
     long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
 };
@@ -125,6 +127,7 @@ struct ZipSplit {                 // segmented variant of a ZipDevice's chunk li
 
 struct ZipDevice {
     int M = 0, nlevels = 0;
+    bool spec = false;                        // run tokens (32-bit words) for the spectral form of the kernel
     long long total_tokens = 0;
     int max_ntok = 0;
     std::vector<ZipChunk> host_chunks;        // sorted by ntok, descending
@@ -147,9 +150,16 @@ struct imc_seqset {
     std::vector<std::vector<uint8_t>> tok_full;   // per stream, over all merges.size() ids, symbols 1..L-1
     std::vector<uint8_t> first_sym;               // per stream
     std::vector<int> stream_of_chunk;             // chunk index as given to imc_seqset_create -> stream (-1: empty chunk)
+    // run tokens for the spectral form (tokenizer.inl): the run symbol is fold_sym; own pair dictionary over the entries
+    ZipMerges run_merges;
+    std::vector<std::vector<uint32_t>> run_tok_full;   // per stream, over all run_merges.size() ids
+    std::vector<int> first_run;                        // per stream
+    long long zip_tokens_full = 0, run_tokens_full = 0;   // stream lengths over the full dictionaries (which form compresses better)
     // device side (lazy)
     bool uploaded = false;
-    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out, d_pnext, d_vec, d_prog;
+    DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out;
+    DeviceBuf d_pnext[2], d_vec[2], d_prog[2];    // scratch of the two passes of a forward call (spectral, plain)
+    DeviceBuf d_spec, d_lists;                    // per-point spectral data; ok / bad point lists + their counts
     std::vector<ZipDevice*> zip_dev;      // one per dictionary size in use
 };
 
@@ -323,9 +333,17 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
                     sample.emplace_back(sy.begin() + 1, sy.begin() + 1 + take);
                     budget -= (long long)take;
                 }
+            std::vector<std::vector<uint32_t>> rsample(sample.size());
+            for (size_t i = 0; i < sample.size(); ++i) {
+                int fr;
+                run_tokenize(sample[i].data(), sample[i].size(), set->fold_sym, &fr, rsample[i]);
+            }
             set->merges = zip_learn(sample, set->nsym, 256, 16);
+            set->run_merges = run_learn(rsample, set->nsym, 256, 16);
         }
         set->tok_full.resize(ns);
+        set->run_tok_full.resize(ns);
+        set->first_run.assign(ns, 0);
         set->first_sym.resize(ns);
         set->stream_of_chunk.assign(C, -1);
         for (int k = 0; k < ns; ++k) set->stream_of_chunk[order[k]] = k;
@@ -333,7 +351,12 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
                 const auto& sy = seqs[order[k]]->sym;
                 set->first_sym[k] = sy[0];
                 zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
+                run_encode(set->run_merges, sy.data() + 1, sy.size() - 1, set->fold_sym, &set->first_run[k], set->run_tok_full[k]);
             })) throw std::bad_alloc();
+        for (int k = 0; k < ns; ++k) {
+            set->zip_tokens_full += (long long)set->tok_full[k].size();
+            set->run_tokens_full += (long long)set->run_tok_full[k].size();
+        }
         // stream geometry of the packed 2-bit layout; the words themselves are built on first use (seqset_pack)
         for (int b0 = 0; set->packable && b0 < ns; b0 += 32) {
             const int nb = std::min(32, ns - b0);
@@ -358,8 +381,9 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
     const bool mine = g_ctx.pid == getpid();
     if (mine) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
-        set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release(); set->d_pnext.release();
-        set->d_vec.release(); set->d_prog.release();
+        set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
+        for (int i = 0; i < 2; ++i) { set->d_pnext[i].release(); set->d_vec[i].release(); set->d_prog[i].release(); }
+        set->d_spec.release(); set->d_lists.release();
     }
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
@@ -492,6 +516,160 @@ static int launch_generic(const FwdArgs& a, cudaStream_t st) {
 
 static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out, cudaStream_t st);   // comm_host.inl
 
+// One pass of the compressed forward over the points of a list (plist == NULL: all N points): plan, token streams, the
+// choice among whole chunks / pipelined pieces / one warp per chain / segments, the launch and (segmented) the folds.
+// spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
+// set->d_chain[n][chunk] for the points served.
+static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E, bool spec,
+                    const int* plist, const int* pcount, const double* d_spec, int spec_stride, cudaStream_t st) {
+    int rc;
+    const int ns = (int)set->streams.size(), pass = spec ? 0 : 1;
+    const int avail = spec ? set->run_merges.size() : set->merges.size();
+    ZipPlan plan;
+    if ((rc = zip_plan(K, S, avail, &plan, 0, spec))) return rc;
+    ZipDevice* z = nullptr;
+    if ((rc = zip_device(set, plan.M, &z, spec))) return rc;
+    // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
+    // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
+    //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
+    //       (8 lanes: 36 K, 4 lanes: 49 K: one warp issuing K*K/lanes DFMA and half as many LDS.128 per step);
+    //   (b) one warp per chain (32 lanes): the shortest possible step, ~80 + 14.5 K clocks;
+    //   (c) segments of s tokens: K times the arithmetic on the segments after the first, but K * #segments times
+    //       the chains; throughput cost c clocks of shared-memory pipe per chain-step and SM (K=10: 14, K=20: 35).
+    ZipSplit* split = nullptr;
+    long long seglen = g_ctx.opt_zip_segment_tokens;
+    {
+        const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+        const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
+        const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64;
+        if (scarce && (seglen == 0 || g_ctx.opt_zip_lanes == 0)) {
+            const double c = 1.4 * K * K / 16.0 + 5.0;
+            const double lat = (plan.lanes == 4 ? 49.0 : 36.0) * K, lat32 = 80.0 + 14.5 * K;
+            auto cost_seg = [&](long long sl) {
+                double steps = 0.0, longest = 0.0, nseg_max = 1.0;
+                for (const ZipChunk& ch : z->host_chunks) {
+                    const double first = (double)std::min<long long>(sl, ch.ntok);
+                    steps += first + ((double)ch.ntok - first) * K;
+                    longest = std::max(longest, first);
+                    nseg_max = std::max(nseg_max, std::ceil((double)ch.ntok / (double)sl));
+                }
+                const double fold = nseg_max > 1.0 ? 20000.0 + 1500.0 * 2.0 * std::sqrt(nseg_max) : 0.0;
+                return std::max(longest * lat, 1.3 * steps * N * c / sms) + fold;      // 1.3: tails and imbalance
+            };
+            double best = cost_seg(z->max_ntok);          // (a)
+            long long best_seg = -1;
+            int best_lanes = plan.lanes;
+            if (seglen == 0) {
+                for (long long sl = 256; sl < z->max_ntok; sl *= 2) {        // (c)
+                    const double t = cost_seg(sl);
+                    if (t < 0.8 * best) { best = t; best_seg = sl; }
+                }
+            }
+            if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0) {   // (b)
+                const long long warps = (long long)sms * (zip_tile(K) <= 24 ? 16 : 8);
+                const double rounds = std::ceil((double)((long long)N * ns) / (double)warps);
+                const double t = rounds * z->max_ntok * lat32;
+                if (t < best) { best = t; best_seg = -1; best_lanes = 32; }
+            }
+            if (seglen == 0) seglen = best_seg;
+            if (best_lanes != plan.lanes) {
+                if ((rc = zip_plan(K, S, avail, &plan, best_lanes, spec))) return rc;
+                if ((rc = zip_device(set, plan.M, &z, spec))) return rc;
+            }
+        }
+    }
+    ZipArgs za;
+    za.tokens = (const uint8_t*)z->tokens.p;
+    za.chunks = (const ZipChunk*)z->chunks.p;
+    za.nchunks = ns;
+    if ((rc = set->d_pnext[pass].reserve(sizeof(int) * (size_t)N))) return rc;
+    CUDA_TRY(cudaMemsetAsync(set->d_pnext[pass].p, 0, sizeof(int) * (size_t)N, st));
+    za.point_next = (int*)set->d_pnext[pass].p;
+    za.pairs = (const uint8_t*)z->pairs.p;
+    za.level_start = (const int*)z->levels.p;
+    za.nlevels = z->nlevels;
+    za.M = plan.M;
+    za.N = N; za.K = K; za.S = S;
+    za.pi = d_pi; za.T = d_T; za.E = d_E;
+    za.chain_out = (double*)set->d_chain.p;
+    za.out_stride = ns;
+    za.vec_out = nullptr;
+    za.vec_stride = 0;
+    za.plist = plist; za.pcount = pcount;
+    za.spec = d_spec; za.spec_stride = spec_stride;
+    DeviceBuf& d_vec = set->d_vec[pass];
+    DeviceBuf& d_prog = set->d_prog[pass];
+    if (seglen > 0 && K <= 64) {
+        seglen = (seglen + 15) / 16 * 16;
+        if (seglen < z->max_ntok) {
+            if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
+            const size_t vec_bytes = sizeof(double) * (size_t)N * ((size_t)split->nchains + split->nvec2) * (K + 1);
+            if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
+            else if ((rc = d_vec.reserve(vec_bytes))) return rc;
+        }
+    }
+    za.nseg = 1; za.seglen = 0; za.carry = nullptr; za.carry_stride = 0; za.progress = nullptr;
+    if (!split) {
+        // ---- few work units per warp: walk every chunk in pieces that are separate, ordered work units (pipelined
+        // mode of zip_run_unit), so that the end of the launch is not a wait for whole-chunk stragglers.  Config 2 has
+        // 2.7 warp-loads per warp: SMs were idle 9 % of the launch.
+        const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+        const int cpw = 32 / plan.lanes, nquads = (ns + cpw - 1) / cpw;
+        const double waves = (double)N * nquads / ((double)sms * plan.ctas_per_sm * (plan.threads / 32));
+        long long nseg = 1;
+        if (g_ctx.opt_zip_pipeline >= 2) nseg = g_ctx.opt_zip_pipeline;
+        else if (g_ctx.opt_zip_pipeline == 0 && waves >= 1.0 && waves < 40.0) nseg = (long long)std::ceil(40.0 / waves);
+        nseg = std::min<long long>({nseg, 32, z->max_ntok / 256});
+        if (nseg >= 2) {
+            const int plen = (int)(((z->max_ntok + nseg - 1) / nseg + 15) / 16 * 16);
+            nseg = (z->max_ntok + plen - 1) / plen;
+            if (nseg >= 2) {
+                const int cstride = zip_tile(K) + 4;
+                if ((rc = d_vec.reserve(sizeof(double) * (size_t)N * ns * cstride))) return rc;
+                if ((rc = d_prog.reserve(sizeof(int) * (size_t)N * ns))) return rc;
+                CUDA_TRY(cudaMemsetAsync(d_prog.p, 0, sizeof(int) * (size_t)N * ns, st));
+                za.nseg = (int)nseg; za.seglen = plen;
+                za.carry = (double*)d_vec.p; za.carry_stride = cstride;
+                za.progress = (int*)d_prog.p;
+            }
+        }
+    }
+    if (split) {
+        za.chunks = (const ZipChunk*)split->chunks.p;
+        za.nchunks = split->nchains;
+        za.vec_out = (double*)d_vec.p;
+        za.vec_stride = K + 1;
+    }
+    if (spec || !plist) {
+        g_last_kernel = spec ? (split ? "zip-spectral-segmented" : (plan.lanes == 32 ? "zip-spectral-warp" : "zip-spectral"))
+                             : (split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip"));
+    }
+    if ((rc = launch_zip(za, plan, st))) return rc;
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    if (split) {
+        double* vec2 = za.vec_out + (size_t)N * split->nchains * za.vec_stride;
+        for (int n0 = 0; n0 < N; n0 += 65535) {      // gridDim.y <= 65535
+            const int nn = std::min(N - n0, 65535);
+            // without a list blockIdx.y is the point itself: shift the per-point bases instead
+            const size_t voff = plist ? 0 : (size_t)n0;
+            if (split->n_level1 > 0) {
+                zip_fold_kernel<<<dim3(split->n_level1, nn), 64, 0, st>>>(za.vec_out + voff * split->nchains * za.vec_stride, split->nchains,
+                    vec2 + voff * split->nvec2 * za.vec_stride, split->nvec2, za.vec_stride, (const ZipFoldItem*)split->items1.p, K,
+                    za.chain_out + voff * za.out_stride, za.out_stride, d_spec ? d_spec + voff * spec_stride : nullptr, spec_stride, plist, pcount, n0);
+                CUDA_TRY(cudaGetLastError());
+                g_launches += 1;
+            }
+            zip_fold_kernel<<<dim3(split->n_final, nn), 64, 0, st>>>(za.vec_out + voff * split->nchains * za.vec_stride, split->nchains,
+                vec2 + voff * split->nvec2 * za.vec_stride, split->nvec2, za.vec_stride, (const ZipFoldItem*)split->items2.p, K,
+                za.chain_out + voff * za.out_stride, za.out_stride, d_spec ? d_spec + voff * spec_stride : nullptr, spec_stride, plist, pcount, n0);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 1;
+        }
+    }
+    return IMC_OK;
+}
+
 static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
                              double* d_out, cudaStream_t st) {
     if (!set) return fail(IMC_ERR_INVALID, "NULL set");
@@ -523,135 +701,52 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         }
     }
     if (which == KERNEL_ZIP) {
-        ZipPlan plan;
-        if ((rc = zip_plan(K, S, set->merges.size(), &plan))) return rc;
-        ZipDevice* z = nullptr;
-        if ((rc = zip_device(set, plan.M, &z))) return rc;
-        // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
-        // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
-        //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
-        //       (8 lanes: 36 K, 4 lanes: 49 K: one warp issuing K*K/lanes DFMA and half as many LDS.128 per step);
-        //   (b) one warp per chain (32 lanes): the shortest possible step, ~80 + 14.5 K clocks;
-        //   (c) segments of s tokens: K times the arithmetic on the segments after the first, but K * #segments times
-        //       the chains; throughput cost c clocks of shared-memory pipe per chain-step and SM (K=10: 14, K=20: 35).
-        ZipSplit* split = nullptr;
-        long long seglen = g_ctx.opt_zip_segment_tokens;
+        // Spectral form where the run symbol's runs carry most of the compression: zip_spectral_kernel diagonalises C_r of
+        // every point and sorts the points into those it could serve (ok list) and the others (plain form, bad list).
+        bool use_spec = g_ctx.opt_zip_spectral == 1;
+        if (g_ctx.opt_zip_spectral == 0) use_spec = set->run_tokens_full * 115 < set->zip_tokens_full * 100;
+        if (use_spec && (set->nsym < 2 || K > 64)) use_spec = false;
+        ZipPlan probe;
+        if (use_spec && zip_plan(K, S, set->run_merges.size(), &probe, 0, true) != IMC_OK) use_spec = false;
+        if (!use_spec) {
+            g_last_kernel = "zip";
+            if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, false, nullptr, nullptr, nullptr, 0, st))) return rc;
+            return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
+        }
+        const int sstride = 2 * K + S * K + S * K * K;
+        if ((rc = set->d_spec.reserve(sizeof(double) * (size_t)N * sstride))) return rc;
+        if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)2 * N + 2)))) return rc;
+        int* lists = (int*)set->d_lists.p;
+        CUDA_TRY(cudaMemsetAsync(lists, 0, sizeof(int) * 2, st));
+        ZipSpecArgs sa;
+        sa.N = N; sa.K = K; sa.S = S; sa.run_sym = set->fold_sym;
+        sa.pi = d_pi; sa.T = d_T; sa.E = d_E;
+        sa.spec = (double*)set->d_spec.p; sa.spec_stride = sstride;
+        sa.counts = lists; sa.ok_list = lists + 2; sa.bad_list = lists + 2 + N;
+        sa.force_bad = g_ctx.opt_zip_spectral_force_bad ? 1 : 0;
+        sa.point_base = 0;
         {
-            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
-            const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
-            const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64;
-            if (scarce && (seglen == 0 || g_ctx.opt_zip_lanes == 0)) {
-                const double c = 1.4 * K * K / 16.0 + 5.0;
-                const double lat = (plan.lanes == 4 ? 49.0 : 36.0) * K, lat32 = 80.0 + 14.5 * K;
-                auto cost_seg = [&](long long sl) {
-                    double steps = 0.0, longest = 0.0, nseg_max = 1.0;
-                    for (const ZipChunk& ch : z->host_chunks) {
-                        const double first = (double)std::min<long long>(sl, ch.ntok);
-                        steps += first + ((double)ch.ntok - first) * K;
-                        longest = std::max(longest, first);
-                        nseg_max = std::max(nseg_max, std::ceil((double)ch.ntok / (double)sl));
-                    }
-                    const double fold = nseg_max > 1.0 ? 20000.0 + 1500.0 * 2.0 * std::sqrt(nseg_max) : 0.0;
-                    return std::max(longest * lat, 1.3 * steps * N * c / sms) + fold;      // 1.3: tails and imbalance
-                };
-                double best = cost_seg(z->max_ntok);          // (a)
-                long long best_seg = -1;
-                int best_lanes = plan.lanes;
-                if (seglen == 0) {
-                    for (long long sl = 256; sl < z->max_ntok; sl *= 2) {        // (c)
-                        const double t = cost_seg(sl);
-                        if (t < 0.8 * best) { best = t; best_seg = sl; }
-                    }
-                }
-                if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0) {   // (b)
-                    const long long warps = (long long)sms * (zip_tile(K) <= 24 ? 16 : 8);
-                    const double rounds = std::ceil((double)((long long)N * ns) / (double)warps);
-                    const double t = rounds * z->max_ntok * lat32;
-                    if (t < best) { best = t; best_seg = -1; best_lanes = 32; }
-                }
-                if (seglen == 0) seglen = best_seg;
-                if (best_lanes != plan.lanes) {
-                    if ((rc = zip_plan(K, S, set->merges.size(), &plan, best_lanes))) return rc;
-                    if ((rc = zip_device(set, plan.M, &z))) return rc;
-                }
+            static size_t attr_max = 0;
+            const size_t sm = zip_spec_smem(K);
+            if (sm > 48 * 1024 && sm > attr_max) {
+                CUDA_TRY(cudaFuncSetAttribute(zip_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                attr_max = sm;
             }
-        }
-        ZipArgs za;
-        za.tokens = (const uint8_t*)z->tokens.p;
-        za.chunks = (const ZipChunk*)z->chunks.p;
-        za.nchunks = ns;
-        if ((rc = set->d_pnext.reserve(sizeof(int) * (size_t)N))) return rc;
-        CUDA_TRY(cudaMemsetAsync(set->d_pnext.p, 0, sizeof(int) * (size_t)N, st));
-        za.point_next = (int*)set->d_pnext.p;
-        za.pairs = (const uint8_t*)z->pairs.p;
-        za.level_start = (const int*)z->levels.p;
-        za.nlevels = z->nlevels;
-        za.M = plan.M;
-        za.N = N; za.K = K; za.S = S;
-        za.pi = d_pi; za.T = d_T; za.E = d_E;
-        za.chain_out = (double*)set->d_chain.p;
-        za.out_stride = ns;
-        za.vec_out = nullptr;
-        za.vec_stride = 0;
-        if (seglen > 0 && K <= 64) {
-            seglen = (seglen + 15) / 16 * 16;
-            if (seglen < z->max_ntok) {
-                if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
-                const size_t vec_bytes = sizeof(double) * (size_t)N * ((size_t)split->nchains + split->nvec2) * (K + 1);
-                if (vec_bytes > (size_t)1 << 30) split = nullptr;      // not worth a gigabyte of scratch
-                else if ((rc = set->d_vec.reserve(vec_bytes))) return rc;
-            }
-        }
-        za.nseg = 1; za.seglen = 0; za.carry = nullptr; za.carry_stride = 0; za.progress = nullptr;
-        if (!split) {
-            // ---- few work units per warp: walk every chunk in pieces that are separate, ordered work units (pipelined
-            // mode of zip_run_unit), so that the end of the launch is not a wait for whole-chunk stragglers.  Config 2 has
-            // 2.7 warp-loads per warp: SMs were idle 9 % of the launch.
-            const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
-            const int cpw = 32 / plan.lanes, nquads = (ns + cpw - 1) / cpw;
-            const double waves = (double)N * nquads / ((double)sms * plan.ctas_per_sm * (plan.threads / 32));
-            long long nseg = 1;
-            if (g_ctx.opt_zip_pipeline >= 2) nseg = g_ctx.opt_zip_pipeline;
-            else if (g_ctx.opt_zip_pipeline == 0 && waves >= 1.0 && waves < 40.0) nseg = (long long)std::ceil(40.0 / waves);
-            nseg = std::min<long long>({nseg, 32, z->max_ntok / 256});
-            if (nseg >= 2) {
-                const int seglen = (int)(((z->max_ntok + nseg - 1) / nseg + 15) / 16 * 16);
-                nseg = (z->max_ntok + seglen - 1) / seglen;
-                if (nseg >= 2) {
-                    const int cstride = zip_tile(K) + 4;
-                    if ((rc = set->d_vec.reserve(sizeof(double) * (size_t)N * ns * cstride))) return rc;
-                    if ((rc = set->d_prog.reserve(sizeof(int) * (size_t)N * ns))) return rc;
-                    CUDA_TRY(cudaMemsetAsync(set->d_prog.p, 0, sizeof(int) * (size_t)N * ns, st));
-                    za.nseg = (int)nseg; za.seglen = seglen;
-                    za.carry = (double*)set->d_vec.p; za.carry_stride = cstride;
-                    za.progress = (int*)set->d_prog.p;
-                }
-            }
-        }
-        if (split) {
-            za.chunks = (const ZipChunk*)split->chunks.p;
-            za.nchunks = split->nchains;
-            za.vec_out = (double*)set->d_vec.p;
-            za.vec_stride = K + 1;
-        }
-        g_last_kernel = split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip");
-        if ((rc = launch_zip(za, plan, st))) return rc;
-        CUDA_TRY(cudaGetLastError());
-        if (split) {
-            double* vec2 = za.vec_out + (size_t)N * split->nchains * za.vec_stride;
-            if (split->n_level1 > 0) {
-                zip_fold_kernel<<<dim3(split->n_level1, N), 64, 0, st>>>(za.vec_out, split->nchains, vec2, split->nvec2, za.vec_stride,
-                                                                        (const ZipFoldItem*)split->items1.p, K, za.chain_out, za.out_stride);
+            for (int n0 = 0; n0 < N; n0 += 65535) {       // gridDim.x is not limited, but keep launches bounded
+                ZipSpecArgs sb = sa;
+                sb.N = std::min(N - n0, 65535);
+                sb.pi += (size_t)n0 * K; sb.T += (size_t)n0 * K * K; sb.E += (size_t)n0 * K * S;
+                sb.spec += (size_t)n0 * sstride;
+                sb.point_base = n0;
+                zip_spectral_kernel<<<sb.N, SPEC_THREADS, sm, st>>>(sb);
                 CUDA_TRY(cudaGetLastError());
                 g_launches += 1;
             }
-            zip_fold_kernel<<<dim3(split->n_final, N), 64, 0, st>>>(za.vec_out, split->nchains, vec2, split->nvec2, za.vec_stride,
-                                                                   (const ZipFoldItem*)split->items2.p, K, za.chain_out, za.out_stride);
-            CUDA_TRY(cudaGetLastError());
-            g_launches += 1;
         }
-        g_launches += 1;
-        return launch_chain_reduce(za.chain_out, ns, N, d_out, st);
+        g_last_kernel = "zip-spectral";
+        if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, true, sa.ok_list, sa.counts, sa.spec, sstride, st))) return rc;
+        if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, false, sa.bad_list, sa.counts + 1, nullptr, 0, st))) return rc;
+        return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
     }
     if (!set->packable)
         return fail(IMC_ERR_UNSUPPORTED, "alphabets larger than 3 symbols run on the zip kernel only (nsym = %d, K = %d)", set->nsym, K);
@@ -762,6 +857,8 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_lanes")) { if (value != 0 && value != 4 && value != 8 && value != 32) return fail(IMC_ERR_INVALID, "zip_lanes must be 0, 4, 8 or 32"); g_ctx.opt_zip_lanes = value; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { if (value < 0 || value > 256) return fail(IMC_ERR_INVALID, "zip_max_entries must be in [0, 256]"); g_ctx.opt_zip_max_entries = value; return IMC_OK; }
     if (!strcmp(key, "zip_pipeline")) { if (value < 0 || value > 32) return fail(IMC_ERR_INVALID, "zip_pipeline must be in [0, 32]"); g_ctx.opt_zip_pipeline = value; return IMC_OK; }
+    if (!strcmp(key, "zip_spectral")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_spectral must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_spectral = value; return IMC_OK; }
+    if (!strcmp(key, "zip_spectral_force_bad")) { g_ctx.opt_zip_spectral_force_bad = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
@@ -776,6 +873,8 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_lanes")) { *value_out = g_ctx.opt_zip_lanes; return IMC_OK; }
     if (!strcmp(key, "zip_max_entries")) { *value_out = g_ctx.opt_zip_max_entries; return IMC_OK; }
     if (!strcmp(key, "zip_pipeline")) { *value_out = g_ctx.opt_zip_pipeline; return IMC_OK; }
+    if (!strcmp(key, "zip_spectral")) { *value_out = g_ctx.opt_zip_spectral; return IMC_OK; }
+    if (!strcmp(key, "zip_spectral_force_bad")) { *value_out = g_ctx.opt_zip_spectral_force_bad; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);

@@ -124,6 +124,97 @@ static ZipLevels zip_levels(const ZipMerges& mg, int M) {
     return zl;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Run tokens for the spectral form of the kernel (zip_kernels.cuh, ZipArgs::spec).  The most frequent symbol r of a
+// set (the "run symbol": matching sites in a pairwise alignment) is taken out of the dictionary altogether: in the
+// eigenbasis of C_r a run of n such sites is the diagonal matrix Lambda^n, whatever n is.  A chunk (symbols 1..L-1)
+// becomes   first_run x r,  then tokens (id, n) = "dictionary entry id, followed by n x r",   one 32-bit word each:
+//     word = id | n << 8,   id < 256 (ids < nsym: single symbols, larger ids: pairs as above),   n <= RUN_MAX.
+// Pairs are learned on the entries only: (x, y) may merge where x carries no run (n == 0); the merged token keeps
+// y's run.  Any such encoding is exact, like the pair dictionary itself.  Runs longer than RUN_MAX are continued by
+// tokens whose entry is the run symbol itself (one site) -- rare, and it keeps the kernel free of special cases.
+// ------------------------------------------------------------------------------------------------
+// (RUN_LO_BITS, RUN_MAX, ...: zip_kernels.cuh)
+static inline uint32_t run_word(int id, int n) { return (uint32_t)id | ((uint32_t)n << 8); }
+
+// symbols 1..L-1 of a chunk -> leading run + run tokens over the plain symbols (no pairs yet)
+static void run_tokenize(const uint8_t* sym, size_t n, int run_sym, int* first_run, std::vector<uint32_t>& out) {
+    out.clear();
+    size_t t = 0;
+    while (t < n && sym[t] == run_sym && (int)t < RUN_MAX) ++t;
+    *first_run = (int)t;
+    while (t < n) {
+        const int id = sym[t++];               // equals run_sym only when it continues an over-long run
+        int r = 0;
+        while (t < n && sym[t] == run_sym && r < RUN_MAX) { ++t; ++r; }
+        out.push_back(run_word(id, r));
+    }
+}
+
+// one left-to-right pass: (a with no run, b) -> id keeping b's run; in place, returns the new length
+static inline size_t run_replace(uint32_t* s, size_t n, uint32_t a, uint32_t b, uint32_t id) {
+    size_t w = 0, t = 0;
+    while (t < n) {
+        if (t + 1 < n && s[t] == a && (s[t + 1] & 0xffu) == b) { s[w++] = (s[t + 1] & ~0xffu) | id; t += 2; }
+        else { s[w++] = s[t++]; }
+    }
+    return w;
+}
+
+static ZipMerges run_learn(std::vector<std::vector<uint32_t>>& sample, int nsym, int max_ids, long long min_count) {
+    ZipMerges mg;
+    mg.nsym = nsym;
+    if (max_ids > 256) max_ids = 256;
+    std::vector<long long> counts;
+    int ns = nsym;
+    while (ns < max_ids) {
+        counts.assign((size_t)ns * ns, 0);
+        for (const auto& s : sample)
+            for (size_t t = 0; t + 1 < s.size(); ++t)
+                if (s[t] < 256u) counts[(size_t)s[t] * ns + (s[t + 1] & 0xffu)]++;      // s[t] < 256: no run attached
+        long long best = 0;
+        int ba = 0, bb = 0;
+        for (int a = 0; a < ns; ++a)
+            for (int b = 0; b < ns; ++b)
+                if (counts[(size_t)a * ns + b] > best) { best = counts[(size_t)a * ns + b]; ba = a; bb = b; }
+        if (best < min_count) break;
+        for (auto& s : sample) s.resize(run_replace(s.data(), s.size(), (uint32_t)ba, (uint32_t)bb, (uint32_t)ns));
+        mg.pairs.push_back({(uint8_t)ba, (uint8_t)bb});
+        ++ns;
+    }
+    return mg;
+}
+
+static void run_encode(const ZipMerges& mg, const uint8_t* sym, size_t n, int run_sym, int* first_run, std::vector<uint32_t>& out) {
+    run_tokenize(sym, n, run_sym, first_run, out);
+    size_t len = out.size();
+    for (size_t i = 0; i < mg.pairs.size() && len >= 2; ++i)
+        len = run_replace(out.data(), len, mg.pairs[i][0], mg.pairs[i][1], (uint32_t)(mg.nsym + i));
+    out.resize(len);
+    out.shrink_to_fit();
+}
+
+// run tokens over the first M ids only (larger ids expanded into their parts, the run stays with the last part)
+static void run_expand(const ZipMerges& mg, const std::vector<uint32_t>& in, int M, std::vector<uint32_t>& out) {
+    out.clear();
+    out.reserve(in.size());
+    uint8_t stack[512];
+    for (uint32_t w : in) {
+        const int id = (int)(w & 0xffu);
+        if (id < M) { out.push_back(w); continue; }
+        int sp = 0;
+        stack[sp++] = (uint8_t)id;
+        while (sp > 0) {
+            const uint8_t x = stack[--sp];
+            if (x < M) { out.push_back(x); continue; }
+            const auto& p = mg.pairs[x - mg.nsym];
+            stack[sp++] = p[1];
+            stack[sp++] = p[0];
+        }
+        out.back() |= w & ~0xffu;
+    }
+}
+
 // fn(i) for i in [0, n) on the host cores of the affinity mask; returns false if any call threw (out of memory)
 template <typename F>
 static bool parallel_for(int n, F&& fn) {

@@ -18,7 +18,7 @@ static int zip_tile(int K) {
 }
 static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
 
-struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; };
+struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; bool spec; };
 #ifndef IMC_ZIP8_THREADS
 #define IMC_ZIP8_THREADS 512     // threads of the single-CTA-per-SM shape with 8 lanes per chain, K <= 24 (experiment builds: 640, 768)
 #endif
@@ -34,7 +34,7 @@ static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM 
 // rows of four tokens)
 static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 : 8; }
 
-template <int K>
+template <int K, bool SPEC>
 static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
     ZipPlan p;
     p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
@@ -45,18 +45,18 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
         using C = ZipCfg32<K>;
         t1 = K <= 24 ? 512 : 256;
         m2 = 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+        m1 = ZipSmem<C, SPEC>::max_entries(ZIP_SMEM_SM, S, t1);
         want_ctas = 1;
     } else if (p.lanes == 8) {
         using C = ZipCfg8<K>;
         t1 = K <= 24 ? IMC_ZIP8_THREADS : 256;
-        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+        m2 = K <= 24 ? ZipSmem<C, SPEC>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C, SPEC>::max_entries(ZIP_SMEM_SM, S, t1);
     } else {
         using C = ZipCfg4<K>;
         t1 = 256;
-        m2 = K <= 24 ? ZipSmem<C>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
-        m1 = ZipSmem<C>::max_entries(ZIP_SMEM_SM, S, t1);
+        m2 = K <= 24 ? ZipSmem<C, SPEC>::max_entries((ZIP_SMEM_SM - 1024) / 2, S, 256) : 0;
+        m1 = ZipSmem<C, SPEC>::max_entries(ZIP_SMEM_SM, S, t1);
     }
     int ctas = want_ctas;
     if (ctas == 2 && K > 24) ctas = 1;
@@ -66,15 +66,17 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
     p.M = std::min(avail_ids, ctas == 2 ? m2 : m1);
     if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
     p.M = std::max(p.M, S);
-    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>>::bytes(p.M, S, p.threads)
-           : (p.lanes == 4 ? ZipSmem<ZipCfg4<K>>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg32<K>>::bytes(p.M, S, p.threads));
+    p.spec = SPEC;
+    p.smem = p.lanes == 8 ? ZipSmem<ZipCfg8<K>, SPEC>::bytes(p.M, S, p.threads)
+           : (p.lanes == 4 ? ZipSmem<ZipCfg4<K>, SPEC>::bytes(p.M, S, p.threads) : ZipSmem<ZipCfg32<K>, SPEC>::bytes(p.M, S, p.threads));
     return p;
 }
 
-static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0) {
+// spec: plan for the spectral form (run tokens, power table in shared memory) over avail_ids run-dictionary ids
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0, bool spec = false) {
     const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
     switch (zip_tile(K)) {
-#define X(k) case k: *out = zip_plan_k<k>(S, avail_ids, want, lanes); break;
+#define X(k) case k: *out = spec ? zip_plan_k<k, true>(S, avail_ids, want, lanes) : zip_plan_k<k, false>(S, avail_ids, want, lanes); break;
         ZIP_K_LIST(X)
 #undef X
         default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
@@ -83,52 +85,62 @@ static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_overrid
     return IMC_OK;
 }
 
-// token streams over the first M dictionary ids, level-ordered, on the device (cached per M)
-static int zip_device_build(imc_seqset* set, int M, ZipDevice** out);
-static int zip_device(imc_seqset* set, int M, ZipDevice** out) {
-    try { return zip_device_build(set, M, out); }
+// token streams over the first M dictionary ids, level-ordered, on the device (cached per M and form)
+static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out);
+static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false) {
+    try { return zip_device_build(set, M, spec, out); }
     catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams"); }
 }
-static int zip_device_build(imc_seqset* set, int M, ZipDevice** out) {
-    for (ZipDevice* z : set->zip_dev) if (z->M == M) { *out = z; return IMC_OK; }
+static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) {
+    for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec) { *out = z; return IMC_OK; }
     const int ns = (int)set->streams.size();
-    ZipLevels zl = zip_levels(set->merges, M);
-    std::vector<std::vector<uint8_t>> tok(ns);
+    const ZipMerges& mg = spec ? set->run_merges : set->merges;
+    ZipLevels zl = zip_levels(mg, M);
+    const size_t tsz = spec ? 4 : 1, align = spec ? 32 : 16;      // bytes per token; streams padded to whole blocks + one block of slack
+    std::vector<std::vector<uint8_t>> tok(spec ? 0 : ns);
+    std::vector<std::vector<uint32_t>> rtok(spec ? ns : 0);
     if (!parallel_for(ns, [&](int k) {
-            zip_expand(set->merges, set->tok_full[k], M, tok[k]);
-            for (auto& t : tok[k]) t = zl.perm[t];
+            if (spec) {
+                run_expand(mg, set->run_tok_full[k], M, rtok[k]);
+                for (auto& t : rtok[k]) t = (t & ~0xffu) | zl.perm[t & 0xffu];
+            } else {
+                zip_expand(mg, set->tok_full[k], M, tok[k]);
+                for (auto& t : tok[k]) t = zl.perm[t];
+            }
         })) return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams");
+    auto ntok = [&](int k) { return spec ? rtok[k].size() : tok[k].size(); };
     std::vector<int> order(ns);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tok[x].size() > tok[y].size(); });
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ntok(x) > ntok(y); });
     std::vector<ZipChunk> chunks(ns);
     long long off = 0;
     for (int i = 0; i < ns; ++i) {
         const int k = order[i];
-        if (tok[k].size() > 0x7fffffffULL) return fail(IMC_ERR_UNSUPPORTED, "a chunk has more than 2^31-1 tokens");
+        if (ntok(k) > 0x7fffffffULL) return fail(IMC_ERR_UNSUPPORTED, "a chunk has more than 2^31-1 tokens");
         chunks[i].tok_off = off;
-        chunks[i].ntok = (int)tok[k].size();
+        chunks[i].ntok = (int)ntok(k);
         chunks[i].first_sym = set->first_sym[k];
         chunks[i].out_index = k;
-        chunks[i].pad = 0;
-        off += (long long)((tok[k].size() + 15) / 16) * 16 + 16;
+        chunks[i].first_run = spec ? set->first_run[k] : 0;
+        off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
     std::vector<uint8_t> flat((size_t)off, 0);
     long long total = 0;
     for (int i = 0; i < ns; ++i) {
-        const auto& t = tok[order[i]];
-        if (!t.empty()) memcpy(flat.data() + chunks[i].tok_off, t.data(), t.size());
-        total += (long long)t.size();
+        const int k = order[i];
+        if (ntok(k)) memcpy(flat.data() + chunks[i].tok_off, spec ? (const void*)rtok[k].data() : (const void*)tok[k].data(), ntok(k) * tsz);
+        total += (long long)ntok(k);
     }
     ZipDevice* z = new (std::nothrow) ZipDevice;
     if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
     z->M = M;
+    z->spec = spec;
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
     z->max_ntok = ns ? chunks[0].ntok : 0;
     z->host_chunks.swap(chunks);      // no copy, cannot throw
     int rc;
-    if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 16))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
+    if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 64))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||
         (rc = z->pairs.reserve(std::max<size_t>(zl.pairs.size(), 16))) || (rc = z->levels.reserve(sizeof(int) * zl.level_start.size()))) {
         z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release();
         delete z;
@@ -165,10 +177,11 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
         const int first_chain = (int)chains.size();
         for (int sg = 0; sg < nseg; ++sg) {
             ZipChunk c = ch;
-            c.tok_off = ch.tok_off + (long long)sg * seglen;
+            c.tok_off = ch.tok_off + (long long)sg * seglen * (z->spec ? 4 : 1);
             c.ntok = std::max(0, std::min(seglen, ch.ntok - sg * seglen));
             for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
                 c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
+                c.first_run = sg == 0 ? ch.first_run : 0;
                 c.out_index = (int)chains.size();
                 chains.push_back(c);
             }
@@ -217,36 +230,36 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
     return IMC_OK;
 }
 
-template <class C, int THREADS, int MINB>
+template <class C, int THREADS, int MINB, bool SPEC>
 static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
     static size_t attr_max = 0;
     if (p.smem > attr_max) {
-        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<C, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        CUDA_TRY(cudaFuncSetAttribute(zip_forward_kernel<C, THREADS, MINB, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         attr_max = p.smem;
     }
-    zip_forward_kernel<C, THREADS, MINB><<<grid, THREADS, p.smem, st>>>(a);
+    zip_forward_kernel<C, THREADS, MINB, SPEC><<<grid, THREADS, p.smem, st>>>(a);
     return IMC_OK;
 }
 
-template <int K>
+template <int K, bool SPEC>
 static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
     if constexpr (K >= 10) {
         if (p.lanes == 32) {
-            if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1>(a, p, grid, st);
-            else return launch_zip_k<ZipCfg32<K>, 256, 1>(a, p, grid, st);
+            if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1, SPEC>(a, p, grid, st);
+            else return launch_zip_k<ZipCfg32<K>, 256, 1, SPEC>(a, p, grid, st);
         }
     }
     if constexpr (K >= 8) {
         if (p.lanes == 4) {
-            if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2>(a, p, grid, st); }
-            return launch_zip_k<ZipCfg4<K>, 256, 1>(a, p, grid, st);
+            if constexpr (K <= 24) { if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg4<K>, 256, 2, SPEC>(a, p, grid, st); }
+            return launch_zip_k<ZipCfg4<K>, 256, 1, SPEC>(a, p, grid, st);
         }
     }
     if constexpr (K <= 24) {
-        if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2>(a, p, grid, st);
-        return launch_zip_k<ZipCfg8<K>, IMC_ZIP8_THREADS, 1>(a, p, grid, st);
+        if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfg8<K>, 256, 2, SPEC>(a, p, grid, st);
+        return launch_zip_k<ZipCfg8<K>, IMC_ZIP8_THREADS, 1, SPEC>(a, p, grid, st);
     } else {
-        return launch_zip_k<ZipCfg8<K>, 256, 1>(a, p, grid, st);
+        return launch_zip_k<ZipCfg8<K>, 256, 1, SPEC>(a, p, grid, st);
     }
 }
 
@@ -261,7 +274,7 @@ static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
     // them: the chains then spread over all SMs instead of piling onto the first CTAs that arrive
     a.active_warps = (int)std::min<long long>(p.threads / 32, std::max<long long>(1, (units + grid - 1) / grid));
     switch (zip_tile(a.K)) {
-#define X(k) case k: return launch_zip_shape<k>(a, p, grid, st);
+#define X(k) case k: return p.spec ? launch_zip_shape<k, true>(a, p, grid, st) : launch_zip_shape<k, false>(a, p, grid, st);
         ZIP_K_LIST(X)
 #undef X
     }
@@ -313,3 +326,67 @@ extern "C" int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_
     return IMC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ run tokens (spectral form)
+extern "C" int imc_seqset_run_info(imc_seqset* set, int K, int* run_sym, int* ids_available, int* ids_used, int64_t* tokens, int* levels) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    if (run_sym) *run_sym = set->fold_sym;
+    if (ids_available) *ids_available = set->run_merges.size();
+    if (!ids_used && !tokens && !levels) return IMC_OK;
+    ZipPlan plan;
+    int rc = zip_plan(K, set->nsym, set->run_merges.size(), &plan, 0, true);
+    if (rc) return rc;
+    if (ids_used) *ids_used = plan.M;
+    if (levels) *levels = (int)zip_levels(set->run_merges, plan.M).level_start.size() - 1;
+    if (tokens) {
+        const ZipMerges& mg = set->run_merges;
+        std::vector<long long> len(mg.size(), 1);      // entries a full-dictionary token expands to over the first plan.M ids
+        for (int id = std::max(plan.M, set->nsym); id < mg.size(); ++id) {
+            const auto& pr = mg.pairs[id - set->nsym];
+            len[id] = len[pr[0]] + len[pr[1]];
+        }
+        long long total = 0;
+        for (const auto& t : set->run_tok_full) for (uint32_t x : t) total += len[x & 0xffu];
+        *tokens = total;
+    }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_run_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs) {
+    if (!set || !pairs_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    const auto& pairs = set->run_merges.pairs;
+    if (capacity_pairs < (int)pairs.size()) return fail(IMC_ERR_INVALID, "capacity %d < %zu pairs", capacity_pairs, pairs.size());
+    for (size_t i = 0; i < pairs.size(); ++i) { pairs_out[2 * i] = pairs[i][0]; pairs_out[2 * i + 1] = pairs[i][1]; }
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_run_tokens(imc_seqset* set, int chunk, int ids, uint32_t* out, int64_t capacity, int64_t* ntokens, int* first_run) {
+    if (!set || !ntokens) return fail(IMC_ERR_INVALID, "NULL argument");
+    if (chunk < 0 || chunk >= set->n_chunks) return fail(IMC_ERR_INVALID, "chunk %d out of range", chunk);
+    if (ids < set->nsym || ids > set->run_merges.size()) return fail(IMC_ERR_INVALID, "ids must be in [%d, %d]", set->nsym, set->run_merges.size());
+    const int k = set->stream_of_chunk[chunk];
+    if (first_run) *first_run = k < 0 ? 0 : set->first_run[k];
+    if (k < 0) { *ntokens = 0; return IMC_OK; }
+    std::vector<uint32_t> tok;
+    try { run_expand(set->run_merges, set->run_tok_full[k], ids, tok); }
+    catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory"); }
+    *ntokens = (int64_t)tok.size();
+    if (out) {
+        if (capacity < (int64_t)tok.size()) return fail(IMC_ERR_INVALID, "capacity %lld < %zu tokens", (long long)capacity, tok.size());
+        if (!tok.empty()) memcpy(out, tok.data(), tok.size() * sizeof(uint32_t));
+    }
+    return IMC_OK;
+}
+
+// how the last spectral call on this set split its points (synchronises the device; tests)
+extern "C" int imc_seqset_spectral_counts(imc_seqset* set, int* ok_points, int* plain_points) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    int c[2] = {0, 0};
+    if (set->d_lists.p) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(c, set->d_lists.p, sizeof c, cudaMemcpyDeviceToHost));
+    }
+    if (ok_points) *ok_points = c[0];
+    if (plain_points) *plain_points = c[1];
+    return IMC_OK;
+}

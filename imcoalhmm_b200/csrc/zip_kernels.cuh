@@ -21,13 +21,20 @@
 
 namespace imc {
 
+// Run tokens of the spectral form (tokenizer.inl): word = id | n << 8, n = a + (b << RUN_LO_BITS) sites of the run symbol
+// after entry id; Lambda^n = ptab[a] o ptab[RUN_LO_ROWS + b] (two rows of the per-point power table).
+constexpr int RUN_LO_BITS = 6, RUN_HI_BITS = 6;
+constexpr int RUN_LO_ROWS = 1 << RUN_LO_BITS, RUN_LO_MASK = RUN_LO_ROWS - 1;
+constexpr int RUN_ROWS = RUN_LO_ROWS + (1 << RUN_HI_BITS);
+constexpr int RUN_MAX = (1 << (RUN_LO_BITS + RUN_HI_BITS)) - 1;
+
 struct ZipChunk {
     long long tok_off;   // byte offset of the chunk's first token (16-byte aligned, 16 readable bytes past the end)
     int ntok;            // tokens (the chunk's symbols 1..L-1 after compression)
     int first_sym;       // >= 0: symbol at position 0 (alpha_0 = pi o E[:,first_sym]);  < 0: the chain starts from the
                          // unit vector e_c, c = -1 - first_sym (column c of a segment's transfer matrix, see zip_fold_kernel)
     int out_index;       // column of chain_out this chunk writes
-    int pad;
+    int first_run;       // spectral form: sites of the run symbol between position 0 and the first token (<= RUN_MAX)
 };
 
 struct ZipArgs {
@@ -55,6 +62,15 @@ struct ZipArgs {
     double* carry;               // [N][nchunks][carry_stride]: state registers of the chain's lanes, exponent, flags
     int carry_stride;
     int* progress;               // [N][nchunks] pieces completed (zeroed before the launch)
+    // Subset of the points served by this launch (NULL: all N).  The spectral form serves the points whose C_r could be
+    // diagonalised, the plain form the others; both lists are written by zip_spectral_kernel, so the split never
+    // touches the host.  point_next is indexed by position in the list, everything else by the point itself.
+    const int* plist;
+    const int* pcount;
+    // spectral form (SPEC kernels): tokens are 32-bit run words (tokenizer.inl), per point spec_stride doubles:
+    // lambda[K], wsum[K], b0[S][K], R[S][K][K]  (see zip_spectral_kernel)
+    const double* spec;
+    int spec_stride;
 };
 
 // Segmented mode (chain-scarce calls: few chunks x few points).  A long chunk is cut into segments of `seglen` tokens.
@@ -133,21 +149,31 @@ struct ZipCfg8 {
         __device__ __forceinline__ bool writer() const { return q == 0; }
     };
     __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
-    // four tokens (one 32-bit word of the stream) on the fast path of the GROUP4 shape
-    __device__ static __forceinline__ void word4(double (&al)[KP], const double* dict, const long long* dexp, uint32_t wv,
-                                                 const Lane& L, int& buf, long long& scale) {
-        const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the word, remainder row pr
-        const int myid = (wv >> (8 * cj)) & 0xffu;
+    // four tokens on the fast path of the GROUP4 shape; w[b] = id | run << 8 (run == 0 in the plain form)
+    template <bool SPEC>
+    __device__ static __forceinline__ void word4(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
+                                                 const int* pexp, const uint32_t (&w)[4], const Lane& L, int& buf, long long& scale) {
+        const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the four, remainder row pr
+        const uint32_t myw = cj == 0 ? w[0] : (cj == 1 ? w[1] : (cj == 2 ? w[2] : w[3]));
+        const int myid = myw & 0xffu;
         const double2* rp = reinterpret_cast<const double2*>(dict + (size_t)myid * STRIDE_D) + FULL * CP * 8 + L.q;
         double2 rm[CP];
 #pragma unroll
         for (int cp = 0; cp < CP; ++cp) rm[cp] = rp[cp * 8];
         scale += dexp[myid];       // every lane pair books the exponent of ITS token; zip_run_unit adds the four pairs up
+        double frem = 1.0;
+        if (SPEC) {
+            const int ra = (myw >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (myw >> (8 + RUN_LO_BITS));
+            frem = ptab[ra * KP + 8 * FULL + pr] * ptab[rb * KP + 8 * FULL + pr];
+            scale += pexp[ra] + pexp[rb];
+        }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int id = (wv >> (8 * b)) & 0xffu;
+            const int id = w[b] & 0xffu;
             double* sb = L.sb0 + buf * KP;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
+            const double* pa = ptab + ((w[b] >> 8) & RUN_LO_MASK) * KP + L.q;
+            const double* pb = ptab + (RUN_LO_ROWS + (w[b] >> (8 + RUN_LO_BITS))) * KP + L.q;
 #pragma unroll
             for (int k = 0; k < FULL; ++k) {
                 double s0 = 0.0, s1 = 0.0;
@@ -157,7 +183,7 @@ struct ZipCfg8 {
                     s0 = fma(m.x, al[2 * cp], s0);
                     s1 = fma(m.y, al[2 * cp + 1], s1);
                 }
-                sb[L.q + 8 * k] = s0 + s1;
+                sb[L.q + 8 * k] = SPEC ? (s0 + s1) * (pa[8 * k] * pb[8 * k]) : s0 + s1;
             }
             if (cj == b) {
                 double s0 = 0.0, s1 = 0.0;
@@ -166,7 +192,7 @@ struct ZipCfg8 {
                     s0 = fma(rm[cp].x, al[2 * cp], s0);
                     s1 = fma(rm[cp].y, al[2 * cp + 1], s1);
                 }
-                sb[8 * FULL + pr] = s0 + s1;
+                sb[8 * FULL + pr] = SPEC ? (s0 + s1) * frem : s0 + s1;
             }
             __syncwarp();
 #pragma unroll
@@ -178,11 +204,15 @@ struct ZipCfg8 {
             buf ^= 1;
         }
     }
-    template <bool PRED>
-    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
-                                                const Lane& L, int buf, long long& scale, bool active) {
+    template <bool PRED, bool SPEC>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
+                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
+            const int id = w & 0xffu;
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            const double* pa = ptab + ra * KP;
+            const double* pb = ptab + rb * KP;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
@@ -194,10 +224,14 @@ struct ZipCfg8 {
                         s0 = fma(m.x, al[2 * cp], s0);
                         s1 = fma(m.y, al[2 * cp + 1], s1);
                     }
-                    sb[k < FULL ? L.q + 8 * k : L.rem_row] = s0 + s1;
+                    const int row = k < FULL ? L.q + 8 * k : L.rem_row;
+                    sb[row] = SPEC ? (s0 + s1) * (pa[row] * pb[row]) : s0 + s1;
                 }
             }
-            if (!GROUP4 || L.q < 2) scale += dexp[id];      // GROUP4: token exponents are per-pair partial sums
+            if (!GROUP4 || L.q < 2) {                       // GROUP4: token exponents are per-pair partial sums
+                scale += dexp[id];
+                if (SPEC) scale += pexp[ra] + pexp[rb];
+            }
         }
         __syncwarp();
         if (!PRED || active) {
@@ -254,11 +288,15 @@ struct ZipCfg4 {
     };
     // register k of a slot-c lane holds state 2*((k/2)^c) + k%2
     __device__ static __forceinline__ int state_of(const Lane& L, int k) { return 2 * ((k >> 1) ^ L.c) + (k & 1); }
-    template <bool PRED>
-    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
-                                                const Lane& L, int buf, long long& scale, bool active) {
+    template <bool PRED, bool SPEC>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
+                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
+            const int id = w & 0xffu;
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            const double* pa = ptab + ra * KP + L.g;
+            const double* pb = ptab + rb * KP + L.g;
             const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
             const char* me = mb + L.off_even;
             const char* mo = mb + L.off_odd;
@@ -272,9 +310,10 @@ struct ZipCfg4 {
                     s0 = fma(m.x, al[2 * cp], s0);
                     s1 = fma(m.y, al[2 * cp + 1], s1);
                 }
-                sb[L.g + 4 * k] = s0 + s1;
+                sb[L.g + 4 * k] = SPEC ? (s0 + s1) * (pa[4 * k] * pb[4 * k]) : s0 + s1;
             }
             scale += dexp[id];
+            if (SPEC) scale += pexp[ra] + pexp[rb];
         }
         __syncwarp();
         if (!PRED || active) {
@@ -317,11 +356,15 @@ struct ZipCfg32 {
         __device__ __forceinline__ bool writer() const { return q == 0; }
     };
     __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
-    template <bool PRED>
-    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, int id,
-                                                const Lane& L, int buf, long long& scale, bool active) {
+    template <bool PRED, bool SPEC>
+    __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
+                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + buf * KP;
         if (!PRED || active) {
+            const int id = w & 0xffu;
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            const double* pa = ptab + ra * KP + L.q;
+            const double* pb = ptab + rb * KP + L.q;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
@@ -333,10 +376,11 @@ struct ZipCfg32 {
                         s0 = fma(m.x, al[2 * cp], s0);
                         s1 = fma(m.y, al[2 * cp + 1], s1);
                     }
-                    sb[L.q + 32 * k] = s0 + s1;
+                    sb[L.q + 32 * k] = SPEC ? (s0 + s1) * (pa[32 * k] * pb[32 * k]) : s0 + s1;
                 }
             }
             scale += dexp[id];
+            if (SPEC) scale += pexp[ra] + pexp[rb];
         }
         __syncwarp();
         if (!PRED || active) {
@@ -350,12 +394,14 @@ struct ZipCfg32 {
     }
 };
 
-template <class C>
+template <class C, bool SPEC>
 struct ZipSmem {
-    __host__ __device__ static constexpr int se_doubles(int S) { return (C::K * S + 1) & ~1; }   // keeps what follows 16-byte aligned
+    // doubles in front of the exchange buffers: plain form E[K][S], spectral form the start vectors b0[S][KP]
+    __host__ __device__ static constexpr int se_doubles(int S) { return ((SPEC ? C::KP : C::K) * S + 1) & ~1; }   // keeps what follows 16-byte aligned
+    __host__ __device__ static constexpr int tab_doubles() { return SPEC ? RUN_ROWS * C::KP : 0; }
     static size_t bytes(int M, int S, int threads) {
-        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP;
-        return d * sizeof(double) + (size_t)M * sizeof(long long) + 4 * sizeof(int);   // dexp[M], s_point[2]
+        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP + tab_doubles();
+        return d * sizeof(double) + (size_t)M * sizeof(long long) + (SPEC ? RUN_ROWS * sizeof(int) : 0) + 4 * sizeof(int);   // dexp[M], pexp, s_point[2] + s_best
     }
     static int max_entries(size_t budget, int S, int threads) {
         const size_t fixed = bytes(0, S, threads);
@@ -365,13 +411,19 @@ struct ZipSmem {
     }
 };
 
-template <class C>
+// Take the binary exponent of the state out of it (exactly).  Plain form: the entries are probabilities, their sum
+// measures the state.  Spectral form: the entries are coordinates in the eigenbasis of C_r and may be negative; the
+// largest magnitude measures the state, the sum of magnitudes only serves to notice NaN / infinity.
+template <class C, bool SPEC>
 __device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scale, bool& dead, bool& isnan) {
-    double sum = 0.0;
+    double sum = 0.0, mx = 0.0;
 #pragma unroll
-    for (int k = 0; k < C::KP; ++k) sum += al[k];       // padding registers hold 0
+    for (int k = 0; k < C::KP; ++k) {       // padding registers hold 0
+        if (SPEC) { const double v = fabs(al[k]); sum += v; mx = fmax(mx, v); }
+        else sum += al[k];
+    }
     if (sum > 0.0 && sum < 1.7e308) {
-        const int e = exponent_of(sum);
+        const int e = exponent_of(SPEC ? mx : sum);
         const double f = pow2_neg(e);
 #pragma unroll
         for (int k = 0; k < C::KP; ++k) al[k] *= f;
@@ -383,8 +435,15 @@ __device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scal
 }
 
 // Build the dictionary of parameter point n in shared memory (all threads of the CTA).
-template <class C, int THREADS>
-__device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, long long* dexp) {
+//   plain form:     base entries C_s[r][c] = E[r][s] T[c][r];  sE = E, spi = pi
+//   spectral form:  base entries R_s = V^-1 C_s V from zip_spectral_kernel;  sE = start vectors b0[s] = V^-1 (pi o E[:,s]),
+//                   spi = wsum = V^T 1 (so that sum(alpha) = wsum . beta), and the power table
+//                   ptab[a]      = lambda^a        (a < 2^RUN_LO_BITS)
+//                   ptab[LO + b] = lambda^(b << RUN_LO_BITS)
+//                   each row scaled by an exact power of two, 2^-pexp[row], so that its largest entry is in [1,2)
+template <class C, int THREADS, bool SPEC>
+__device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, long long* dexp,
+                                                     double* ptab, int* pexp) {
     constexpr int KP = C::KP, NW = THREADS / 32;
     const int K = a.K;          // actual state count <= C::K (the kernel's tile); rows / columns beyond it stay zero
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -392,9 +451,29 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
     const double* Tg = a.T + (size_t)n * K * K;
     const double* Eg = a.E + (size_t)n * K * S;
     const double* pig = a.pi + (size_t)n * K;
+    const double* sp = SPEC ? a.spec + (size_t)n * a.spec_stride : nullptr;     // lambda[K], wsum[K], b0[S][K], R[S][K][K]
     for (int x = tid; x < M * C::STRIDE_D; x += THREADS) dict[x] = 0.0;
-    for (int x = tid; x < K * S; x += THREADS) sE[x] = Eg[x];
-    for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? pig[x] : 0.0;
+    if (SPEC) {
+        for (int x = tid; x < S * KP; x += THREADS) { const int s = x / KP, k = x - s * KP; sE[x] = k < K ? sp[2 * K + s * K + k] : 0.0; }
+        for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? sp[K + x] : 0.0;
+        // power table: with rho_k = lambda_k / lambda_max (|rho| <= 1) and p the row's exponent,
+        // lambda_k^p = rho_k^p * 2^(p log2 lambda_max); the integer part of p log2 lambda_max goes to pexp
+        double lmax = 0.0;
+        for (int k = 0; k < K; ++k) lmax = fmax(lmax, fabs(sp[k]));
+        const double l2 = log2(lmax);
+        for (int x = tid; x < RUN_ROWS * KP; x += THREADS) {
+            const int row = x / KP, k = x - row * KP;
+            const double p = row < RUN_LO_ROWS ? (double)row : (double)((row - RUN_LO_ROWS) << RUN_LO_BITS);
+            const double xe = p * l2, fe = floor(xe);
+            double v = 0.0;
+            if (k < K) v = exp2(xe - fe) * (p == 0.0 ? 1.0 : pow(sp[k] / lmax, p));
+            ptab[x] = v;
+            if (k == 0) pexp[row] = (int)fe;
+        }
+    } else {
+        for (int x = tid; x < K * S; x += THREADS) sE[x] = Eg[x];
+        for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? pig[x] : 0.0;
+    }
     __syncthreads();
     for (int lv = -1; lv < a.nlevels; ++lv) {
         const int lo = lv < 0 ? 0 : a.level_start[lv], hi = lv < 0 ? S : a.level_start[lv + 1];
@@ -403,10 +482,11 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
             double mx = 0.0;
             bool bad = false;
             long long ebase = 0;
-            if (lv < 0) {     // C_s[r][c] = E[r][s] * T[c][r]
+            if (lv < 0) {     // plain: C_s[r][c] = E[r][s] * T[c][r];  spectral: R_s[r][c]
+                const double* Rg = SPEC ? sp + 2 * K + S * K + (size_t)e * K * K : nullptr;
                 for (int x = lane; x < K * K; x += 32) {
                     const int r = x % K, c = x / K;      // rows fastest: consecutive lanes touch consecutive 16-byte units
-                    const double v = sE[r * S + e] * Tg[c * K + r];
+                    const double v = SPEC ? Rg[r * K + c] : sE[r * S + e] * Tg[c * K + r];
                     C::store(D, r, c, v);
                     mx = fmax(mx, fabs(v));
                     bad = bad || !(fabs(v) < 1.7e308);
@@ -444,10 +524,12 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
 
 // One warp-load of chains (C::CPW of them, one per lane group) of parameter point n: the chunks
 // unit*CPW .. unit*CPW + CPW-1 of the sorted chunk list.
-template <class C>
+template <class C, bool SPEC>
 __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
-                                             const double* spi, const long long* dexp, const typename C::Lane& L) {
+                                             const double* spi, const long long* dexp, const double* ptab, const int* pexp,
+                                             const typename C::Lane& L) {
     constexpr int KP = C::KP;
+    constexpr int BLK = SPEC ? 8 : 16;        // tokens per block (two / one 16-byte loads); the state is rescaled every 8 tokens
     const int K = a.K, S = a.S;
     int seg = 0, quad = unit;
     if (a.nseg > 1) {          // pipelined mode: units are numbered piece-major, so a chunk's pieces are claimed in order
@@ -460,7 +542,7 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
     const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
     const int tok0 = seg * a.seglen;
     const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
-    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + tok0);
+    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + (size_t)tok0 * (SPEC ? 4 : 1));
     int maxnt = nt;
 #pragma unroll
     for (int m = 16; m >= C::G; m >>= 1) maxnt = max(maxnt, __shfl_xor_sync(0xffffffffu, maxnt, m));
@@ -475,8 +557,19 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const int st = C::state_of(L, k);
-            if (ch.first_sym >= 0) al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
-            else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
+            if (ch.first_sym >= 0) {
+                if (SPEC) al[k] = sE[ch.first_sym * KP + st];
+                else al[k] = st < K ? spi[st] * sE[st * S + ch.first_sym] : 0.0;
+            } else al[k] = st == -1 - ch.first_sym ? 1.0 : 0.0;
+        }
+        if (SPEC && ch.first_run > 0) {       // run-symbol sites between position 0 and the first token
+            const int ra = ch.first_run & RUN_LO_MASK, rb = RUN_LO_ROWS + (ch.first_run >> RUN_LO_BITS);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int st = C::state_of(L, k);
+                al[k] *= ptab[ra * KP + st] * ptab[rb * KP + st];
+            }
+            scale += pexp[ra] + pexp[rb];
         }
     } else if (have) {         // every lane of the chain waits for the predecessor piece itself, then reads what it left
         while (*((volatile int*)prog) < seg) __nanosleep(200);
@@ -492,45 +585,72 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
         for (int k = 0; k < KP; ++k) al[k] = 0.0;
     }
     int buf = 0;
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (nt > 0) cur = tp[0];
-    for (int blk = 0; blk * 16 < maxnt; ++blk) {
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if ((blk + 1) * 16 < nt) nxt = tp[blk + 1];
-        const int rem = nt - blk * 16;
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        if (__all_sync(0xffffffffu, rem >= 16)) {
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                uint32_t wv = w[wi];
+    uint4 cur = make_uint4(0, 0, 0, 0), cur2 = cur;
+    if (nt > 0) { cur = tp[0]; if (SPEC) cur2 = tp[1]; }        // 16 readable bytes of slack behind every stream
+    for (int blk = 0; blk * BLK < maxnt; ++blk) {
+        uint4 nxt = make_uint4(0, 0, 0, 0), nxt2 = nxt;
+        if ((blk + 1) * BLK < nt) {
+            if (SPEC) { nxt = tp[2 * blk + 2]; nxt2 = tp[2 * blk + 3]; }
+            else nxt = tp[blk + 1];
+        }
+        const int rem = nt - blk * BLK;
+        if (SPEC) {
+            const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, cur2.x, cur2.y, cur2.z, cur2.w};
+            if (__all_sync(0xffffffffu, rem >= BLK)) {
                 if constexpr (C::GROUP4) {
-                    C::word4(al, dict, dexp, wv, L, buf, tscale);
+                    const uint32_t w0[4] = {w[0], w[1], w[2], w[3]}, w1[4] = {w[4], w[5], w[6], w[7]};
+                    C::template word4<true>(al, dict, dexp, ptab, pexp, w0, L, buf, tscale);
+                    C::template word4<true>(al, dict, dexp, ptab, pexp, w1, L, buf, tscale);
                 } else {
 #pragma unroll C::UNROLL
-                    for (int b = 0; b < 4; ++b) {
-                        const int id = wv & 0xffu;
-                        wv >>= 8;
-                        C::template step<false>(al, dict, dexp, id, L, buf, tscale, true);
+                    for (int b = 0; b < 8; ++b) {
+                        C::template step<false, true>(al, dict, dexp, ptab, pexp, w[b], L, buf, tscale, true);
                         buf ^= 1;
                     }
                 }
-                if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
-            }
-        } else {
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                uint32_t wv = w[wi];
+            } else {
 #pragma unroll 1
-                for (int b = 0; b < 4; ++b) {
-                    const int id = wv & 0xffu;
-                    wv >>= 8;
-                    C::template step<true>(al, dict, dexp, id, L, buf, tscale, wi * 4 + b < rem);
+                for (int b = 0; b < 8; ++b) {
+                    C::template step<true, true>(al, dict, dexp, ptab, pexp, w[b], L, buf, tscale, b < rem);
                     buf ^= 1;
                 }
-                if (wi & 1) zip_rescale<C>(al, scale, dead, isnan);
+            }
+            zip_rescale<C, true>(al, scale, dead, isnan);
+        } else {
+            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            if (__all_sync(0xffffffffu, rem >= 16)) {
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t wv = w[wi];
+                    if constexpr (C::GROUP4) {
+                        const uint32_t w4[4] = {wv & 0xffu, (wv >> 8) & 0xffu, (wv >> 16) & 0xffu, wv >> 24};
+                        C::template word4<false>(al, dict, dexp, ptab, pexp, w4, L, buf, tscale);
+                    } else {
+#pragma unroll C::UNROLL
+                        for (int b = 0; b < 4; ++b) {
+                            C::template step<false, false>(al, dict, dexp, ptab, pexp, wv & 0xffu, L, buf, tscale, true);
+                            wv >>= 8;
+                            buf ^= 1;
+                        }
+                    }
+                    if (wi & 1) zip_rescale<C, false>(al, scale, dead, isnan);
+                }
+            } else {
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t wv = w[wi];
+#pragma unroll 1
+                    for (int b = 0; b < 4; ++b) {
+                        C::template step<true, false>(al, dict, dexp, ptab, pexp, wv & 0xffu, L, buf, tscale, wi * 4 + b < rem);
+                        wv >>= 8;
+                        buf ^= 1;
+                    }
+                    if (wi & 1) zip_rescale<C, false>(al, scale, dead, isnan);
+                }
             }
         }
         cur = nxt;
+        cur2 = nxt2;
     }
     if constexpr (C::GROUP4) {      // add the four lane pairs' partial sums (lanes q and q^1 hold the same value)
         tscale += __shfl_xor_sync(0xffffffffu, tscale, 2);
@@ -548,10 +668,13 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
         }
         return;
     }
-    double sum = 0.0;
+    double sum = 0.0, mag = 0.0;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) sum += al[k];
-    const bool bad = isnan || sum != sum;
+    for (int k = 0; k < KP; ++k) {
+        if (SPEC) { sum = fma(spi[C::state_of(L, k)], al[k], sum); mag += fabs(al[k]); }      // sum(alpha) = wsum . beta
+        else sum += al[k];
+    }
+    const bool bad = isnan || sum != sum || (SPEC && mag != mag);
     if (a.vec_out) {       // segmented mode: hand the vector on (a dead chain hands on zeros; a unit-vector chain may
         if (have && L.writer()) {                 // legitimately end at zero, which is not an error by itself)
             double* out = a.vec_out + ((size_t)n * a.nchunks + ch.out_index) * a.vec_stride;
@@ -570,28 +693,32 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
     if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
 }
 
-// Persistent CTAs.  Work unit = (parameter point, warp-load of C::CPW chunks); point_next[n] counts the units of
-// point n already claimed (zeroed before the launch).  A CTA first serves the points blockIdx.x, blockIdx.x +
-// gridDim.x, ... (building each point's dictionary once and letting its warps claim units), then helps whichever
-// point still has unclaimed units, so that the SMs finish together no matter how points and chunks divide among them.
-template <class C, int THREADS, int MINB>
+// Persistent CTAs.  Work unit = (parameter point, warp-load of C::CPW chunks); point_next[i] counts the units of
+// the i-th point of the launch already claimed (zeroed before the launch).  A CTA first serves the points blockIdx.x,
+// blockIdx.x + gridDim.x, ... (building each point's dictionary once and letting its warps claim units), then helps
+// whichever point still has unclaimed units, so that the SMs finish together no matter how points and chunks divide
+// among them.
+template <class C, int THREADS, int MINB, bool SPEC>
 __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     constexpr int KP = C::KP;
     extern __shared__ __align__(128) unsigned char zsm_raw[];
     double* dict = reinterpret_cast<double*>(zsm_raw);
     const int M = a.M, S = a.S;
-    double* sE = dict + (size_t)M * C::STRIDE_D;      // [K][S]
-    double* spi = sE + ZipSmem<C>::se_doubles(S);     // [KP]
+    double* sE = dict + (size_t)M * C::STRIDE_D;      // plain: E[K][S];  spectral: b0[S][KP]
+    double* spi = sE + ZipSmem<C, SPEC>::se_doubles(S);     // [KP] pi / wsum
     double* sbuf = spi + KP;                          // [THREADS/32][SBUF_PER_WARP]
-    long long* dexp = reinterpret_cast<long long*>(sbuf + (THREADS / 32) * C::SBUF_PER_WARP);   // [M] (64-bit: an entry can span millions of sites)
-    int* s_point = reinterpret_cast<int*>(dexp + M);
+    double* ptab = sbuf + (THREADS / 32) * C::SBUF_PER_WARP;            // spectral: [RUN_ROWS][KP]
+    long long* dexp = reinterpret_cast<long long*>(ptab + ZipSmem<C, SPEC>::tab_doubles());   // [M] (64-bit: an entry can span millions of sites)
+    int* pexp = reinterpret_cast<int*>(dexp + M);     // spectral: [RUN_ROWS]
+    int* s_point = pexp + (SPEC ? RUN_ROWS : 0);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const typename C::Lane L(lane, warp, sbuf);
     for (int x = tid; x < (THREADS / 32) * C::SBUF_PER_WARP; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
+    const int NP = a.pcount ? *a.pcount : a.N;         // points served by this launch
     const int nunits = (a.nchunks + C::CPW - 1) / C::CPW * (a.nseg > 1 ? a.nseg : 1);
     int primary = blockIdx.x;          // next point of this CTA's own share
-    int scan = (int)(((long long)blockIdx.x * 7919) % a.N);   // where the search for points to help starts
+    int scan = NP > 0 ? (int)(((long long)blockIdx.x * 7919) % NP) : 0;   // where the search for points to help starts
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_point + 2);
     for (;;) {
         // ---- choose a point: own share first, then the point with the MOST unclaimed warp-loads (ties: the first one
@@ -599,31 +726,207 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
         // -2 = own point already finished by helpers.  All decisions go through shared memory so that they are uniform
         // over the CTA.
         __syncthreads();               // everybody is done with the previous point's dictionary and s_point[0]
-        if (primary < a.N) {
+        if (primary < NP) {
             if (tid == 0) s_point[0] = *((volatile int*)(a.point_next + primary)) < nunits ? primary : -2;
             primary += gridDim.x;
         } else {
             if (tid == 0) { s_point[0] = -1; *s_best = 0ull; }
             __syncthreads();
-            for (int idx = tid; idx < a.N; idx += THREADS) {
-                const int left = nunits - *((volatile int*)(a.point_next + (scan + idx) % a.N));
+            for (int idx = tid; idx < NP; idx += THREADS) {
+                const int left = nunits - *((volatile int*)(a.point_next + (scan + idx) % NP));
                 if (left > 0) atomicMax(s_best, ((unsigned long long)left << 32) | (0xffffffffu - (unsigned)idx));
             }
             __syncthreads();
-            if (tid == 0 && *s_best != 0ull) s_point[0] = (scan + (int)(0xffffffffu - (unsigned)(*s_best & 0xffffffffull))) % a.N;
+            if (tid == 0 && *s_best != 0ull) s_point[0] = (scan + (int)(0xffffffffu - (unsigned)(*s_best & 0xffffffffull))) % NP;
         }
         __syncthreads();
-        const int n = s_point[0];
-        if (n == -1) break;
-        if (n == -2) continue;
-        zip_build_dictionary<C, THREADS>(a, n, dict, sE, spi, dexp);
+        const int slot = s_point[0];
+        if (slot == -1) break;
+        if (slot == -2) continue;
+        const int n = a.plist ? a.plist[slot] : slot;
+        zip_build_dictionary<C, THREADS, SPEC>(a, n, dict, sE, spi, dexp, ptab, pexp);
         for (; warp < a.active_warps;) {
             int unit = 0;
-            if (lane == 0) unit = atomicAdd(a.point_next + n, 1);
+            if (lane == 0) unit = atomicAdd(a.point_next + slot, 1);
             unit = __shfl_sync(0xffffffffu, unit, 0);
             if (unit >= nunits) break;
-            zip_run_unit<C>(a, n, unit, dict, sE, spi, dexp, L);
+            zip_run_unit<C, SPEC>(a, n, unit, dict, sE, spi, dexp, ptab, pexp, L);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spectral preparation, one CTA per parameter point.  With r the run symbol, J = diag(pi) T symmetric (every model
+// of the reference builds T from a symmetric joint matrix, transitions.py:231-246) and w = sqrt(E[:,r] o pi):
+//     C_r = diag(E[:,r]) T^T = W A W^-1,   A[i][j] = sqrt(E[i,r] E[j,r]) J[i][j] / sqrt(pi_i pi_j)   symmetric,
+//     A = Q Lambda Q^T  (cyclic Jacobi, K <= 64),   V = W Q,  V^-1 = Q^T W^-1,
+//     C_s = diag(E[:,s] / E[:,r]) C_r   =>   R_s = V^-1 C_s V = (Q^T diag(E[:,s]/E[:,r]) Q) Lambda,   R_r = Lambda.
+// Written per point (spec_stride doubles): lambda[K], wsum[K] = V^T 1 = Q^T w, b0[S][K] = V^-1 (pi o E[:,s]), R[S][K][K].
+// A point is served by the spectral kernel only if all of this is sound: pi, E[:,r] > 0, J symmetric to 1e-13, Jacobi
+// converged, lambda_max > 0; such points are appended to ok_list, the others to bad_list (plain form of the kernel).
+// ------------------------------------------------------------------------------------------------
+struct ZipSpecArgs {
+    int N, K, S, run_sym;
+    const double* pi; const double* T; const double* E;
+    double* spec; int spec_stride;
+    int* ok_list; int* bad_list;
+    int* counts;            // [2]: points in ok_list, bad_list (zeroed before the launch)
+    int force_bad;          // experiment switch: send every point to the plain form
+    int point_base;         // index of this launch's first point in the caller's batch (the lists hold batch indices)
+};
+
+constexpr int SPEC_THREADS = 128;
+static inline size_t zip_spec_smem(int K) { return sizeof(double) * ((size_t)2 * K * (K + 1) + 6 * (size_t)K + 8) + sizeof(int) * 4; }
+
+__global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs s) {
+    extern __shared__ __align__(16) unsigned char spsm_raw[];
+    const int K = s.K, S = s.S, LD = K + 1, tid = threadIdx.x, n = blockIdx.x;
+    double* A = reinterpret_cast<double*>(spsm_raw);     // [K][LD]
+    double* Q = A + (size_t)K * LD;                      // [K][LD]
+    double* w = Q + (size_t)K * LD;                      // [K]
+    double* rot = w + K;                                 // [K/2+1][2] cosine, sine of the round's rotations
+    double* dsc = rot + 2 * (K / 2 + 1);                 // [K] E[:,s] / E[:,r]
+    double* red = dsc + K;                               // [4] reductions
+    int* flag = reinterpret_cast<int*>(red + 4 + 2 * K); // [2]
+    const double* Tg = s.T + (size_t)n * K * K;
+    const double* Eg = s.E + (size_t)n * K * S;
+    const double* pig = s.pi + (size_t)n * K;
+    double* out = s.spec + (size_t)n * s.spec_stride;
+    const int r = s.run_sym;
+    if (tid == 0) { flag[0] = s.force_bad ? 0 : 1; flag[1] = 0; red[0] = 0.0; red[1] = 0.0; }
+    __syncthreads();
+    for (int i = tid; i < K; i += SPEC_THREADS) {
+        const double v = pig[i] * Eg[i * S + r];
+        if (!(v > 0.0) || !(v < 1.7e308) || !(pig[i] > 0.0)) flag[0] = 0;
+        w[i] = sqrt(v);
+    }
+    __syncthreads();
+    // A and its asymmetry
+    double amax = 0.0, asym = 0.0;
+    for (int x = tid; x < K * K; x += SPEC_THREADS) {
+        const int i = x / K, j = x - i * K;
+        const double gi = Eg[i * S + r] / w[i], gj = Eg[j * S + r] / w[j];          // sqrt(E_i / pi_i)
+        const double aij = gi * gj * (pig[i] * Tg[i * K + j]), aji = gi * gj * (pig[j] * Tg[j * K + i]);
+        A[i * LD + j] = 0.5 * (aij + aji);
+        Q[i * LD + j] = i == j ? 1.0 : 0.0;
+        amax = fmax(amax, fabs(aij));
+        asym = fmax(asym, fabs(aij - aji));
+        if (!(fabs(aij) < 1.7e308)) flag[0] = 0;
+    }
+    for (int m = 16; m >= 1; m >>= 1) { amax = fmax(amax, shfl_xor_f64(amax, m)); asym = fmax(asym, shfl_xor_f64(asym, m)); }
+    if ((tid & 31) == 0) {
+        atomicMax(reinterpret_cast<unsigned long long*>(red), (unsigned long long)__double_as_longlong(amax));     // non-negative doubles order like integers
+        atomicMax(reinterpret_cast<unsigned long long*>(red + 1), (unsigned long long)__double_as_longlong(asym));
+    }
+    __syncthreads();
+    if (tid == 0 && !(red[1] <= 1e-13 * red[0])) flag[0] = 0;
+    __syncthreads();
+    if (flag[0]) {
+        // ---- cyclic Jacobi with the round-robin ordering: m - 1 rounds of m / 2 disjoint rotations per sweep
+        const int m = (K + 1) & ~1, half = m / 2;
+        const double tiny = 1e-300;
+        for (int sweep = 0; sweep < 30; ++sweep) {
+            double off = 0.0;
+            for (int x = tid; x < K * K; x += SPEC_THREADS) { const int i = x / K, j = x - i * K; if (i != j) off = fmax(off, fabs(A[i * LD + j])); }
+            for (int mm = 16; mm >= 1; mm >>= 1) off = fmax(off, shfl_xor_f64(off, mm));
+            if (tid == 0) red[2] = 0.0;
+            __syncthreads();
+            if ((tid & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(red + 2), (unsigned long long)__double_as_longlong(off));
+            __syncthreads();
+            if (red[2] <= 1e-18 * red[0]) { if (tid == 0) flag[1] = 1; break; }
+            for (int round = 0; round < m - 1; ++round) {
+                // pair x of this round: (m-1, round) for x == 0, else ((round + x) mod (m-1), (round - x) mod (m-1))
+                if (tid < half) {
+                    int p = tid == 0 ? m - 1 : (round + tid) % (m - 1), q = tid == 0 ? round : (round - tid + (m - 1)) % (m - 1);
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    double c = 1.0, sn = 0.0;
+                    if (q < K) {
+                        const double apq = A[p * LD + q], app = A[p * LD + p], aqq = A[q * LD + q];
+                        if (fabs(apq) > tiny) {
+                            const double th = (aqq - app) / (2.0 * apq);
+                            const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                            c = 1.0 / sqrt(t * t + 1.0);
+                            sn = t * c;
+                        }
+                    }
+                    rot[2 * tid] = c; rot[2 * tid + 1] = sn;
+                }
+                __syncthreads();
+                for (int x = tid; x < half * K; x += SPEC_THREADS) {          // rows: A <- J^T A
+                    const int pr = x / K, j = x - pr * K;
+                    int p = pr == 0 ? m - 1 : (round + pr) % (m - 1), q = pr == 0 ? round : (round - pr + (m - 1)) % (m - 1);
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    if (q >= K) continue;
+                    const double c = rot[2 * pr], sn = rot[2 * pr + 1];
+                    const double ap = A[p * LD + j], aq = A[q * LD + j];
+                    A[p * LD + j] = c * ap - sn * aq;
+                    A[q * LD + j] = sn * ap + c * aq;
+                }
+                __syncthreads();
+                for (int x = tid; x < half * K; x += SPEC_THREADS) {          // columns: A <- A J, Q <- Q J
+                    const int pr = x / K, i = x - pr * K;
+                    int p = pr == 0 ? m - 1 : (round + pr) % (m - 1), q = pr == 0 ? round : (round - pr + (m - 1)) % (m - 1);
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    if (q >= K) continue;
+                    const double c = rot[2 * pr], sn = rot[2 * pr + 1];
+                    const double ap = A[i * LD + p], aq = A[i * LD + q];
+                    double np = c * ap - sn * aq, nq = sn * ap + c * aq;
+                    if (sn != 0.0) { if (i == p) nq = 0.0; if (i == q) np = 0.0; }     // the annihilated pair, exactly
+                    A[i * LD + p] = np;
+                    A[i * LD + q] = nq;
+                    const double vp = Q[i * LD + p], vq = Q[i * LD + q];
+                    Q[i * LD + p] = c * vp - sn * vq;
+                    Q[i * LD + q] = sn * vp + c * vq;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double lmax = 0.0, lpos = 0.0;
+            for (int k = 0; k < K; ++k) { lmax = fmax(lmax, fabs(A[k * LD + k])); lpos = fmax(lpos, A[k * LD + k]); }
+            if (!flag[1] || !(lmax > 0.0) || !(lpos >= lmax) || !(lmax < 1.7e308)) flag[0] = 0;     // the dominant eigenvalue must be the positive one
+        }
+        __syncthreads();
+    }
+    if (flag[0]) {
+        double* lam = out;
+        double* wsum = out + K;
+        double* b0 = out + 2 * K;
+        double* R = out + 2 * K + (size_t)S * K;
+        for (int k = tid; k < K; k += SPEC_THREADS) {
+            lam[k] = A[k * LD + k];
+            double acc = 0.0;
+            for (int i = 0; i < K; ++i) acc = fma(Q[i * LD + k], w[i], acc);
+            wsum[k] = acc;
+        }
+        for (int x = tid; x < S * K; x += SPEC_THREADS) {
+            const int sy = x / K, k = x - sy * K;
+            double acc = 0.0;
+            for (int i = 0; i < K; ++i) acc = fma(Q[i * LD + k], pig[i] * Eg[i * S + sy] / w[i], acc);
+            b0[x] = acc;
+        }
+        for (int sy = 0; sy < S; ++sy) {
+            __syncthreads();
+            for (int i = tid; i < K; i += SPEC_THREADS) dsc[i] = Eg[i * S + sy] / Eg[i * S + r];
+            __syncthreads();
+            double* Rs = R + (size_t)sy * K * K;
+            for (int x = tid; x < K * K; x += SPEC_THREADS) {
+                const int i = x / K, j = x - i * K;
+                double v;
+                if (sy == r) v = i == j ? A[i * LD + i] : 0.0;
+                else {
+                    double acc = 0.0;
+                    for (int k = 0; k < K; ++k) acc = fma(Q[k * LD + i] * dsc[k], Q[k * LD + j], acc);
+                    v = acc * A[j * LD + j];
+                }
+                Rs[x] = v;
+            }
+        }
+    }
+    if (tid == 0) {
+        if (flag[0]) s.ok_list[atomicAdd(s.counts, 1)] = s.point_base + n;
+        else s.bad_list[atomicAdd(s.counts + 1, 1)] = s.point_base + n;
     }
 }
 
@@ -637,12 +940,17 @@ struct ZipFoldItem {
     int src, dst;        // src: 0 = vec (kernel output), 1 = vec2 (level-1 output)
 };
 
+// Spectral form (spec != NULL): the vectors are coordinates in the eigenbasis of C_r -- entries of either sign, measured
+// by their largest magnitude, and sum(alpha) = wsum . beta at the end.  plist / pcount: the points of this launch
+// (list_base + blockIdx.y indexes the list), as in zip_forward_kernel; without a list blockIdx.y is the point.
 __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nvec, double* vec2, int nvec2, int vec_stride,
-                                                      const ZipFoldItem* items, int K, double* chain_out, int out_stride) {
+                                                      const ZipFoldItem* items, int K, double* chain_out, int out_stride,
+                                                      const double* spec, int spec_stride, const int* plist, const int* pcount, int list_base) {
     __shared__ double w[64];
     __shared__ double red[2];
     __shared__ int s_e[2];
-    const int n = blockIdx.y, j = threadIdx.x;
+    if (pcount && list_base + (int)blockIdx.y >= *pcount) return;
+    const int n = plist ? plist[list_base + blockIdx.y] : blockIdx.y, j = threadIdx.x;
     const ZipFoldItem it = items[blockIdx.x];
     const double* base = it.src == 0 ? vec + (size_t)n * nvec * vec_stride : vec2 + (size_t)n * nvec2 * vec_stride;
     const double* v0 = base + (size_t)it.start * vec_stride;
@@ -669,12 +977,12 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
         double acc = 0.0;
         if (j < K)
             for (int c = 0; c < K; ++c) acc = fma(w[c], cols[(size_t)c * vec_stride + j], acc);
-        double sum = acc;
-        for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
+        double sum = spec ? fabs(acc) : acc;
+        for (int m = 16; m >= 1; m >>= 1) sum = spec ? fmax(sum, shfl_xor_f64(sum, m)) : sum + shfl_xor_f64(sum, m);
         __syncthreads();                               // w and s_e are free again
         if ((j & 31) == 0) red[j >> 5] = sum;
         __syncthreads();
-        sum = red[0] + red[1];
+        sum = spec ? fmax(red[0], red[1]) : red[0] + red[1];
         int en = 0;
         if (sum > 0.0 && sum < 1.7e308) { en = exponent_of(sum); acc *= pow2_neg(en); }
         alpha = acc;
@@ -687,7 +995,7 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
         if (j == 0) out[K] = scale;
         return;
     }
-    double sum = alpha;
+    double sum = spec ? (j < K ? spec[(size_t)n * spec_stride + K + j] * alpha : 0.0) : alpha;
     for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
     if ((j & 31) == 0) red[j >> 5] = sum;
     __syncthreads();

@@ -164,6 +164,47 @@ class ForwarderSet(object):
                                             ctypes.byref(n)))
         return out
 
+    # -- run tokens (spectral form of the compressed kernel; include/imcoalhmm_b200.h) ---------------------------
+    def run_info(self, K=None):
+        """dict(run_sym, ids_available; with K: ids_used, tokens, levels for a K-state model)."""
+        lib = _lib.load()
+        sym, avail, used, lev, tok = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        if K is None:
+            check(lib.imc_seqset_run_info(self._handle, 0, ctypes.byref(sym), ctypes.byref(avail), None, None, None))
+            return {"run_sym": sym.value, "ids_available": avail.value}
+        check(lib.imc_seqset_run_info(self._handle, int(K), ctypes.byref(sym), ctypes.byref(avail), ctypes.byref(used),
+                                      ctypes.byref(tok), ctypes.byref(lev)))
+        return {"run_sym": sym.value, "ids_available": avail.value, "ids_used": used.value, "tokens": tok.value,
+                "levels": lev.value}
+
+    def run_pairs(self):
+        """[P,2] (uint8): row i = (left, right) of run-dictionary id NSYM + i, creation order."""
+        n = self.run_info()["ids_available"] - (self.forwarders[0].NSYM if self.forwarders else 0)
+        out = np.zeros((max(n, 0), 2), dtype=np.uint8)
+        if n > 0:
+            check(_lib.load().imc_seqset_run_pairs(self._handle, out.ctypes.data_as(_lib.c_u8p), n))
+        return out
+
+    def run_tokens(self, chunk, ids=None):
+        """(first_run, words uint32[ntok]) of chunk `chunk` over the first `ids` run-dictionary ids (default: all);
+        word = id | run << 8."""
+        lib = _lib.load()
+        if ids is None:
+            ids = self.run_info()["ids_available"]
+        n, fr = ctypes.c_int64(), ctypes.c_int()
+        check(lib.imc_seqset_run_tokens(self._handle, int(chunk), int(ids), None, 0, ctypes.byref(n), ctypes.byref(fr)))
+        out = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            check(lib.imc_seqset_run_tokens(self._handle, int(chunk), int(ids), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                            out.size, ctypes.byref(n), ctypes.byref(fr)))
+        return fr.value, out
+
+    def spectral_counts(self):
+        """(points served by the spectral form, points served by the plain form) in the last spectral forward call."""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(_lib.load().imc_seqset_spectral_counts(self._handle, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def forward_batch_device(self, d_pi, d_T, d_E, d_out, N, K, S, stream=0):
         """Device-resident variant: arguments are raw device pointers (ints); enqueued on `stream`."""
         check(_lib.load().imc_forward_batch_dev(self._handle, int(N), int(K), int(S), int(d_pi), int(d_T), int(d_E),

@@ -98,6 +98,19 @@ int imc_seqset_zip_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs
  * out may be NULL to query the length. */
 int imc_seqset_zip_tokens(imc_seqset* set, int chunk, int ids, uint8_t* out, int64_t capacity, int64_t* ntokens);
 
+/* Run tokens: the second re-encoding of the set, used by the spectral form of the compressed kernel.  The most frequent
+ * symbol r of the set ("run symbol") leaves the dictionary: a chunk (positions 1..L-1) is first_run sites of r followed by
+ * tokens  word = id | n << 8  = "dictionary entry id, then n sites of r" (n <= 4095; longer runs continue with entries whose
+ * id is r itself).  Pairs are learned over the entries (left part without a run).  In the eigenbasis of
+ * C_r = diag(E[:,r]) T^T a run of any length is a diagonal matrix, so a token costs one mat-vec however long its run --
+ * exact like the pair dictionary (hmm.py:16,20-21 compute the same likelihood).  Same conventions as the zip_* calls above. */
+int imc_seqset_run_info(imc_seqset* set, int K, int* run_sym, int* ids_available, int* ids_used, int64_t* tokens, int* levels);
+int imc_seqset_run_pairs(imc_seqset* set, uint8_t* pairs_out, int capacity_pairs);
+int imc_seqset_run_tokens(imc_seqset* set, int chunk, int ids, uint32_t* out, int64_t capacity, int64_t* ntokens, int* first_run);
+/* how the last spectral forward call on this set split its parameter points: served by the spectral form / by the plain
+ * form (synchronises the device; for tests).  Both 0 if no spectral call was made yet. */
+int imc_seqset_spectral_counts(imc_seqset* set, int* ok_points, int* plain_points);
+
 /* ---- forward log-likelihood ------------------------------------------------------------------------ */
 /* logL_out[0] = sum over the set's chunks of log P(chunk | pi, T, E).  Replaces
  * sum(f.forward(pi, T, E) for f in forwarders)  (hmm.py:19-21, likelihood.py:33). */
@@ -185,6 +198,12 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       in this many pieces that are separate, ordered work units (a piece starts from the state its
  *                       predecessor left in global memory), so that the SMs finish together; bit-identical results.
  *                       0 = auto (about 40 units per warp), 1 = off, 2..32 = forced.
+ * key "zip_spectral":   spectral form of the zip kernel (run tokens, see imc_seqset_run_info): per parameter point C_r is
+ *                       diagonalised on the device (symmetric Jacobi; needs pi, E[:,r] > 0 and diag(pi) T symmetric, which
+ *                       every model of the reference guarantees, transitions.py:231-246); points that do not qualify are
+ *                       served by the plain form in the same call.  0 = auto (where run tokens are >= 15 % fewer than
+ *                       dictionary tokens), 1 = always, 2 = never.
+ * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).
  * key "comm_fused", "comm_enabled": see the multi-GPU section above.
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
@@ -197,7 +216,8 @@ int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t imc_kernel_launches(void);
 /* name of the forward kernel chosen by the last forward call on this thread
- * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls) */
+ * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls;
+ * "zip-spectral", "zip-spectral-segmented", "zip-spectral-warp": the same three shapes over run tokens) */
 const char* imc_last_forward_kernel(void);
 
 #ifdef __cplusplus

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0)
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces]")
+    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off]]")
     ap.add_argument("--plain", action="store_true", help="also time the uncompressed kernel")
     ap.add_argument("--check", type=int, default=2, help="chunks to check against the oracle")
     args = ap.parse_args()
@@ -60,7 +60,7 @@ def main():
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) * 1e-3)
         sp = fset.total_sites * N
-        print("%-34s kernel=%-5s %9.3f ms  %.3e site-pts/s  logL[0]=%.6f" %
+        print("%-60s kernel=%-14s %9.3f ms  %.3e site-pts/s  logL[0]=%.6f" %
               (label, m.last_forward_kernel(), best * 1e3, sp / best, d_out[0].item()), flush=True)
         return d_out.cpu().numpy().copy()
 
@@ -69,7 +69,9 @@ def main():
         f = list(map(int, spec.split(":")))
         ctas, cap, lanes = f[:3]
         pipe = f[3] if len(f) > 3 else 0
+        spec = f[4] if len(f) > 4 else 0
         m.set_option("zip_pipeline", pipe)
+        m.set_option("zip_spectral", spec)
         m.set_option("forward_kernel", 4)
         m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)
@@ -77,7 +79,9 @@ def main():
         info = fset.zip_info(K)
         m.set_option("zip_ctas_per_sm", ctas)   # zip_info reports the plan in effect
         info = fset.zip_info(K)
-        out = timed("zip lanes=%d ctas=%d cap=%d pipe=%d M=%d tok=%d" % (lanes, ctas, cap, pipe, info["ids_used"], info["tokens"]))
+        rinfo = fset.run_info(K)
+        out = timed("zip lanes=%d ctas=%d cap=%d pipe=%d spec=%d M=%d/%d tok=%d/%d" % (lanes, ctas, cap, pipe, spec, info["ids_used"],
+                    rinfo["ids_used"], info["tokens"], rinfo["tokens"]))
         if ref is None:
             ref = out
         else:

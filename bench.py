@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- forward sites x parameter-points / second on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2_small|c3_1gpu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3_1gpu|ns_1gpu|c5_1gpu|c1|...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one batched log-likelihood evaluation: N_theta parameter points scored on every alignment
 chunk of the (per-rank) shard, logL[N_theta] out.  Rank 0 prints ONE JSON line.
 
-  value      device-timed (CUDA events on the launching stream, max over ranks) with the packed sequences and
+  value      device-timed (CUDA events on the launching stream, max over ranks) with the token streams and
              the parameter batch resident in HBM; an L2 flush (256 MiB write) separates timed steps.
   e2e        the same metric through the public host API (Model.batched_log_likelihood -> imc_loglik_batch):
              theta[N,P] copied from pinned host memory, logL[N] + status[N] copied back, every step, wall clock
              around the calls.  The sequences stay resident (uploaded once when the Forwarders are built, exactly
              like the reference preprocesses once in Forwarder.__init__, hmm.py:12-16).
   roofline   dominant kernel (zip_forward_kernel) against the pipe that bounds it, the shared-memory pipe: achieved =
-             tokens*points*8K^2 bytes / kernel time, peak = 128 B/clk/SM.  The SURVEY 8(d) view (plain-forward flops
-             sites*points*(2K^2+3K) / kernel time against the FP64 peak MEASURED IN THIS RUN) sits beside it under
-             "plain_forward_equivalent"; for the per-site kernels (--forward-kernel 2|3) it is the roofline itself.
-  cpu_baseline  the CPU oracle's zipHMM-style forward (oracle/forward_oracle.c, OpenMP over all host cores) on a
-             bounded sample of the same workload -- a reported baseline, not the target.
+             chain-steps * 8K^2 bytes / kernel time (chain-steps = tokens of the form that ran x points), peak =
+             128 B/clk/SM.  The SURVEY 8(d) view (plain-forward flops sites*points*(2K^2+3K) / kernel time against
+             the FP64 peak MEASURED IN THIS RUN) sits beside it under "plain_forward_equivalent".
+  parity     EVERY output of the timed launch (all points, all chunks of the shard) against the CPU oracle's
+             zipHMM-style forward (oracle/forward_oracle.c, float64); the first 16 points use the (pi,T,E) the
+             REFERENCE's own build_hidden_markov_model produced (tests/golden), the others the GPU model build.
+  secondary  (default run on one GPU only) the same measurement + parity for the shapes the north star names:
+             c3_1gpu (IM model K=20 shard of configs[2]), ns_1gpu (north-star shard), c5_1gpu (K=40 shard), and the
+             drop-in latency of ONE Likelihood(theta) call on the reference's example alignment (c1).
+  cpu_baseline  the CPU oracle's zipHMM-style forward (OpenMP over all host cores) on a bounded sample of the same
+             workload -- a reported baseline, not the target.
 """
 import argparse
 import json
@@ -61,7 +67,14 @@ WORKLOADS = {
                     default=[1e-3] + [1000.0] * 10 + [0.4], K=40, chunks=375, chunk_len=1_000_000, points=1024,
                     desc="configs[4] per-GPU shard: psmc-style isolation model K=40 (10 epochs x 4), 375 x 1 Mbp chunks, "
                          "1024 parameter points"),
+    # BASELINE.json configs[0]: isolation-model.py on examples/example_data.fa (hg18 vs pantro2, 65 255 sites), ONE
+    # Likelihood(theta) call at a time -- the latency a drop-in user of the scripts sees (scripts/isolation-model.py:82-100)
+    "c1": dict(model="isolation_k10", ctor=("IsolationModel", (10,)), default=[1e-3, 2000.0, 0.4], K=10,
+               chunks=1, chunk_len=65255, points=1,
+               desc="configs[0]: isolation model K=10 on the reference's example alignment (hg18 vs pantro2, 65 255 sites), "
+                    "one Likelihood(theta) call at a time"),
 }
+SECONDARY = ("c3_1gpu", "ns_1gpu", "c5_1gpu")
 
 
 def thetas_around(default, n, seed=7, scale=0.1):
@@ -75,6 +88,13 @@ def thetas_around(default, n, seed=7, scale=0.1):
 
 def flops_per_site_point(K):
     return 2 * K * K + 3 * K
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ---------------------------------------------------------------------------------------- synthetic data
@@ -113,9 +133,9 @@ def simulate_chunk(rng, pi, T, E, L, missing=0.04, mean_run=100):
 
 
 def load_points(model, n_points):
-    """(pi, T, E) for the CPU reference arm only: the committed reference-derived fixture
-    tests/golden/model_<name>.npz (16 points theta_b = default * exp(0.1 N(0,1)), built by the reference's own
-    build_hidden_markov_model) tiled to n_points, so that arm touches none of this repository's kernels."""
+    """(pi, T, E) built by the REFERENCE's own build_hidden_markov_model: the committed fixture
+    tests/golden/model_<name>.npz (16 points theta_b = default * exp(0.1 N(0,1)) = the first 16 points of
+    thetas_around) tiled to n_points.  Used to simulate the alignments, by the CPU arm, and by the parity gate."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "model_%s.npz" % model))
     reps = (n_points + g["pi"].shape[0] - 1) // g["pi"].shape[0]
     pis = np.ascontiguousarray(np.tile(g["pi"], (reps, 1))[:n_points])
@@ -124,7 +144,43 @@ def load_points(model, n_points):
     return pis, Ts, Es
 
 
+def _sim_task(task):
+    model, chunk_len, cid = task
+    pis, Ts, Es = load_points(model, 1)
+    rng = np.random.Generator(np.random.PCG64(SEED0 + int(cid)))
+    return simulate_chunk(rng, pis[0], Ts[0], Es[0], chunk_len)
+
+
+class ChunkFactory(object):
+    """Synthetic alignment chunks, simulated from the reference-built model at the scripts' default parameters (point 0 of
+    the fixture), chunk c with PCG64(SEED0 + c).  A pool of forked workers (created before CUDA is touched) spreads the
+    simulation over the host cores: the K=40 workload alone is a minute of single-core Python otherwise."""
+
+    def __init__(self, nworkers):
+        self.pool = None
+        if nworkers > 1:
+            import multiprocessing as mp
+            try:
+                self.pool = mp.get_context("fork").Pool(nworkers)
+            except Exception:
+                self.pool = None
+
+    def make(self, wl, chunk_ids):
+        if wl.get("example"):
+            return [np.load(os.path.join(ROOT, "tests", "golden", "example_pair.npz"))["symbols"]]
+        tasks = [(wl["model"], wl["chunk_len"], int(c)) for c in chunk_ids]
+        if self.pool is not None and len(tasks) > 4:
+            return self.pool.map(_sim_task, tasks, chunksize=max(1, len(tasks) // 64))
+        return [_sim_task(t) for t in tasks]
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool = None
+
+
 def make_chunks(wl, pis, Ts, Es, chunk_ids):
+    """Kept for tools/: chunks simulated from the given point-0 model."""
     out = []
     for cid in chunk_ids:
         rng = np.random.Generator(np.random.PCG64(SEED0 + int(cid)))
@@ -199,28 +255,72 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-# ---------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
+# ---------------------------------------------------------------------------------------- CPU oracle legs
+def oracle_zip(chunks, max_syms=256):
+    """zipHMM-style preprocessing of every chunk with the oracle (hmm.py:16), spread over the host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import forward as F
+    F.build()
+    with ThreadPoolExecutor(max(1, min(32, host_cores()))) as ex:
+        return list(ex.map(lambda c: F.zip_preprocess(c.astype(np.int32), 3, max_syms=max_syms), chunks))
+
+
+def parity_check(chunks, logl, pis_ref, Ts_ref, Es_ref, pis_gpu, Ts_gpu, Es_gpu, kernel, budget_s, label_full):
+    """Every output of the timed launch against the oracle's zipHMM-style forward on the same chunks: the sum over ALL
+    chunks for every point, or -- when the CPU cannot do that inside budget_s -- for an evenly spaced subset of the
+    points (stated in `sample`).  Points < 16 use the reference-built (pi,T,E) of the fixture."""
+    from oracle import forward as F
+    N = logl.size
+    t0 = time.perf_counter()
+    zipped = oracle_zip(chunks, max_syms=128 if pis_gpu.shape[1] >= 32 else 256)
+    t_prep = time.perf_counter() - t0
+    nref = min(16, N, pis_ref.shape[0])
+    pis, Ts, Es = pis_gpu.copy(), Ts_gpu.copy(), Es_gpu.copy()
+    pis[:nref], Ts[:nref], Es[:nref] = pis_ref[:nref], Ts_ref[:nref], Es_ref[:nref]
+    # calibrate on 2 points, then as many evenly spaced points as the budget allows (always including the first 16)
+    t0 = time.perf_counter()
+    F.forward_batch(None, pis[:2], Ts[:2], Es[:2], mode="zip_fast", zipped=zipped, nthreads=host_cores())
+    per_point = max((time.perf_counter() - t0) / 2, 1e-6)
+    can = int(max(budget_s - t_prep, 1.0) / per_point)
+    if can >= N:
+        idx = np.arange(N)
+    else:
+        extra = max(0, can - nref)
+        idx = np.unique(np.concatenate([np.arange(nref), np.linspace(nref, N - 1, max(extra, 1)).astype(int)])) if N > nref else np.arange(nref)
+    t0 = time.perf_counter()
+    want, _ = F.forward_batch(None, pis[idx], Ts[idx], Es[idx], mode="zip_fast", zipped=zipped, nthreads=host_cores())
+    t_cpu = time.perf_counter() - t0
+    rel = np.abs(logl[idx] - want) / np.abs(want)
+    worst = int(idx[int(np.argmax(rel))])
+    sites = sum(len(c) for c in chunks)
+    return {"max_rel_err": float(rel.max()), "tolerance": 1e-9, "ok": bool(rel.max() <= 1e-9), "kernel": kernel,
+            "checked_outputs": int(idx.size), "outputs": int(N), "worst_point": worst,
+            "max_rel_err_reference_built_points": float(rel[:nref].max()) if nref else None,
+            "sample": ("full: " if idx.size == N else "subset: ") +
+                      "%d of the %d outputs of the timed launch (%s), each the sum over all %d chunks (%d sites), vs the oracle's "
+                      "zipHMM-style float64 forward; points 0..%d with the reference-built (pi,T,E) of tests/golden, the rest "
+                      "with the GPU-built ones" % (idx.size, N, label_full, len(chunks), sites, nref - 1),
+            "oracle_seconds": round(t_prep + t_cpu, 2)}
+
+
+def cpu_reference_run(wl, chunk_factory, steps, warmup, budget_s=12.0):
     """The reference's CPU path restated (oracle, zipHMM-style pair compression + forward, OpenMP over
     (point, chunk) tasks on all host cores).  Each step scores a bounded sample of the workload."""
     from oracle import forward as F
     F.build()
-    ncores = os.cpu_count() or 1
-    try:
-        ncores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    ncores = host_cores()
+    pis, Ts, Es = load_points(wl["model"], wl["points"])
     # bounded sample: n_c chunks x n_p points sized from a calibration run
     n_c = min(wl["chunks"], max(ncores, 8))
     n_p = min(wl["points"], 16)
-    chunks = make_chunks(wl, pis, Ts, Es, range(n_c))
+    chunks = chunk_factory.make(wl, range(n_c))
     # The dictionary size trades K^3 work per new symbol (rebuilt in every zip_forward call, hmm.py:20-21) against
     # K^2 work per remaining symbol; mini-ziphmm tunes it from its own cost estimate.  Give the CPU arm the best of a
     # small sweep so that it is not handicapped by our choice.
     best = None
     for max_syms in (64, 128, 256, 512, 1024):
         t0 = time.perf_counter()
-        z = [F.zip_preprocess(c.astype(np.int32), 3, max_syms=max_syms) for c in chunks]
+        z = oracle_zip(chunks, max_syms)
         tp = time.perf_counter() - t0
         t0 = time.perf_counter()
         F.forward_batch(None, pis[:n_p], Ts[:n_p], Es[:n_p], mode="zip_fast", zipped=z, nthreads=ncores)
@@ -251,8 +351,282 @@ def cpu_reference_run(wl, pis, Ts, Es, steps, warmup, budget_s=12.0):
             "sample": "%d chunks x %d bp x %d points per step, zipHMM-style compressed forward (imco_zip_forward_fast: "
                       "column-major matrices, power-of-two rescaling every 8 symbols; per-chunk dictionaries of "
                       "<= %d symbols, the fastest of 64..1024 on this host; %.0fx fewer symbols, preprocess %.1fs excluded "
-                      "like hmm.py:16), OpenMP, %d steps" % (n_c, wl["chunk_len"], n_p, max_syms, ratio, t_prep, len(times)),
+                      "like hmm.py:16), OpenMP, %d steps; (pi,T,E) from the committed fixture built by the reference's own "
+                      "build_hidden_markov_model" % (n_c, wl["chunk_len"], n_p, max_syms, ratio, t_prep, len(times)),
             "ms_per_step": 1e3 * t / len(times)}
+
+
+def base_config(wl):
+    """The same dict for both arms (the driver compares them)."""
+    return {"workload": wl["desc"], "chunks_per_gpu": wl["chunks"], "chunk_len": wl["chunk_len"],
+            "points": wl["points"], "K": wl["K"], "sharding": "chunks across ranks, no data-path collective except one "
+            "all-reduce of float64[points]", "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ---------------------------------------------------------------------------------------- one workload on the GPU
+class GpuCtx(object):
+    def __init__(self, m, torch, dist, dev, local_rank, rank, world, lib_comm, flush, peaks):
+        self.m, self.torch, self.dist, self.dev = m, torch, dist, dev
+        self.local_rank, self.rank, self.world, self.lib_comm = local_rank, rank, world, lib_comm
+        self.flush, self.peaks = flush, peaks
+
+
+def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0, parity_budget_s=20.0, e2e=True,
+                     parity=True, collective="fused"):
+    """Times one workload on this rank's GPU; returns (result dict for rank 0, extras)."""
+    m, torch, dist, dev = g.m, g.torch, g.dist, g.dev
+    K, N, S = wl["K"], wl["points"], 3
+    m.set_option("forward_kernel", forward_kernel)
+    model = getattr(m, wl["ctor"][0])(*wl["ctor"][1])
+    thetas = thetas_around(wl["default"], N)
+    # weak scaling: every rank owns wl["chunks"] chunks (distinct seeds), all ranks score the same points
+    chunks = chunk_factory.make(wl, range(g.rank * wl["chunks"], (g.rank + 1) * wl["chunks"]))
+    t0 = time.perf_counter()
+    fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
+    t_preprocess = time.perf_counter() - t0      # one-off, like Forwarder.__init__ (hmm.py:12-16); not in any timed region
+    sites_rank = fset.total_sites
+    pis, Ts, Es, st = model.build_hidden_markov_models(thetas)       # host copies for the kernel-only leg and the parity gate
+    assert (st == 0).all()
+    d_theta = torch.tensor(thetas, device=dev)
+    d_pi, d_T, d_E = (torch.tensor(x, device=dev) for x in (pis, Ts, Es))
+    d_out = torch.empty(N, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    reduce_torch = dist is not None and not g.lib_comm
+
+    def step():
+        # theta -> (pi,T,E) -> logL on the device: model-build kernels, (spectral preparation,) forward, chunk reduction
+        model.batched_log_likelihood_device(d_theta.data_ptr(), fset, d_out.data_ptr(), N, 0, stream.cuda_stream)
+        if reduce_torch:
+            dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods (lib_comm: done inside the call)
+
+    sampler = ClockSampler(g.local_rank)
+    sampler.start()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    launches0 = m.kernel_launches()
+    evs = []
+    for _ in range(steps):
+        g.flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step()
+        b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = m.kernel_launches() - launches0
+    kernel = m.last_forward_kernel()
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    if dist is not None:
+        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+    logl_dev = d_out.cpu().numpy().copy()        # the outputs of the LAST timed step: what the parity gate checks
+
+    # ---- N > 1: the fused all-reduce against torch.distributed on this run's own partial sums ----
+    collective_check = None
+    if dist is not None and g.lib_comm:
+        m.set_option("comm_enabled", 0)          # this rank's partial sums
+        part = torch.empty(N, dtype=torch.float64, device=dev)
+        model.batched_log_likelihood_device(d_theta.data_ptr(), fset, part.data_ptr(), N, 0, stream.cuda_stream)
+        torch.cuda.synchronize()
+        m.set_option("comm_enabled", 1)
+        gathered = [torch.empty_like(part) for _ in range(g.world)]
+        dist.all_gather(gathered, part)
+        ordered = torch.zeros_like(part)
+        for p in gathered:                       # rank order: the order reduce_chains_peer_kernel adds the rows in
+            ordered += p
+        nccl_sum = part.clone()
+        dist.all_reduce(nccl_sum)
+        fused = torch.tensor(logl_dev, device=dev)
+        collective_check = {"collective": collective, "fused_in_kernel": bool(m._lib.comm_info()["fused"]),
+                            "bit_equal_to_rank_ordered_sum": bool(torch.equal(fused, ordered)),
+                            "max_rel_diff_vs_torch_all_reduce": float(((fused - nccl_sum).abs() / nccl_sum.abs()).max().item()),
+                            "ranks": g.world}
+        ok = torch.tensor([1 if collective_check["bit_equal_to_rank_ordered_sum"] else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        collective_check["all_ranks_agree"] = bool(ok.item())
+
+    # ---- kernel-only time of the dominant kernel (forward kernel without model build / all-reduce) ----
+    kt = []
+    m.set_option("comm_enabled", 0)          # this rank's kernel alone
+    for _ in range(min(3, steps)):
+        g.flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fset.forward_batch_device(d_pi.data_ptr(), d_T.data_ptr(), d_E.data_ptr(), d_out.data_ptr(), N, K, S,
+                                  stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b) * 1e-3)
+    t_kernel = float(np.mean(kt))
+    m.set_option("comm_enabled", 1)
+
+    # ---- end to end through the host API (Model.batched_log_likelihood -> imc_loglik_batch): pinned host theta in,
+    # host logL + status out, every step; model build and forward on the device in between ----
+    t_e2e = None
+    if e2e:
+        h_theta = torch.tensor(thetas).pin_memory()
+        np_theta = h_theta.numpy()
+        for _ in range(2):
+            np_out = model.batched_log_likelihood(np_theta, fset)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            np_out = model.batched_log_likelihood(np_theta, fset)   # synchronous: returns with logL on the host
+            if reduce_torch:
+                tmp = torch.from_numpy(np_out).to(dev)
+                dist.all_reduce(tmp)
+                np_out[:] = tmp.cpu().numpy()
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt.item())
+        if g.world == 1:
+            assert np.allclose(np_out, logl_dev, rtol=1e-12), "host API and device API disagree"
+    if g.rank != 0:
+        return None
+
+    spectral = kernel.startswith("zip-spectral")
+    zinfo = fset.run_info(K) if spectral else fset.zip_info(K)
+    total_site_points = float(sites_rank) * N * g.world
+    peak_dfma, peak_dmma = g.peaks
+    peak = max(peak_dfma, peak_dmma)
+    algo_flops = float(sites_rank) * N * flops_per_site_point(K)          # per launch (one rank), SURVEY 8(d)
+    achieved = algo_flops / t_kernel / 1e12
+    kname = "imc::%s_kernel" % ("zip_forward" if kernel.startswith("zip") else "fwd_" + kernel)
+    fp64_view = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                 "peak_source": "measured in this run (imc_measure_fp64_peak): DFMA %.1f, DMMA %.1f TFLOP/s; "
+                 "MEASURED_PEAKS.json has no FP64 entry" % (peak_dfma, peak_dmma),
+                 "algorithmic_flop_per_site_point": flops_per_site_point(K)}
+    if kernel.startswith("zip"):
+        # The kernel runs the reference's own algorithm (zipHMM: one mat-vec per COMPRESSED symbol; in the spectral form one
+        # per non-run dictionary entry).  Its necessary work per launch is tokens x points chain-steps, each of which must
+        # stream one K x K dictionary matrix (8 K^2 bytes) out of shared memory for 2 K^2 flops: the pipe that bounds it is the
+        # shared-memory pipe (128 B/clk/SM nominal, 122 measured with full LDS.128, profiles/r01_smem_patterns.txt), not FP64
+        # and not HBM (ncu: ~1 MB of DRAM traffic per launch).
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        steps_exec = float(zinfo["tokens"]) * N
+        smem_peak = 128.0 * 148 * sm_clock / 1e9
+        smem_ach = steps_exec * 8.0 * K * K / t_kernel / 1e9
+        exec_tflops = steps_exec * (2 * K * K + K) / t_kernel / 1e12
+        roofline = {
+            "bound": "smem", "kernel": kname + (" (spectral form: run tokens)" if spectral else ""), "achieved": smem_ach,
+            "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak, "frac_of_measured_pipe": smem_ach / (smem_peak * 122.0 / 128.0),
+            "traffic": None, "kernel_ms": 1e3 * t_kernel,
+            "bound_note": "shared-memory pipe: every chain-step streams one K x K dictionary matrix from shared memory; "
+                          "achieved = tokens x points x 8 K^2 bytes / kernel time (the spectral form adds 16 K bytes of power-table "
+                          "rows per chain-step, not counted)",
+            "peak_source": "nominal 128 B/clk/SM x 148 SMs x %.0f MHz (median SM clock sampled during the timed region); "
+                           "frac_of_measured_pipe uses the 122 B/clk/SM a full LDS.128 stream reaches on this part" % (sm_clock / 1e6),
+            "algorithmic_bytes_per_chain_step": 8 * K * K, "chain_steps_per_launch": steps_exec,
+            "executed_tflops_fp64": exec_tflops, "executed_frac_of_fp64_peak": exec_tflops / peak,
+            "compression": {"sites": int(sites_rank), "tokens": int(zinfo["tokens"]), "ratio": sites_rank / max(1, zinfo["tokens"]),
+                            "form": "run tokens (spectral)" if spectral else "pair dictionary",
+                            "dictionary_ids_used": zinfo["ids_used"], "dictionary_ids_available": zinfo["ids_available"],
+                            "dictionary_levels": zinfo["levels"], "preprocess_s_one_off": t_preprocess},
+            "plain_forward_equivalent": fp64_view}
+    else:
+        roofline = dict(fp64_view, kernel=kname, traffic=None, kernel_ms=1e3 * t_kernel)
+    try:    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this workload and kernel form
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+        if tr and tr.get("kernel_form") == kernel and forward_kernel == 0:
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = "%s, ncu --set full: %s" % (tr["kernel"], tr["source"])
+    except (OSError, ValueError):
+        pass
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, ValueError, KeyError):
+        hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+    if roofline.get("traffic"):
+        ach = roofline["traffic"] / t_kernel / 1e9
+        roofline["hbm_view"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                "peak_source": hbm_src, "note": "not the bound: the working set lives in shared memory and registers"}
+    res = {"value": total_site_points * steps / t_dev, "unit": "sites*points/s", "ms_per_step": 1e3 * t_dev / steps,
+           "steps": steps, "warmup": warmup, "clocks": clocks, "gpu_launches": int(launches), "kernel": kernel,
+           "roofline": roofline,
+           "logL_check": {"first": float(logl_dev[0]), "finite": bool(np.isfinite(logl_dev).all())}}
+    if t_e2e is not None:
+        res["e2e"] = {"value": total_site_points * steps / t_e2e, "unit": "sites*points/s",
+                      "h2d_bytes_per_step": int(thetas.nbytes), "d2h_bytes_per_step": int(N * 8 + N * 4)}
+    if collective_check is not None:
+        res["collective_check"] = collective_check
+    if parity and g.world == 1:
+        pr, Tr, Er = load_points(wl["model"], min(16, N))
+        res["parity"] = parity_check(chunks, logl_dev, pr, Tr, Er, pis, Ts, Es, kernel, parity_budget_s,
+                                     "%d chunks x %d points" % (len(chunks), N))
+    elif parity:
+        # N > 1: the timed outputs are sums over all ranks' shards; rank 0 checks them against the collective check above
+        # and its own shard's partial sums against the oracle
+        m.set_option("comm_enabled", 0)
+        part = model.batched_log_likelihood(thetas, fset)
+        m.set_option("comm_enabled", 1)
+        pr, Tr, Er = load_points(wl["model"], min(16, N))
+        res["parity"] = parity_check(chunks, part, pr, Tr, Er, pis, Ts, Es, kernel, parity_budget_s,
+                                     "rank 0's partial sums, %d chunks x %d points" % (len(chunks), N))
+    return res
+
+
+def measure_latency(g, chunk_factory, calls=300):
+    """configs[0]: one Likelihood(theta) call at a time through the reference-facing Python API
+    (scripts/isolation-model.py:82-100), then a 200-evaluation Nelder-Mead run (likelihood.py:36-87)."""
+    m = g.m
+    wl = dict(WORKLOADS["c1"], example=True)
+    obs = chunk_factory.make(wl, [0])[0]
+    f = m.Forwarder.from_symbols(obs, 3)
+    model = m.IsolationModel(10)
+    like = m.Likelihood(model, [f])
+    theta = np.array(wl["default"])
+    for _ in range(5):
+        val = like(theta)
+    ts = []
+    rng = np.random.default_rng(1)
+    for _ in range(calls):
+        th = theta * np.exp(0.05 * rng.standard_normal(3))
+        t0 = time.perf_counter()
+        like(th)
+        ts.append(time.perf_counter() - t0)
+    kernel = m.last_forward_kernel()
+    ts = np.sort(np.asarray(ts)) * 1e3
+    evals = [0]
+
+    def counted(th):
+        evals[0] += 1
+        return like(th)
+    import scipy.optimize
+    t0 = time.perf_counter()
+    res = scipy.optimize.minimize(lambda p: -counted(np.asarray(p)), theta * 1.3, method="Nelder-Mead",
+                                  options={"maxfev": 200, "disp": False})
+    t_opt = time.perf_counter() - t0
+    # CPU: the oracle's zipHMM-style forward, one thread, the way the reference runs (one process per chain)
+    from oracle import forward as F
+    pis, Ts, Es = load_points(wl["model"], 1)
+    z = F.zip_preprocess(obs.astype(np.int32), 3, max_syms=256)
+    F.zip_forward_fast(pis[0], Ts[0], Es[0], z[1], z[0], 3, z[2])
+    t0 = time.perf_counter()
+    for _ in range(20):
+        want = F.zip_forward_fast(pis[0], Ts[0], Es[0], z[1], z[0], 3, z[2])
+    t_cpu = (time.perf_counter() - t0) / 20
+    return {"workload": wl["desc"], "calls": calls, "p50_ms": float(ts[len(ts) // 2]), "p99_ms": float(ts[int(len(ts) * 0.99)]),
+            "min_ms": float(ts[0]), "kernel": kernel, "api": "imcoalhmm_b200.Likelihood(IsolationModel(10), [Forwarder])(theta): "
+            "model build + forward fused on the device, host theta in, python float out",
+            "nelder_mead": {"evaluations": evals[0], "seconds": t_opt, "ms_per_evaluation": 1e3 * t_opt / max(1, evals[0]),
+                            "logL_at_optimum": float(-res.fun)},
+            "parity": {"logL": float(val), "oracle": float(want), "rel_err": float(abs(val - want) / abs(want)),
+                       "note": "theta = script defaults; oracle on the reference-built (pi,T,E) of tests/golden"},
+            "cpu_forward_only_ms_single_thread": 1e3 * t_cpu,
+            "cpu_note": "oracle zipHMM-style forward alone (no model build; the reference's Python build_hidden_markov_model "
+                        "adds 2.4 ms per call for this model, SURVEY 3.1)"}
 
 
 # ---------------------------------------------------------------------------------------- main
@@ -265,6 +639,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the default run")
+    ap.add_argument("--secondary-budget-s", type=float, default=110.0,
+                    help="CPU seconds the oracle may spend on the parity gates of the secondary workloads (all together)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl", "torch"],
                     help="N > 1: all-reduce inside the library's reduction kernel over peer memory (falls back to its "
                          "ncclAllReduce where the mailboxes cannot be mapped), the library's ncclAllReduce, or "
@@ -276,25 +653,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    K = wl["K"]
-    pis, Ts, Es = load_points(wl["model"], wl["points"])
-    config = {"workload": wl["desc"], "chunks_per_gpu": wl["chunks"], "chunk_len": wl["chunk_len"],
-              "points": wl["points"], "K": K, "sharding": "chunks across ranks, no data-path collective except one "
-              "all-reduce of float64[points]", "l2": "flushed between timed steps (256 MiB write)",
-              "model_build": "inside the timed region, on the GPU (theta -> pi,T,E -> logL fused on the device)"}
+    config = base_config(wl)
+    # forked before anything touches CUDA; the workers only ever run numpy
+    chunk_factory = ChunkFactory(max(1, min(16, host_cores() // max(1, world))))
 
     if args.impl == "reference":
         if rank != 0:
+            chunk_factory.close()
             return
-        res = cpu_reference_run(wl, pis, Ts, Es, args.steps, max(args.warmup, 1))
-        config = dict(config, model_build="not part of this arm: (pi,T,E) come from the committed fixture built by the "
-                      "reference's own Python build_hidden_markov_model (2.4 ms/theta for this model on one core, SURVEY 3.1)")
+        res = cpu_reference_run(wl, chunk_factory, args.steps, max(args.warmup, 1))
+        chunk_factory.close()
         line = {"metric": "forward sites*param-points/sec", "value": res["value"], "unit": "sites*points/s",
                 "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": 0,
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread_value")},
-                "e2e": {"value": res["value"], "unit": "sites*points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": res["value"], "unit": "sites*points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "notes": {"model_build": "not part of this arm: (pi,T,E) come from the committed fixture built by the reference's "
+                          "own Python build_hidden_markov_model (2.4 ms/theta for the isolation model on one core, SURVEY 3.1)",
+                          "kind": "port: ziphmm (birc-aeh/mini-ziphmm) is absent from /root/reference; this is the oracle's "
+                                  "restatement of its published algorithm"}}
         print(json.dumps(line))
         return
 
@@ -320,201 +698,100 @@ def main():
     m._lib.check(m._lib.load().imc_init(local_rank))
     dev = torch.device("cuda", local_rank)
     lib_comm = False
+    collective_note = "none (one rank)"
     if world > 1 and args.collective != "torch":
         # the library's own communicator: rank 0 draws the id, torch.distributed carries it to the other ranks
         from imcoalhmm_b200.sharding import init_library_comm
         init_library_comm(dev, fused=(args.collective == "fused"))
         lib_comm = True
-        config["collective"] = ("all-reduce fused into the chain-reduction kernel (peer-to-peer stores over NVLink)"
-                                if m._lib.comm_info()["fused"] else "ncclAllReduce issued by the library")
+        collective_note = ("all-reduce fused into the chain-reduction kernel (peer-to-peer stores over NVLink)"
+                           if m._lib.comm_info()["fused"] else "ncclAllReduce issued by the library")
     elif world > 1:
-        config["collective"] = "torch.distributed.all_reduce (NCCL)"
+        collective_note = "torch.distributed.all_reduce (NCCL)"
 
-    m.set_option("forward_kernel", args.forward_kernel)
-    model = getattr(m, wl["ctor"][0])(*wl["ctor"][1])
-    thetas = thetas_around(wl["default"], wl["points"])
-    # the synthetic alignment is simulated from the model at the scripts' default parameters (thetas[0])
-    pis, Ts, Es, st = model.build_hidden_markov_models(thetas)
-    assert (st == 0).all()
-    # weak scaling: every rank owns wl["chunks"] chunks (distinct seeds), all ranks score the same points
-    chunk_ids = range(rank * wl["chunks"], (rank + 1) * wl["chunks"])
-    chunks = make_chunks(wl, pis, Ts, Es, chunk_ids)
-    t0 = time.perf_counter()
-    fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
-    t_preprocess = time.perf_counter() - t0      # one-off, like Forwarder.__init__ (hmm.py:12-16); not in any timed region
-    zinfo = fset.zip_info(K)
-    sites_rank = fset.total_sites
-    N, S = wl["points"], 3
-    d_theta = torch.tensor(thetas, device=dev)
-    d_pi, d_T, d_E = (torch.tensor(x, device=dev) for x in (pis, Ts, Es))
-    d_out = torch.empty(N, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    peaks = m.measure_fp64_peak()
+    g = GpuCtx(m, torch, dist, dev, local_rank, rank, world, lib_comm, flush, peaks)
 
-    def step():
-        # theta -> (pi,T,E) -> logL on the device: 3 model-build kernels, forward, chunk reduction, status fix-up
-        model.batched_log_likelihood_device(d_theta.data_ptr(), fset, d_out.data_ptr(), N, 0, stream.cuda_stream)
-        if dist is not None and not lib_comm:
-            dist.all_reduce(d_out)        # the only collective: float64[N] partial log-likelihoods (lib_comm: done inside the call)
+    if args.workload == "c1":
+        lat = measure_latency(g, chunk_factory)
+        chunk_factory.close()
+        sites = WORKLOADS["c1"]["chunk_len"]
+        line = {"metric": "forward sites*param-points/sec", "value": sites / (lat["p50_ms"] * 1e-3), "unit": "sites*points/s",
+                "n_gpus": 1, "steps": lat["calls"], "warmup": 5, "ms_per_step": lat["p50_ms"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference example alignment (tests/golden/example_pair.npz)",
+                "config": config, "latency": lat, "gpu_launches": int(m.kernel_launches())}
+        print(json.dumps(line))
+        return
 
-    peak_dfma, peak_dmma = m.measure_fp64_peak()
-    sampler = ClockSampler(local_rank)       # samples nvidia-smi every ~100 ms from the warm-up steps to the end of the timed region
-    sampler.start()
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    launches0 = m.kernel_launches()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        step()
-        b.record(stream)
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    clocks = sampler.stop()
-    launches = m.kernel_launches() - launches0
-    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
-    if dist is not None:
-        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt.item())
-    logl_dev = d_out.cpu().numpy().copy()
-
-    # ---- kernel-only time of the dominant kernel (forward kernel without the reduce / all-reduce) ----
-    kt = []
-    m.set_option("comm_enabled", 0)          # this rank's kernel alone
-    for _ in range(min(3, args.steps)):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        fset.forward_batch_device(d_pi.data_ptr(), d_T.data_ptr(), d_E.data_ptr(), d_out.data_ptr(), N, K, S,
-                                  stream.cuda_stream)
-        b.record(stream)
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b) * 1e-3)
-    t_kernel = float(np.mean(kt))
-    m.set_option("comm_enabled", 1)
-
-    # ---- end to end through the host API (Model.batched_log_likelihood -> imc_loglik_batch): pinned host theta in,
-    # host logL + status out, every step; model build and forward on the device in between ----
-    h_theta = torch.tensor(thetas).pin_memory()
-    np_theta = h_theta.numpy()
-    np_out = np.empty(N)
-    for _ in range(2):
-        np_out = model.batched_log_likelihood(np_theta, fset)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        np_out = model.batched_log_likelihood(np_theta, fset)   # synchronous: returns with logL on the host
-        if dist is not None and not lib_comm:
-            tmp = torch.from_numpy(np_out).to(dev)
-            dist.all_reduce(tmp)
-            np_out[:] = tmp.cpu().numpy()
-    t_e2e = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-    h2d = thetas.nbytes
-    d2h = N * 8 + N * 4
-    if lib_comm:
-        m._lib.comm_destroy()      # collective; what follows (parity gate, CPU baseline) runs on rank 0 alone
-    if world == 1:
-        assert np.allclose(np_out, logl_dev, rtol=1e-12), "host API and device API disagree"
-
+    res = measure_workload(g, args.workload, wl, chunk_factory, args.steps, args.warmup, args.forward_kernel,
+                           parity_budget_s=25.0, parity=not args.no_parity, collective=args.collective)
     if rank != 0:
+        if lib_comm:
+            m._lib.comm_destroy()
+        chunk_factory.close()
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    total_site_points = float(sites_rank) * N * world
-    value = total_site_points * args.steps / t_dev
-    kernel = m.last_forward_kernel()
-    algo_flops = float(sites_rank) * N * flops_per_site_point(K)          # per launch (one rank), SURVEY 8(d)
-    peak = max(peak_dfma, peak_dmma)
-    achieved = algo_flops / t_kernel / 1e12
-    kname = "imc::%s_kernel" % ("zip_forward" if kernel == "zip" else "fwd_" + kernel)
-    fp64_view = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                 "peak_source": "measured in this run (imc_measure_fp64_peak): DFMA %.1f, DMMA %.1f TFLOP/s; "
-                 "MEASURED_PEAKS.json has no FP64 entry" % (peak_dfma, peak_dmma),
-                 "algorithmic_flop_per_site_point": flops_per_site_point(K)}
-    if kernel == "zip":
-        # The kernel runs the reference's own algorithm (zipHMM: one mat-vec per COMPRESSED symbol).  Its necessary work per
-        # launch is tokens x points chain-steps, each of which must stream one K x K dictionary matrix (8 K^2 bytes) out of
-        # shared memory for 2 K^2 flops: the pipe that bounds it is the shared-memory pipe (128 B/clk/SM), not FP64 and not
-        # HBM (ncu: ~1 MB of DRAM traffic per launch).  `roofline` is therefore quoted against that pipe; the plain-forward
-        # flop rate of SURVEY 8(d) (sites x points x (2K^2+3K) / time, which exceeds the FP64 peak by about the compression
-        # ratio) is kept beside it under "plain_forward_equivalent".
-        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        steps_exec = float(zinfo["tokens"]) * N
-        smem_peak = 128.0 * 148 * sm_clock / 1e9
-        smem_ach = steps_exec * 8.0 * K * K / t_kernel / 1e9
-        exec_tflops = steps_exec * (2 * K * K + K) / t_kernel / 1e12
-        roofline = {
-            "bound": "smem", "kernel": kname, "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
-            "frac": smem_ach / smem_peak, "traffic": None, "kernel_ms": 1e3 * t_kernel,
-            "bound_note": "shared-memory pipe: every chain-step streams one K x K dictionary matrix from shared memory; "
-                          "achieved = tokens x points x 8 K^2 bytes / kernel time",
-            "peak_source": "128 B/clk/SM x 148 SMs x %.0f MHz (median SM clock sampled during the timed region)" % (sm_clock / 1e6),
-            "algorithmic_bytes_per_chain_step": 8 * K * K, "chain_steps_per_launch": steps_exec,
-            "executed_tflops_fp64": exec_tflops, "executed_frac_of_fp64_peak": exec_tflops / peak,
-            "compression": {"sites": int(sites_rank), "tokens": int(zinfo["tokens"]), "ratio": sites_rank / max(1, zinfo["tokens"]),
-                            "dictionary_ids_used": zinfo["ids_used"], "dictionary_ids_available": zinfo["ids_available"],
-                            "dictionary_levels": zinfo["levels"], "preprocess_s_one_off": t_preprocess},
-            "plain_forward_equivalent": fp64_view}
-    else:
-        roofline = dict(fp64_view, kernel=kname, traffic=None, kernel_ms=1e3 * t_kernel)
-    try:    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this workload
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tr and kernel == "zip" and args.forward_kernel == 0:
-            roofline["traffic"] = tr["bytes"]
-            roofline["traffic_source"] = "%s, ncu --set full: %s" % (tr["kernel"], tr["source"])
-    except (OSError, ValueError):
-        pass
-    # the HBM view, for completeness: DRAM bytes of the dominant kernel (ncu) / kernel time against the measured copy bandwidth
-    try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    except (OSError, ValueError, KeyError):
-        hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
-    if roofline.get("traffic"):
-        ach = roofline["traffic"] / t_kernel / 1e9
-        roofline["hbm_view"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                "peak_source": hbm_src, "note": "not the bound: the working set lives in shared memory and registers"}
     line = {
-        "metric": "forward sites*param-points/sec", "value": value, "unit": "sites*points/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+        "metric": "forward sites*param-points/sec", "value": res["value"], "unit": "sites*points/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config, "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": total_site_points * args.steps / t_e2e, "unit": "sites*points/s",
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "roofline": roofline,
-        "logL_check": {"first": float(logl_dev[0]), "finite": bool(np.isfinite(logl_dev).all())},
+        "config": config, "clocks": res["clocks"], "gpu_launches": res["gpu_launches"], "e2e": res["e2e"],
+        "roofline": res["roofline"], "logL_check": res["logL_check"],
+        "notes": {"model_build": "inside the timed region, on the GPU (theta -> pi,T,E -> logL fused on the device)",
+                  "collective": collective_note,
+                  "oracle": "forward parity is against the repository's CPU restatement of zipHMM (oracle/): the reference's "
+                            "ziphmm dependency is absent and its tests pin no log-likelihood, so parity at that boundary is "
+                            "UNPINNED by the reference; the model-build half is pinned by the reference's own code"},
     }
-    # ---- parity gate: logL of this run's kernels vs the CPU oracle's plain forward on a prefix ----
-    if not args.no_parity:
-        from oracle import forward as F
-        pc, pp = min(2, len(chunks)), min(8, N)
-        sub = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks[:pc]])
-        got = sub.forward_batch(pis[:pp], Ts[:pp], Es[:pp])
-        want, _ = F.forward_batch([c.astype(np.int32) for c in chunks[:pc]], pis[:pp], Ts[:pp], Es[:pp])
-        rel = float(np.max(np.abs(got - want) / np.abs(want)))
-        line["parity"] = {"max_rel_err": rel, "tolerance": 1e-9, "ok": bool(rel <= 1e-9), "kernel": m.last_forward_kernel(),
-                          "sample": "%d chunks x %d bp x %d points vs oracle plain forward (float64)" % (pc, wl["chunk_len"], pp)}
-        assert rel <= 1e-9, "parity gate failed: %g" % rel
+    if "parity" in res:
+        line["parity"] = res["parity"]
+    if "collective_check" in res:
+        line["collective_check"] = res["collective_check"]
+    if lib_comm:
+        m._lib.comm_destroy()      # collective; rank 0 goes on alone
+    failures = []
+    if "parity" in res and not res["parity"]["ok"]:
+        failures.append("primary parity %g" % res["parity"]["max_rel_err"])
+    if "collective_check" in res and not res["collective_check"]["all_ranks_agree"]:
+        failures.append("fused all-reduce differs from the rank-ordered sum")
+
+    # ---- secondary block: the shapes the north star names + the drop-in latency, measured in the same run ----
+    if world == 1 and args.workload == "c2" and not args.no_secondary and args.forward_kernel == 0:
+        sec = {}
+        share = args.secondary_budget_s / len(SECONDARY)
+        for name in SECONDARY:
+            try:
+                r = measure_workload(g, name, WORKLOADS[name], chunk_factory, steps=5, warmup=3, parity_budget_s=share,
+                                     e2e=False, parity=not args.no_parity)
+                rf = r["roofline"]
+                sec[name] = {"workload": WORKLOADS[name]["desc"], "ms_per_step": r["ms_per_step"], "value": r["value"],
+                             "unit": r["unit"], "steps": r["steps"], "warmup": r["warmup"], "kernel": r["kernel"],
+                             "kernel_ms": rf["kernel_ms"], "smem_pipe_frac": rf.get("frac"),
+                             "smem_pipe_frac_of_measured": rf.get("frac_of_measured_pipe"),
+                             "executed_frac_of_fp64_peak": rf.get("executed_frac_of_fp64_peak"),
+                             "plain_forward_equivalent_tflops": rf["plain_forward_equivalent"]["achieved"],
+                             "compression": rf.get("compression"), "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+                             "parity": r.get("parity")}
+                if r.get("parity") and not r["parity"]["ok"]:
+                    failures.append("%s parity %g" % (name, r["parity"]["max_rel_err"]))
+            except Exception as e:      # a secondary workload must not cost the run its primary line
+                sec[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            sec["c1"] = measure_latency(g, chunk_factory)
+        except Exception as e:
+            sec["c1"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        line["secondary"] = sec
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, pis, Ts, Es, 3, 1).items() if k != "ms_per_step"}
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, chunk_factory, 3, 1).items() if k != "ms_per_step"}
+    chunk_factory.close()
+    if failures:
+        line["failed"] = failures
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    assert not failures, "; ".join(failures)
 
 
 if __name__ == "__main__":

@@ -16,8 +16,12 @@ ZIP_MAX_K = 40      # tiles 2..40; any K below runs in the next tile with zero p
 
 @pytest.fixture(autouse=True)
 def _reset_options():
+    """These are the tests of the plain (pair-dictionary) form and of the per-site kernels; the spectral form over run
+    tokens, which the automatic choice prefers on alignment-like data, has tests/test_spectral_gpu.py."""
     import imcoalhmm_b200 as m
+    m.set_option("zip_spectral", 2)
     yield
+    m.set_option("zip_spectral", 0)
     m.set_option("forward_kernel", 0)
     m.set_option("dmma_mtiles", 0)
     m.set_option("fold_emission", 0)

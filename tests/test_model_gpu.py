@@ -132,7 +132,7 @@ def test_batched_callers_drive_the_gpu_likelihood():
     chains = BatchedMCMC(priors, lik, thinning=3, no_chains=32, rng=np.random.default_rng(0))
     before = m.kernel_launches()
     theta, prior, like, post = chains.sample()
-    assert chains.likelihood_calls == 4 and m.kernel_launches() - before <= 3 * 8
+    assert chains.likelihood_calls == 4 and m.kernel_launches() - before <= 3 * 12     # per call: model build, spectral preparation, the two passes, folds, reduction
     assert np.isfinite(like).all() and np.allclose(post, prior + like)
     # each chain's stored likelihood is what the scalar reference-style call returns for its theta
     for i in (0, 7, 31):

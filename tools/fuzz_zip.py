@@ -1,5 +1,6 @@
-"""Randomised cross-check of the zip kernel (all launch shapes, segmented / warp-per-chain modes, dictionary caps)
-against the CPU oracle.  python tools/fuzz_zip.py [trials] [seed]"""
+"""Randomised cross-check of the zip kernel (all launch shapes, segmented / warp-per-chain modes, dictionary caps, the
+spectral form over run tokens with reversible, non-reversible and mixed batches) against the CPU oracle.
+python tools/fuzz_zip.py [trials] [seed]"""
 import os
 import sys
 
@@ -23,6 +24,14 @@ for trial in range(trials):
     stick = rng.choice([0.5, 0.99, 0.9999])
     Ts = np.stack([stick * np.eye(K) + (1 - stick) * rng.dirichlet(np.ones(K), size=K) for _ in range(N)])
     Es = rng.dirichlet(np.ones(nsym), size=(N, K))
+    rev = rng.random(N) < rng.choice([0.0, 0.5, 1.0, 1.0])    # reversible points: diag(pi) T symmetric, as the reference's models are
+    for n in np.flatnonzero(rev):
+        J = rng.random((K, K)) + 0.01
+        J = 0.5 * (J + J.T) * (1 - stick) / J.sum()
+        J[np.diag_indices(K)] += stick * rng.dirichlet(np.ones(K) * 3.0)
+        J /= J.sum()
+        pis[n] = J.sum(axis=1)
+        Ts[n] = J / pis[n][:, None]
     if rng.random() < 0.2:                                   # an impossible symbol for some states
         Es[:, rng.integers(0, K), rng.integers(0, nsym)] = 0.0
     p = rng.dirichlet(np.ones(nsym) * rng.choice([0.05, 1.0]))
@@ -45,8 +54,9 @@ for trial in range(trials):
         fk = 1
     if fk == 3 and K not in (10, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64):
         fk = 1
+    spec = int(rng.choice([0, 1, 1, 1, 2]))                  # spectral form: auto, forced (points that do not qualify take the plain form), off
     for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap),
-                 ("zip_pipeline", pipe)):
+                 ("zip_pipeline", pipe), ("zip_spectral", spec)):
         m.set_option(k, v)
     got = fset.forward_batch(pis, Ts, Es)
     # the oracle's plain forward divides by the zero scale of an impossible observation and returns NaN where the
@@ -59,7 +69,7 @@ for trial in range(trials):
     ok = bool(same_inf.all()) and err < 1e-10 and bool((np.isfinite(got) == np.isfinite(want)).all())
     worst = max(worst, err)
     if not ok:
-        print("MISMATCH trial %d: K=%d N=%d C=%d nsym=%d lanes=%d ctas=%d seg=%d cap=%d pipe=%d kernel=%s err=%.3e\n got %s\nwant %s"
-              % (trial, K, N, C, nsym, lanes, ctas, seg, cap, pipe, m.last_forward_kernel(), err, got[:4], want[:4]))
+        print("MISMATCH trial %d: K=%d N=%d C=%d nsym=%d lanes=%d ctas=%d seg=%d cap=%d pipe=%d spec=%d rev=%s kernel=%s err=%.3e\n got %s\nwant %s"
+              % (trial, K, N, C, nsym, lanes, ctas, seg, cap, pipe, spec, rev.astype(int), m.last_forward_kernel(), err, got[:4], want[:4]))
         sys.exit(1)
 print("fuzz ok: %d trials, worst relative error %.2e" % (trials, worst))

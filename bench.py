@@ -455,6 +455,7 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
     # ---- kernel-only time of the dominant kernel (forward kernel without model build / all-reduce) ----
     kt = []
     m.set_option("comm_enabled", 0)          # this rank's kernel alone
+    passes0 = m.mma_passes()
     for _ in range(min(3, steps)):
         g.flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -464,6 +465,7 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
         b.record(stream)
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b) * 1e-3)
+    passes_per_launch = (m.mma_passes() - passes0) / float(len(kt))
     t_kernel = float(np.mean(kt))
     m.set_option("comm_enabled", 1)
 
@@ -509,31 +511,45 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
                  "algorithmic_flop_per_site_point": flops_per_site_point(K)}
     if kernel.startswith("zip"):
         # The kernel runs the reference's own algorithm (zipHMM: one mat-vec per COMPRESSED symbol; in the spectral form one
-        # per non-run dictionary entry).  Its necessary work per launch is tokens x points chain-steps, each of which must
-        # stream one K x K dictionary matrix (8 K^2 bytes) out of shared memory for 2 K^2 flops: the pipe that bounds it is the
-        # shared-memory pipe (128 B/clk/SM nominal, 122 measured with full LDS.128, profiles/r01_smem_patterns.txt), not FP64
-        # and not HBM (ncu: ~1 MB of DRAM traffic per launch).
+        # per non-run dictionary entry).  Its necessary work per launch is tokens x points chain-steps = K x K mat-vecs.
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
         steps_exec = float(zinfo["tokens"]) * N
         smem_peak = 128.0 * 148 * sm_clock / 1e9
         smem_ach = steps_exec * 8.0 * K * K / t_kernel / 1e9
         exec_tflops = steps_exec * (2 * K * K + K) / t_kernel / 1e12
-        roofline = {
-            "bound": "smem", "kernel": kname + (" (spectral form: run tokens)" if spectral else ""), "achieved": smem_ach,
-            "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak, "frac_of_measured_pipe": smem_ach / (smem_peak * 122.0 / 128.0),
-            "traffic": None, "kernel_ms": 1e3 * t_kernel,
-            "bound_note": "shared-memory pipe: every chain-step streams one K x K dictionary matrix from shared memory; "
-                          "achieved = tokens x points x 8 K^2 bytes / kernel time (the spectral form adds 16 K bytes of power-table "
-                          "rows per chain-step, not counted)",
-            "peak_source": "nominal 128 B/clk/SM x 148 SMs x %.0f MHz (median SM clock sampled during the timed region); "
-                           "frac_of_measured_pipe uses the 122 B/clk/SM a full LDS.128 stream reaches on this part" % (sm_clock / 1e6),
-            "algorithmic_bytes_per_chain_step": 8 * K * K, "chain_steps_per_launch": steps_exec,
-            "executed_tflops_fp64": exec_tflops, "executed_frac_of_fp64_peak": exec_tflops / peak,
-            "compression": {"sites": int(sites_rank), "tokens": int(zinfo["tokens"]), "ratio": sites_rank / max(1, zinfo["tokens"]),
-                            "form": "run tokens (spectral)" if spectral else "pair dictionary",
-                            "dictionary_ids_used": zinfo["ids_used"], "dictionary_ids_available": zinfo["ids_available"],
-                            "dictionary_levels": zinfo["levels"], "preprocess_s_one_off": t_preprocess},
-            "plain_forward_equivalent": fp64_view}
+        compression = {"sites": int(sites_rank), "tokens": int(zinfo["tokens"]), "ratio": sites_rank / max(1, zinfo["tokens"]),
+                       "form": "run tokens (spectral)" if spectral else "pair dictionary",
+                       "dictionary_ids_used": zinfo["ids_used"], "dictionary_ids_available": zinfo["ids_available"],
+                       "dictionary_levels": zinfo["levels"], "preprocess_s_one_off": t_preprocess}
+        smem_view = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
+                     "frac_of_measured_pipe": smem_ach / (smem_peak * 122.0 / 128.0),
+                     "note": "chain-steps x 8 K^2 bytes / kernel time against 128 B/clk/SM (122 measured with full LDS.128, "
+                             "profiles/r01_smem_patterns.txt): the roofline of the FMA shapes, which stream one K x K matrix per "
+                             "chain-step out of shared memory"}
+        if "mma" in kernel:
+            # MMA shape: the hot entry's matrix is in registers (B fragments), chains are rows of mma.sync.m8n8k4.f64 tiles; the pipe
+            # that bounds it is the FP64 tensor (DMMA) pipe.  achieved = algorithmic flops (chain-steps x (2 K^2 + K)); the
+            # executed DMMA flops (incl. tile padding and the rows of cold passes that serve other chains) are reported beside.
+            KT, NT = (K + 3) // 4, (K + 7) // 8
+            dmma_tflops = passes_per_launch * KT * NT * 512.0 / t_kernel / 1e12
+            roofline = {
+                "bound": "fp64-tensor", "kernel": kname + " (spectral form, MMA shape)", "achieved": exec_tflops, "peak": peak_dmma,
+                "unit": "TFLOP/s", "frac": exec_tflops / peak_dmma, "traffic": None, "kernel_ms": 1e3 * t_kernel,
+                "bound_note": "FP64 tensor pipe: achieved = chain-steps x (2 K^2 + K) flop / kernel time; peak = DMMA.8x8x4 rate "
+                              "measured in this run (imc_measure_fp64_peak)",
+                "algorithmic_flop_per_chain_step": 2 * K * K + K, "chain_steps_per_launch": steps_exec,
+                "executed_dmma_tflops": dmma_tflops, "executed_dmma_frac_of_peak": dmma_tflops / peak_dmma,
+                "dmma_passes_per_launch": passes_per_launch, "dmma_per_pass": KT * NT,
+                "passes_per_warp_step": passes_per_launch / max(1.0, steps_exec / 8.0),
+                "executed_note": "every pass is KT x NT DMMAs of 512 flop for the 8 chains of a warp: tiles are padded to 8 x 4 "
+                                 "(K=10: 100 of 192 MACs useful) and a pass for a cold entry serves only the chains on that entry",
+                "smem_view_of_the_fma_shapes": smem_view, "compression": compression, "plain_forward_equivalent": fp64_view}
+        else:
+            roofline = dict(smem_view, kernel=kname + (" (spectral form: run tokens)" if spectral else ""), traffic=None,
+                            kernel_ms=1e3 * t_kernel, algorithmic_bytes_per_chain_step=8 * K * K, chain_steps_per_launch=steps_exec,
+                            executed_tflops_fp64=exec_tflops, executed_frac_of_fp64_peak=exec_tflops / peak,
+                            compression=compression, plain_forward_equivalent=fp64_view)
+            roofline["bound_note"] = roofline.pop("note")
     else:
         roofline = dict(fp64_view, kernel=kname, traffic=None, kernel_ms=1e3 * t_kernel)
     try:    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this workload and kernel form
@@ -768,9 +784,10 @@ def main():
                 rf = r["roofline"]
                 sec[name] = {"workload": WORKLOADS[name]["desc"], "ms_per_step": r["ms_per_step"], "value": r["value"],
                              "unit": r["unit"], "steps": r["steps"], "warmup": r["warmup"], "kernel": r["kernel"],
-                             "kernel_ms": rf["kernel_ms"], "smem_pipe_frac": rf.get("frac"),
-                             "smem_pipe_frac_of_measured": rf.get("frac_of_measured_pipe"),
-                             "executed_frac_of_fp64_peak": rf.get("executed_frac_of_fp64_peak"),
+                             "kernel_ms": rf["kernel_ms"], "roofline_bound": rf.get("bound"), "roofline_frac": rf.get("frac"),
+                             "executed_dmma_frac_of_peak": rf.get("executed_dmma_frac_of_peak"),
+                             "passes_per_warp_step": rf.get("passes_per_warp_step"),
+                             "smem_view_frac": (rf.get("smem_view_of_the_fma_shapes") or rf).get("frac"),
                              "plain_forward_equivalent_tflops": rf["plain_forward_equivalent"]["achieved"],
                              "compression": rf.get("compression"), "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
                              "parity": r.get("parity")}

@@ -16,7 +16,7 @@ from . import _lib
 
 _lib.load()   # fail loudly at import time if the CUDA library is missing
 
-from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel, measure_fp64_peak  # noqa: E402
+from ._lib import IMCError, set_option, get_option, kernel_launches, last_forward_kernel, measure_fp64_peak, mma_passes  # noqa: E402
 from .hmm import Forwarder, ForwarderSet  # noqa: E402
 from .likelihood import Likelihood, maximum_likelihood_estimate  # noqa: E402
 from .models import (Model, IsolationModel, IsolationMigrationModel, VariableCoalescenceRateIsolationModel,  # noqa: E402
@@ -27,4 +27,4 @@ from . import mcmc  # noqa: E402
 __all__ = ["Forwarder", "ForwarderSet", "Likelihood", "maximum_likelihood_estimate", "IMCError", "ziphmm", "mcmc", "Model", "IsolationModel",
            "IsolationMigrationModel", "VariableCoalescenceRateIsolationModel", "VariableCoalAndMigrationRateModel",
            "IsolationMigrationEpochsModel",
-           "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak"]
+           "set_option", "get_option", "kernel_launches", "last_forward_kernel", "measure_fp64_peak", "mma_passes"]

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "imc_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "imc_get_option": (ctypes.c_int, [ctypes.c_char_p, c_i64p]),
     "imc_kernel_launches": (ctypes.c_int64, []),
+    "imc_mma_passes": (ctypes.c_int, [c_i64p]),
     "imc_last_forward_kernel": (ctypes.c_char_p, []),
 }
 
@@ -149,6 +150,12 @@ def comm_info():
     n, r, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     check(load().imc_comm_info(ctypes.byref(n), ctypes.byref(r), ctypes.byref(f)))
     return {"nranks": n.value, "rank": r.value, "fused": bool(f.value)}
+
+
+def mma_passes():
+    v = ctypes.c_int64()
+    check(load().imc_mma_passes(ctypes.byref(v)))
+    return v.value
 
 
 def kernel_launches():

@@ -17,7 +17,7 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "forward_kernels.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "imcoalhmm_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl", "--split-compile", "0"]
 
 
 def needs_build():

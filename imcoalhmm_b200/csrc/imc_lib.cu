@@ -63,6 +63,8 @@ struct Context {
     long long opt_zip_max_entries = 0; // cap on dictionary entries used (0 = whatever fits in shared memory)
     long long opt_zip_pipeline = 0;    // pieces per chunk in pipelined mode: 0 = auto, 1 = off, >= 2 forced
     long long opt_zip_spectral = 0;    // spectral form of the zip kernel (run tokens): 0 = auto, 1 = always, 2 = never
+    long long opt_zip_mma = 0;         // MMA form of the spectral kernel: 0 = auto, 1 = always (tiles >= 8), 2 = never
+    long long opt_zip_mma_shape = 0;   // launch shape of the MMA form: 0 = auto, 1..4 see zip_plan_k
     long long opt_zip_spectral_force_bad = 0;   // test switch: zip_spectral_kernel declares every point unfit (plain-form pass serves them)
     long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
     long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
@@ -128,6 +130,8 @@ struct ZipSplit {                 // segmented variant of a ZipDevice's chunk li
 struct ZipDevice {
     int M = 0, nlevels = 0;
     bool spec = false;                        // run tokens (32-bit words) for the spectral form of the kernel
+    int hot_id = 0;                           // spec: the most frequent entry and its share of the tokens
+    double hot_share = 0.0;
     long long total_tokens = 0;
     int max_ntok = 0;
     std::vector<ZipChunk> host_chunks;        // sorted by ntok, descending
@@ -525,10 +529,23 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     int rc;
     const int ns = (int)set->streams.size(), pass = spec ? 0 : 1;
     const int avail = spec ? set->run_merges.size() : set->merges.size();
+    g_plan_chunks = ns;
     ZipPlan plan;
     if ((rc = zip_plan(K, S, avail, &plan, 0, spec))) return rc;
     ZipDevice* z = nullptr;
     if ((rc = zip_device(set, plan.M, &z, spec))) return rc;
+    // MMA form: eight chains per warp as the rows of FP64 tensor-core tiles, the most frequent entry's matrix in registers.
+    // Worth it where one entry dominates the streams (the lone mismatch followed by its run: 75-90 % of the tokens of a
+    // pairwise alignment); chains on other entries cost a pass of their own.
+    bool mma = false;
+    if (spec && zip_mma_tile(zip_tile(K)) && g_ctx.opt_zip_mma != 2 && g_ctx.opt_zip_lanes == 0) {
+        ZipPlan mp;
+        ZipDevice* mz = nullptr;
+        if (zip_plan(K, S, avail, &mp, 0, true, true) == IMC_OK && zip_device(set, mp.M, &mz, true) == IMC_OK &&
+            (g_ctx.opt_zip_mma == 1 || mz->hot_share >= 0.5)) {
+            plan = mp; z = mz; mma = true;
+        }
+    }
     // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
     // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
     //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
@@ -565,7 +582,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
                     if (t < 0.8 * best) { best = t; best_seg = sl; }
                 }
             }
-            if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0) {   // (b)
+            if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0 && g_ctx.opt_zip_mma != 1) {   // (b)
                 const long long warps = (long long)sms * (zip_tile(K) <= 24 ? 16 : 8);
                 const double rounds = std::ceil((double)((long long)N * ns) / (double)warps);
                 const double t = rounds * z->max_ntok * lat32;
@@ -575,6 +592,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             if (best_lanes != plan.lanes) {
                 if ((rc = zip_plan(K, S, avail, &plan, best_lanes, spec))) return rc;
                 if ((rc = zip_device(set, plan.M, &z, spec))) return rc;
+                mma = false;
             }
         }
     }
@@ -597,6 +615,15 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     za.vec_stride = 0;
     za.plist = plist; za.pcount = pcount;
     za.spec = d_spec; za.spec_stride = spec_stride;
+    za.hot_id = z->hot_id;
+    za.mma_passes = nullptr;
+    if (mma) {
+        if (!g_mma_passes) {
+            CUDA_TRY(cudaMalloc((void**)&g_mma_passes, sizeof(unsigned long long)));
+            CUDA_TRY(cudaMemset(g_mma_passes, 0, sizeof(unsigned long long)));
+        }
+        za.mma_passes = g_mma_passes;
+    }
     DeviceBuf& d_vec = set->d_vec[pass];
     DeviceBuf& d_prog = set->d_prog[pass];
     if (seglen > 0 && K <= 64) {
@@ -624,7 +651,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             const int plen = (int)(((z->max_ntok + nseg - 1) / nseg + 15) / 16 * 16);
             nseg = (z->max_ntok + plen - 1) / plen;
             if (nseg >= 2) {
-                const int cstride = zip_tile(K) + 4;
+                const int cstride = (zip_tile(K) + 7) / 8 * 8 + 4;       // state registers of a chain's lanes (MMA form: 8 per n-tile) + exponent + flags
                 if ((rc = d_vec.reserve(sizeof(double) * (size_t)N * ns * cstride))) return rc;
                 if ((rc = d_prog.reserve(sizeof(int) * (size_t)N * ns))) return rc;
                 CUDA_TRY(cudaMemsetAsync(d_prog.p, 0, sizeof(int) * (size_t)N * ns, st));
@@ -641,7 +668,8 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
         za.vec_stride = K + 1;
     }
     if (spec || !plist) {
-        g_last_kernel = spec ? (split ? "zip-spectral-segmented" : (plan.lanes == 32 ? "zip-spectral-warp" : "zip-spectral"))
+        g_last_kernel = spec ? (split ? (mma ? "zip-spectral-mma-segmented" : "zip-spectral-segmented")
+                                      : (plan.lanes == 32 ? "zip-spectral-warp" : (mma ? "zip-spectral-mma" : "zip-spectral")))
                              : (split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip"));
     }
     if ((rc = launch_zip(za, plan, st))) return rc;
@@ -701,6 +729,9 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         }
     }
     if (which == KERNEL_ZIP) {
+        // every chain result is written by exactly one of the passes below; a slot nobody writes must read as NaN, never as
+        // the previous call's value
+        CUDA_TRY(cudaMemsetAsync(set->d_chain.p, 0xff, sizeof(double) * (size_t)N * ns, st));
         // Spectral form where the run symbol's runs carry most of the compression: zip_spectral_kernel diagonalises C_r of
         // every point and sorts the points into those it could serve (ok list) and the others (plain form, bad list).
         bool use_spec = g_ctx.opt_zip_spectral == 1;
@@ -713,7 +744,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
             if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, false, nullptr, nullptr, nullptr, 0, st))) return rc;
             return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
         }
-        const int sstride = 2 * K + S * K + S * K * K;
+        const int sstride = 2 * K + S * K + S * K * K + 1;
         if ((rc = set->d_spec.reserve(sizeof(double) * (size_t)N * sstride))) return rc;
         if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)2 * N + 2)))) return rc;
         int* lists = (int*)set->d_lists.p;
@@ -859,6 +890,8 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_pipeline")) { if (value < 0 || value > 32) return fail(IMC_ERR_INVALID, "zip_pipeline must be in [0, 32]"); g_ctx.opt_zip_pipeline = value; return IMC_OK; }
     if (!strcmp(key, "zip_spectral")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_spectral must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_spectral = value; return IMC_OK; }
     if (!strcmp(key, "zip_spectral_force_bad")) { g_ctx.opt_zip_spectral_force_bad = value ? 1 : 0; return IMC_OK; }
+    if (!strcmp(key, "zip_mma")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_mma must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_mma = value; return IMC_OK; }
+    if (!strcmp(key, "zip_mma_shape")) { if (value < 0 || value > 4) return fail(IMC_ERR_INVALID, "zip_mma_shape must be in [0, 4]"); g_ctx.opt_zip_mma_shape = value; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
@@ -875,6 +908,8 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_pipeline")) { *value_out = g_ctx.opt_zip_pipeline; return IMC_OK; }
     if (!strcmp(key, "zip_spectral")) { *value_out = g_ctx.opt_zip_spectral; return IMC_OK; }
     if (!strcmp(key, "zip_spectral_force_bad")) { *value_out = g_ctx.opt_zip_spectral_force_bad; return IMC_OK; }
+    if (!strcmp(key, "zip_mma")) { *value_out = g_ctx.opt_zip_mma; return IMC_OK; }
+    if (!strcmp(key, "zip_mma_shape")) { *value_out = g_ctx.opt_zip_mma_shape; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);

@@ -18,7 +18,7 @@ static int zip_tile(int K) {
 }
 static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
 
-struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; bool spec; };
+struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; bool spec, mma; };
 #ifndef IMC_ZIP8_THREADS
 #define IMC_ZIP8_THREADS 512     // threads of the single-CTA-per-SM shape with 8 lanes per chain, K <= 24 (experiment builds: 640, 768)
 #endif
@@ -34,9 +34,40 @@ static const size_t ZIP_SMEM_SM = 227 * 1024;    // usable shared memory per SM 
 // rows of four tokens)
 static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 : 8; }
 
+// MMA form (ZipCfgM): spectral form, tiles >= 8 states
+static bool zip_mma_tile(int K) { return K >= 8; }
+static thread_local int g_plan_chunks = 0;     // chunks of the set being planned for (0 = unknown), set by zip_pass
+static unsigned long long* g_mma_passes = nullptr;      // device counter (ZipArgs::mma_passes)
+
 template <int K, bool SPEC>
-static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
+static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, bool mma) {
     ZipPlan p;
+    p.mma = false;
+    if constexpr (SPEC && K >= 8) {
+        if (mma) {
+            // shapes: 1 = one CTA of 512 threads per SM (256 for K >= 32), 2 = two CTAs of 256, 3 = four CTAs of 256 threads
+            // with 64 registers (K <= 12), 4 = four CTAs of 128 threads (K <= 24).  More CTAs per SM = more parameter
+            // points in flight per SM (a point offers chunks / 8 warp-loads at a time) and smaller dictionaries, which cost
+            // little in the spectral form (K=10: 62 instead of 162 entries = 5 % more tokens).
+            using C = ZipCfgM<K>;
+            int shape = (int)g_ctx.opt_zip_mma_shape;
+            // a point offers ceil(chunks / 8) independent warp-loads at a time: CTAs with more warps than that would idle
+            if (shape == 0) shape = 1;       // measured on B200 (c2: 3.52 vs 3.70 ms, K=20: 12.4 vs 13.2 ms with two CTAs of 256)
+            if (K > 24) shape = 1;
+            if (K > 12 && shape == 3) shape = 2;
+            p.mma = true;
+            p.lanes = 4;                     // four lanes per chain, eight chains per warp
+            p.ctas_per_sm = shape == 1 ? 1 : (shape == 2 ? 2 : 4);
+            p.threads = shape == 1 ? (K <= 24 ? 512 : 256) : (shape == 4 ? 128 : 256);
+            const size_t budget = (ZIP_SMEM_SM - 1024 * (p.ctas_per_sm - 1)) / p.ctas_per_sm;
+            p.M = std::min(avail_ids, ZipSmem<C, true>::max_entries(budget, S, p.threads));
+            if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
+            p.M = std::max(p.M, S);
+            p.spec = true;
+            p.smem = ZipSmem<C, true>::bytes(p.M, S, p.threads);
+            return p;
+        }
+    }
     p.lanes = want_lanes ? want_lanes : zip_default_lanes(K);
     if (K < 8) p.lanes = 8;
     if (p.lanes == 32 && K < 10) p.lanes = 8;
@@ -73,10 +104,10 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes) {
 }
 
 // spec: plan for the spectral form (run tokens, power table in shared memory) over avail_ids run-dictionary ids
-static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0, bool spec = false) {
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0, bool spec = false, bool mma = false) {
     const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
     switch (zip_tile(K)) {
-#define X(k) case k: *out = spec ? zip_plan_k<k, true>(S, avail_ids, want, lanes) : zip_plan_k<k, false>(S, avail_ids, want, lanes); break;
+#define X(k) case k: *out = spec ? zip_plan_k<k, true>(S, avail_ids, want, lanes, mma) : zip_plan_k<k, false>(S, avail_ids, want, lanes, false); break;
         ZIP_K_LIST(X)
 #undef X
         default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
@@ -122,6 +153,10 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
         chunks[i].first_sym = set->first_sym[k];
         chunks[i].out_index = k;
         chunks[i].first_run = spec ? set->first_run[k] : 0;
+        long long rs = chunks[i].first_run;
+        if (spec) for (uint32_t t : rtok[k]) rs += t >> 8;
+        chunks[i].run_sites = (int)rs;
+        chunks[i].pad = 0;
         off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
     std::vector<uint8_t> flat((size_t)off, 0);
@@ -135,6 +170,12 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
     if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
     z->M = M;
     z->spec = spec;
+    if (spec) {        // the most frequent entry of the streams: the MMA form keeps its matrix in registers
+        std::vector<long long> hist(256, 0);
+        for (int k = 0; k < ns; ++k) for (uint32_t t : rtok[k]) hist[t & 0xffu]++;
+        z->hot_id = (int)(std::max_element(hist.begin(), hist.end()) - hist.begin());
+        z->hot_share = total > 0 ? (double)hist[z->hot_id] / (double)total : 0.0;
+    }
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
     z->max_ntok = ns ? chunks[0].ntok : 0;
@@ -188,20 +229,20 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
         }
         // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
         if (nseg <= 32) {
-            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0});
+            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0, ch.run_sites, 0});
         } else {        // two levels: groups of gs segments folded in parallel, then the groups
             const int gs = (int)std::ceil(std::sqrt((double)nseg)), ngroups = (nseg + gs - 1) / gs;
             const int base2 = nvec2;
             for (int g = 0; g < ngroups; ++g) {
                 const int s0 = g * gs, s1 = std::min(nseg, s0 + gs);     // segments [s0, s1)
                 if (g == 0) {
-                    items1.push_back({first_chain, first_chain + 1, s1 - 1, nvec2++, 0, 1});
+                    items1.push_back({first_chain, first_chain + 1, s1 - 1, nvec2++, 0, 1, 0, 0});
                 } else {
                     for (int col = 0; col < K; ++col)
-                        items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1});
+                        items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1, 0, 0});
                 }
             }
-            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0});
+            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0, ch.run_sites, 0});
         }
     }
     // the kernel takes chunks in list order, longest first: full segments first, tails last (out_index keeps identity)
@@ -243,6 +284,16 @@ static int launch_zip_k(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream
 
 template <int K, bool SPEC>
 static int launch_zip_shape(const ZipArgs& a, const ZipPlan& p, int grid, cudaStream_t st) {
+    if constexpr (SPEC && K >= 8) {
+        if (p.mma) {
+            if constexpr (K <= 12) { if (p.ctas_per_sm == 4 && p.threads == 256) return launch_zip_k<ZipCfgM<K>, 256, 4, true>(a, p, grid, st); }
+            if constexpr (K <= 24) {
+                if (p.ctas_per_sm == 4) return launch_zip_k<ZipCfgM<K>, 128, 4, true>(a, p, grid, st);
+                if (p.ctas_per_sm == 2) return launch_zip_k<ZipCfgM<K>, 256, 2, true>(a, p, grid, st);
+                return launch_zip_k<ZipCfgM<K>, 512, 1, true>(a, p, grid, st);
+            } else return launch_zip_k<ZipCfgM<K>, 256, 1, true>(a, p, grid, st);
+        }
+    }
     if constexpr (K >= 10) {
         if (p.lanes == 32) {
             if constexpr (K <= 24) return launch_zip_k<ZipCfg32<K>, 512, 1, SPEC>(a, p, grid, st);
@@ -273,6 +324,8 @@ static int launch_zip(ZipArgs a, const ZipPlan& p, cudaStream_t st) {
     // with fewer warp-loads than warps on the machine, let only as many warps per CTA claim work as it takes to cover
     // them: the chains then spread over all SMs instead of piling onto the first CTAs that arrive
     a.active_warps = (int)std::min<long long>(p.threads / 32, std::max<long long>(1, (units + grid - 1) / grid));
+    // pipelined pieces: a point has only (chunks / chains per warp) chains of pieces; more warps than that would just poll
+    if (a.nseg > 1) a.active_warps = std::min(a.active_warps, (a.nchunks + cpw - 1) / cpw);
     switch (zip_tile(a.K)) {
 #define X(k) case k: return p.spec ? launch_zip_shape<k, true>(a, p, grid, st) : launch_zip_shape<k, false>(a, p, grid, st);
         ZIP_K_LIST(X)
@@ -388,5 +441,17 @@ extern "C" int imc_seqset_spectral_counts(imc_seqset* set, int* ok_points, int* 
     }
     if (ok_points) *ok_points = c[0];
     if (plain_points) *plain_points = c[1];
+    return IMC_OK;
+}
+
+// passes of the MMA form executed by this process so far (each pass = KT x NT DMMAs of 512 flop per warp); bench.py
+extern "C" int imc_mma_passes(int64_t* passes_out) {
+    if (!passes_out) return fail(IMC_ERR_INVALID, "NULL argument");
+    *passes_out = 0;
+    if (!g_mma_passes) return IMC_OK;
+    unsigned long long v = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&v, g_mma_passes, sizeof v, cudaMemcpyDeviceToHost));
+    *passes_out = (int64_t)v;
     return IMC_OK;
 }

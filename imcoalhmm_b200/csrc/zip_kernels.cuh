@@ -18,6 +18,7 @@
 // the segmented (scan) form below.  DESIGN.md section 4.1 has the measurements behind every choice made here.
 #pragma once
 #include "forward_kernels.cuh"
+#include <type_traits>
 
 namespace imc {
 
@@ -35,6 +36,8 @@ struct ZipChunk {
                          // unit vector e_c, c = -1 - first_sym (column c of a segment's transfer matrix, see zip_fold_kernel)
     int out_index;       // column of chain_out this chunk writes
     int first_run;       // spectral form: sites of the run symbol between position 0 and the first token (<= RUN_MAX)
+    int run_sites;       // spectral form: first_run + the runs of all tokens; the result gets run_sites * ln(lambda_max)
+    int pad;
 };
 
 struct ZipArgs {
@@ -68,9 +71,11 @@ struct ZipArgs {
     const int* plist;
     const int* pcount;
     // spectral form (SPEC kernels): tokens are 32-bit run words (tokenizer.inl), per point spec_stride doubles:
-    // lambda[K], wsum[K], b0[S][K], R[S][K][K]  (see zip_spectral_kernel)
+    // lambda[K], wsum[K], b0[S][K], R[S][K][K], ln(lambda_max)  (see zip_spectral_kernel)
     const double* spec;
     int spec_stride;
+    int hot_id;                  // MMA form: the most frequent entry of the streams (its matrix lives in registers)
+    unsigned long long* mma_passes;   // MMA form: passes (of KT x NT DMMAs each) executed, for the roofline (one atomic per work unit)
 };
 
 // Segmented mode (chain-scarce calls: few chunks x few points).  A long chunk is cut into segments of `seglen` tokens.
@@ -91,8 +96,11 @@ struct ZipArgs {
 template <int K_>
 struct ZipCfg8 {
     static constexpr int K = K_;
+    static constexpr bool MMA = false;
+    __host__ __device__ static constexpr int slot(int k) { return k; }      // where state k sits in the per-chain arrays (b0, wsum, power table)
     static constexpr int G = 8, CPW = 4;
     static constexpr int KP = (K + 1) & ~1;            // columns padded to an even count (16-byte units)
+    static constexpr int PT = KP;                      // row stride of the power table (spectral form)
     static constexpr int CP = KP / 2;                  // units per row
     static constexpr int RPL = (K + 7) / 8;            // rows per lane
     static constexpr int STRIDE_D = RPL * CP * 16;     // doubles per dictionary matrix
@@ -152,7 +160,7 @@ struct ZipCfg8 {
     // four tokens on the fast path of the GROUP4 shape; w[b] = id | run << 8 (run == 0 in the plain form)
     template <bool SPEC>
     __device__ static __forceinline__ void word4(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
-                                                 const int* pexp, const uint32_t (&w)[4], const Lane& L, int& buf, long long& scale) {
+                                                 const uint32_t (&w)[4], const Lane& L, int& buf, long long& scale) {
         const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the four, remainder row pr
         const uint32_t myw = cj == 0 ? w[0] : (cj == 1 ? w[1] : (cj == 2 ? w[2] : w[3]));
         const int myid = myw & 0xffu;
@@ -164,16 +172,15 @@ struct ZipCfg8 {
         double frem = 1.0;
         if (SPEC) {
             const int ra = (myw >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (myw >> (8 + RUN_LO_BITS));
-            frem = ptab[ra * KP + 8 * FULL + pr] * ptab[rb * KP + 8 * FULL + pr];
-            scale += pexp[ra] + pexp[rb];
+            frem = ptab[ra * PT + 8 * FULL + pr] * ptab[rb * PT + 8 * FULL + pr];
         }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int id = w[b] & 0xffu;
             double* sb = L.sb0 + buf * KP;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
-            const double* pa = ptab + ((w[b] >> 8) & RUN_LO_MASK) * KP + L.q;
-            const double* pb = ptab + (RUN_LO_ROWS + (w[b] >> (8 + RUN_LO_BITS))) * KP + L.q;
+            const double* pa = ptab + ((w[b] >> 8) & RUN_LO_MASK) * PT + L.q;
+            const double* pb = ptab + (RUN_LO_ROWS + (w[b] >> (8 + RUN_LO_BITS))) * PT + L.q;
 #pragma unroll
             for (int k = 0; k < FULL; ++k) {
                 double s0 = 0.0, s1 = 0.0;
@@ -206,13 +213,13 @@ struct ZipCfg8 {
     }
     template <bool PRED, bool SPEC>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
-                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
+                                                uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            const double* pa = ptab + ra * KP;
-            const double* pb = ptab + rb * KP;
+            const double* pa = ptab + ra * PT;
+            const double* pb = ptab + rb * PT;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
@@ -230,7 +237,6 @@ struct ZipCfg8 {
             }
             if (!GROUP4 || L.q < 2) {                       // GROUP4: token exponents are per-pair partial sums
                 scale += dexp[id];
-                if (SPEC) scale += pexp[ra] + pexp[rb];
             }
         }
         __syncwarp();
@@ -257,9 +263,12 @@ struct ZipCfg8 {
 template <int K_>
 struct ZipCfg4 {
     static constexpr int K = K_;
+    static constexpr bool MMA = false;
+    __host__ __device__ static constexpr int slot(int k) { return k; }      // where state k sits in the per-chain arrays (b0, wsum, power table)
     static constexpr int G = 4, CPW = 8;
     static constexpr bool GROUP4 = false;
     static constexpr int KP = (K + 3) & ~3;            // states padded to a multiple of 4
+    static constexpr int PT = KP;
     static constexpr int CP = KP / 2;                  // column pairs per row (even)
     static constexpr int RPL = KP / 4;                 // rows per lane
     static constexpr int STRIDE_D = KP * KP;           // dense
@@ -290,13 +299,13 @@ struct ZipCfg4 {
     __device__ static __forceinline__ int state_of(const Lane& L, int k) { return 2 * ((k >> 1) ^ L.c) + (k & 1); }
     template <bool PRED, bool SPEC>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
-                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
+                                                uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            const double* pa = ptab + ra * KP + L.g;
-            const double* pb = ptab + rb * KP + L.g;
+            const double* pa = ptab + ra * PT + L.g;
+            const double* pb = ptab + rb * PT + L.g;
             const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
             const char* me = mb + L.off_even;
             const char* mo = mb + L.off_odd;
@@ -313,7 +322,6 @@ struct ZipCfg4 {
                 sb[L.g + 4 * k] = SPEC ? (s0 + s1) * (pa[4 * k] * pb[4 * k]) : s0 + s1;
             }
             scale += dexp[id];
-            if (SPEC) scale += pexp[ra] + pexp[rb];
         }
         __syncwarp();
         if (!PRED || active) {
@@ -335,9 +343,12 @@ struct ZipCfg4 {
 template <int K_>
 struct ZipCfg32 {
     static constexpr int K = K_;
+    static constexpr bool MMA = false;
+    __host__ __device__ static constexpr int slot(int k) { return k; }      // where state k sits in the per-chain arrays (b0, wsum, power table)
     static constexpr int G = 32, CPW = 1;
     static constexpr bool GROUP4 = false;
     static constexpr int KP = (K + 1) & ~1;
+    static constexpr int PT = KP;
     static constexpr int CP = KP / 2;
     static constexpr int RPL = (K + 31) / 32;
     static constexpr int STRIDE_D = CP * K * 2;        // dense: K units of 16 bytes per column pair
@@ -358,13 +369,13 @@ struct ZipCfg32 {
     __device__ static __forceinline__ int state_of(const Lane&, int k) { return k; }
     template <bool PRED, bool SPEC>
     __device__ static __forceinline__ void step(double (&al)[KP], const double* dict, const long long* dexp, const double* ptab,
-                                                const int* pexp, uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
+                                                uint32_t w, const Lane& L, int buf, long long& scale, bool active) {
         double* sb = L.sb0 + buf * KP;
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            const double* pa = ptab + ra * KP + L.q;
-            const double* pb = ptab + rb * KP + L.q;
+            const double* pa = ptab + ra * PT + L.q;
+            const double* pb = ptab + rb * PT + L.q;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
@@ -380,7 +391,6 @@ struct ZipCfg32 {
                 }
             }
             scale += dexp[id];
-            if (SPEC) scale += pexp[ra] + pexp[rb];
         }
         __syncwarp();
         if (!PRED || active) {
@@ -394,14 +404,50 @@ struct ZipCfg32 {
     }
 };
 
+// MMA form (spectral form only): the 8 chains of a warp are the ROWS of mma.sync.m8n8k4.f64 tiles, alpha' = alpha M^T,
+// so chains that apply the SAME matrix share it as the B operand.  In run-token streams one entry -- the lone
+// mismatch "1" followed by its run -- is 75-90 % of all tokens: its matrix (the "hot" entry) is held as B fragments in
+// REGISTERS (KT x NT doubles per lane), and a step of the warp is KT x NT DMMAs with no shared-memory traffic for the
+// matrix and no state exchange at all: the D fragment of one step is the A fragment of the next under the state
+// order below (lane q = l % 4 of chain l / 4 holds states 8t + 4e + q in D[t][e], which is column q of k-tile 2t + e).
+// Chains whose token is another entry are served by extra passes with B fragments read from shared memory (entries
+// are stored in fragment order: one conflict-free LDS.64 per tile), one pass per distinct cold entry in the warp.
+// The bound moves from the shared-memory pipe to the FP64 tensor pipe.
+template <int K_>
+struct ZipCfgM {
+    static constexpr int K = K_;
+    static constexpr bool MMA = true;
+    static constexpr int G = 4, CPW = 8;
+    static constexpr bool GROUP4 = false;
+    static constexpr int KT = (K + 3) / 4, NT = (K + 7) / 8;     // k-tiles of 4 input states, n-tiles of 8 output states
+    static constexpr int KP = NT * 8;                            // slots per chain, lane order: t*8 + q*2 + e
+    // power-table rows start at alternating halves of a 128-byte line, so that the two chains of a quarter-warp (64 bytes
+    // each per load) collide only when their rows have the same parity
+    static constexpr int PT = (KP % 16 == 0) ? KP + 8 : KP;
+    static constexpr int STRIDE_D = KT * NT * 32;                // doubles per dictionary entry (fragment order)
+    static constexpr int SBUF_PER_WARP = 0;
+    static constexpr int UNROLL = 1;
+    __host__ __device__ static constexpr int slot(int s) { return (s >> 3) * 8 + (s & 3) * 2 + ((s >> 2) & 1); }
+    // element (row r = output state, column c = input state): tile (u = c/4, t = r/8), lane = n-column * 4 + k-row
+    __host__ __device__ static constexpr int off(int r, int c) {
+        return ((c >> 2) * NT + (r >> 3)) * 32 + (2 * (r & 3) + ((r >> 2) & 1)) * 4 + (c & 3);
+    }
+    __device__ static __forceinline__ void store(double* D, int r, int c, double v) { D[off(r, c)] = v; }
+    struct Lane {
+        int q, grp;
+        __device__ __forceinline__ Lane(int lane, int, double*) { q = lane & 3; grp = lane >> 2; }
+        __device__ __forceinline__ bool writer() const { return q == 0; }
+    };
+};
+
 template <class C, bool SPEC>
 struct ZipSmem {
     // doubles in front of the exchange buffers: plain form E[K][S], spectral form the start vectors b0[S][KP]
     __host__ __device__ static constexpr int se_doubles(int S) { return ((SPEC ? C::KP : C::K) * S + 1) & ~1; }   // keeps what follows 16-byte aligned
-    __host__ __device__ static constexpr int tab_doubles() { return SPEC ? RUN_ROWS * C::KP : 0; }
+    __host__ __device__ static constexpr int tab_doubles() { return SPEC ? RUN_ROWS * C::PT : 0; }
     static size_t bytes(int M, int S, int threads) {
         size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP + tab_doubles();
-        return d * sizeof(double) + (size_t)M * sizeof(long long) + (SPEC ? RUN_ROWS * sizeof(int) : 0) + 4 * sizeof(int);   // dexp[M], pexp, s_point[2] + s_best
+        return d * sizeof(double) + (size_t)M * sizeof(long long) + 4 * sizeof(int);   // dexp[M], s_point[2] + s_best
     }
     static int max_entries(size_t budget, int S, int threads) {
         const size_t fixed = bytes(0, S, threads);
@@ -438,12 +484,11 @@ __device__ __forceinline__ void zip_rescale(double (&al)[C::KP], long long& scal
 //   plain form:     base entries C_s[r][c] = E[r][s] T[c][r];  sE = E, spi = pi
 //   spectral form:  base entries R_s = V^-1 C_s V from zip_spectral_kernel;  sE = start vectors b0[s] = V^-1 (pi o E[:,s]),
 //                   spi = wsum = V^T 1 (so that sum(alpha) = wsum . beta), and the power table
-//                   ptab[a]      = lambda^a        (a < 2^RUN_LO_BITS)
-//                   ptab[LO + b] = lambda^(b << RUN_LO_BITS)
-//                   each row scaled by an exact power of two, 2^-pexp[row], so that its largest entry is in [1,2)
+//                   ptab[a]      = (lambda / lambda_max)^a        (a < 2^RUN_LO_BITS)
+//                   ptab[LO + b] = (lambda / lambda_max)^(b << RUN_LO_BITS)
 template <class C, int THREADS, bool SPEC>
 __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, double* dict, double* sE, double* spi, long long* dexp,
-                                                     double* ptab, int* pexp) {
+                                                     double* ptab) {
     constexpr int KP = C::KP, NW = THREADS / 32;
     const int K = a.K;          // actual state count <= C::K (the kernel's tile); rows / columns beyond it stay zero
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -454,21 +499,20 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
     const double* sp = SPEC ? a.spec + (size_t)n * a.spec_stride : nullptr;     // lambda[K], wsum[K], b0[S][K], R[S][K][K]
     for (int x = tid; x < M * C::STRIDE_D; x += THREADS) dict[x] = 0.0;
     if (SPEC) {
-        for (int x = tid; x < S * KP; x += THREADS) { const int s = x / KP, k = x - s * KP; sE[x] = k < K ? sp[2 * K + s * K + k] : 0.0; }
-        for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? sp[K + x] : 0.0;
-        // power table: with rho_k = lambda_k / lambda_max (|rho| <= 1) and p the row's exponent,
-        // lambda_k^p = rho_k^p * 2^(p log2 lambda_max); the integer part of p log2 lambda_max goes to pexp
+        for (int x = tid; x < S * KP; x += THREADS) sE[x] = 0.0;
+        for (int x = tid; x < KP; x += THREADS) spi[x] = 0.0;
+        for (int x = tid; x < RUN_ROWS * C::PT; x += THREADS) ptab[x] = 0.0;
+        __syncthreads();
+        for (int x = tid; x < S * K; x += THREADS) { const int s = x / K, k = x - s * K; sE[s * KP + C::slot(k)] = sp[2 * K + x]; }
+        for (int x = tid; x < K; x += THREADS) spi[C::slot(x)] = sp[K + x];
+        // power table: rows hold rho_k^p with rho_k = lambda_k / lambda_max (|rho| <= 1, the dominant entry exactly 1); the
+        // common factor lambda_max^(all run sites of the chunk) is added to the result analytically (ZipChunk::run_sites)
         double lmax = 0.0;
         for (int k = 0; k < K; ++k) lmax = fmax(lmax, fabs(sp[k]));
-        const double l2 = log2(lmax);
-        for (int x = tid; x < RUN_ROWS * KP; x += THREADS) {
-            const int row = x / KP, k = x - row * KP;
+        for (int x = tid; x < RUN_ROWS * K; x += THREADS) {
+            const int row = x / K, k = x - row * K;
             const double p = row < RUN_LO_ROWS ? (double)row : (double)((row - RUN_LO_ROWS) << RUN_LO_BITS);
-            const double xe = p * l2, fe = floor(xe);
-            double v = 0.0;
-            if (k < K) v = exp2(xe - fe) * (p == 0.0 ? 1.0 : pow(sp[k] / lmax, p));
-            ptab[x] = v;
-            if (k == 0) pexp[row] = (int)fe;
+            ptab[row * C::PT + C::slot(k)] = p == 0.0 ? 1.0 : pow(sp[k] / lmax, p);
         }
     } else {
         for (int x = tid; x < K * S; x += THREADS) sE[x] = Eg[x];
@@ -526,7 +570,7 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
 // unit*CPW .. unit*CPW + CPW-1 of the sorted chunk list.
 template <class C, bool SPEC>
 __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
-                                             const double* spi, const long long* dexp, const double* ptab, const int* pexp,
+                                             const double* spi, const long long* dexp, const double* ptab,
                                              const typename C::Lane& L) {
     constexpr int KP = C::KP;
     constexpr int BLK = SPEC ? 8 : 16;        // tokens per block (two / one 16-byte loads); the state is rescaled every 8 tokens
@@ -567,9 +611,8 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 const int st = C::state_of(L, k);
-                al[k] *= ptab[ra * KP + st] * ptab[rb * KP + st];
+                al[k] *= ptab[ra * C::PT + st] * ptab[rb * C::PT + st];
             }
-            scale += pexp[ra] + pexp[rb];
         }
     } else if (have) {         // every lane of the chain waits for the predecessor piece itself, then reads what it left
         while (*((volatile int*)prog) < seg) __nanosleep(200);
@@ -599,19 +642,19 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
             if (__all_sync(0xffffffffu, rem >= BLK)) {
                 if constexpr (C::GROUP4) {
                     const uint32_t w0[4] = {w[0], w[1], w[2], w[3]}, w1[4] = {w[4], w[5], w[6], w[7]};
-                    C::template word4<true>(al, dict, dexp, ptab, pexp, w0, L, buf, tscale);
-                    C::template word4<true>(al, dict, dexp, ptab, pexp, w1, L, buf, tscale);
+                    C::template word4<true>(al, dict, dexp, ptab, w0, L, buf, tscale);
+                    C::template word4<true>(al, dict, dexp, ptab, w1, L, buf, tscale);
                 } else {
 #pragma unroll C::UNROLL
                     for (int b = 0; b < 8; ++b) {
-                        C::template step<false, true>(al, dict, dexp, ptab, pexp, w[b], L, buf, tscale, true);
+                        C::template step<false, true>(al, dict, dexp, ptab, w[b], L, buf, tscale, true);
                         buf ^= 1;
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int b = 0; b < 8; ++b) {
-                    C::template step<true, true>(al, dict, dexp, ptab, pexp, w[b], L, buf, tscale, b < rem);
+                    C::template step<true, true>(al, dict, dexp, ptab, w[b], L, buf, tscale, b < rem);
                     buf ^= 1;
                 }
             }
@@ -624,11 +667,11 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
                     uint32_t wv = w[wi];
                     if constexpr (C::GROUP4) {
                         const uint32_t w4[4] = {wv & 0xffu, (wv >> 8) & 0xffu, (wv >> 16) & 0xffu, wv >> 24};
-                        C::template word4<false>(al, dict, dexp, ptab, pexp, w4, L, buf, tscale);
+                        C::template word4<false>(al, dict, dexp, ptab, w4, L, buf, tscale);
                     } else {
 #pragma unroll C::UNROLL
                         for (int b = 0; b < 4; ++b) {
-                            C::template step<false, false>(al, dict, dexp, ptab, pexp, wv & 0xffu, L, buf, tscale, true);
+                            C::template step<false, false>(al, dict, dexp, ptab, wv & 0xffu, L, buf, tscale, true);
                             wv >>= 8;
                             buf ^= 1;
                         }
@@ -641,7 +684,7 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
                     uint32_t wv = w[wi];
 #pragma unroll 1
                     for (int b = 0; b < 4; ++b) {
-                        C::template step<true, false>(al, dict, dexp, ptab, pexp, wv & 0xffu, L, buf, tscale, wi * 4 + b < rem);
+                        C::template step<true, false>(al, dict, dexp, ptab, wv & 0xffu, L, buf, tscale, wi * 4 + b < rem);
                         wv >>= 8;
                         buf ^= 1;
                     }
@@ -689,7 +732,225 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
     }
     double result;
     if (dead || !(sum > 0.0)) result = bad ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
-    else result = log(sum) + (double)scale * LN2;
+    else {
+        result = log(sum) + (double)scale * LN2;
+        if (SPEC) result += (double)ch.run_sites * __ldg(a.spec + (size_t)n * a.spec_stride + a.spec_stride - 1);     // ln(lambda_max) per run site
+    }
+    if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
+}
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ long long lds_s64(uint32_t addr) {
+    long long v;
+    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+// The same work unit in the MMA form (ZipCfgM, spectral form only): 8 chains per warp, state in the D / A fragments.
+template <class C>
+__device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
+                                                 const double* spi, const long long* dexp, const double* ptab,
+                                                 const double (&Bh)[C::KT][C::NT], const typename C::Lane& L) {
+    constexpr int KP = C::KP, KT = C::KT, NT = C::NT, PT = C::PT;
+    const int K = a.K, lane = threadIdx.x & 31, hot = a.hot_id;
+    int seg = 0, quad = unit;
+    if (a.nseg > 1) {
+        const int nquads = (a.nchunks + C::CPW - 1) / C::CPW;
+        seg = unit / nquads;
+        quad = unit - seg * nquads;
+    }
+    const int ci = quad * C::CPW + L.grp;
+    const bool have = ci < a.nchunks;
+    const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
+    const int tok0 = seg * a.seglen;
+    const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
+    const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + (size_t)tok0 * 4);
+    int maxnt = nt;
+#pragma unroll
+    for (int m = 16; m >= C::G; m >>= 1) maxnt = max(maxnt, __shfl_xor_sync(0xffffffffu, maxnt, m));
+
+    double D[NT][2];           // D[t][e]: state 8t + 4e + q of this lane's chain (slot t*8 + 2q + e of the per-chain arrays)
+    long long scale = 0;
+    bool dead = false, isnan = false;
+    double* carry = a.carry + ((size_t)n * a.nchunks + (have ? ci : 0)) * a.carry_stride;
+    int* prog = a.progress + (size_t)n * a.nchunks + (have ? ci : 0);
+    if (seg == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (ch.first_sym >= 0) {
+                const double2 v = *reinterpret_cast<const double2*>(sE + ch.first_sym * KP + t * 8 + 2 * L.q);
+                D[t][0] = v.x; D[t][1] = v.y;
+            } else {
+                const int c = -1 - ch.first_sym;
+                D[t][0] = 8 * t + L.q == c ? 1.0 : 0.0;
+                D[t][1] = 8 * t + 4 + L.q == c ? 1.0 : 0.0;
+            }
+        }
+        if (ch.first_run > 0) {
+            const int ra = ch.first_run & RUN_LO_MASK, rb = RUN_LO_ROWS + (ch.first_run >> RUN_LO_BITS);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double2 fa = *reinterpret_cast<const double2*>(ptab + ra * PT + t * 8 + 2 * L.q);
+                const double2 fb = *reinterpret_cast<const double2*>(ptab + rb * PT + t * 8 + 2 * L.q);
+                D[t][0] *= fa.x * fb.x; D[t][1] *= fa.y * fb.y;
+            }
+        }
+    } else if (have) {
+        while (*((volatile int*)prog) < seg) __nanosleep(200);
+        __threadfence();
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { D[t][0] = __ldcg(carry + t * 8 + 2 * L.q); D[t][1] = __ldcg(carry + t * 8 + 2 * L.q + 1); }
+        scale = (long long)__ldcg(carry + KP);
+        const int fl = (int)__ldcg(carry + KP + 1);
+        dead = fl & 1;
+        isnan = fl & 2;
+    } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { D[t][0] = 0.0; D[t][1] = 0.0; }
+    }
+    // shared-memory addresses of what a step reads, as 32-bit registers the compiler cannot rematerialise from the kernel
+    // arguments every step (it did: ~25 integer instructions per step in an issue-bound loop)
+    uint32_t ptab_s = (uint32_t)__cvta_generic_to_shared(ptab) + 16u * L.q;      // this lane's column pair of a table row
+    uint32_t dict_s = (uint32_t)__cvta_generic_to_shared(dict) + 8u * lane;      // this lane's element of a fragment tile
+    uint32_t dexp_s = (uint32_t)__cvta_generic_to_shared(dexp);
+    asm volatile("" : "+r"(ptab_s), "+r"(dict_s), "+r"(dexp_s));
+    unsigned passes = 0;
+    // one token of every chain of the warp; ALL: every chain has one (no predicates)
+    auto step = [&](uint32_t wb, bool active, auto all_tag) {
+        constexpr bool ALL = decltype(all_tag)::value;
+        if (!ALL && !active) wb = 0u;
+        const int id = wb & 0xffu;
+        const uint32_t pa = ptab_s + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = ptab_s + (RUN_LO_ROWS + (wb >> (8 + RUN_LO_BITS))) * (PT * 8);
+        double2 fa[NT], fb[NT];            // (lambda / lambda_max)^n of this token for the lane's states: independent of the products below
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { fa[t] = lds_f64x2(pa + t * 64); fb[t] = lds_f64x2(pb + t * 64); }
+        const long long ex = lds_s64(dexp_s + id * 8);
+        const bool is_cold = (ALL || active) && id != hot;
+        unsigned cold = __ballot_sync(0xffffffffu, is_cold);
+        ++passes;
+        double N[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { N[t][0] = 0.0; N[t][1] = 0.0; }
+#pragma unroll
+        for (int u = 0; u < KT; ++u)       // hot pass, unconditionally: a warp without a single hot chain is rare
+#pragma unroll
+            for (int t = 0; t < NT; ++t) dmma884(N[t][0], N[t][1], D[u >> 1][u & 1], Bh[u][t]);
+        while (cold) {                     // one pass per distinct cold entry among the warp's chains
+            const int idc = __shfl_sync(0xffffffffu, id, __ffs(cold) - 1);
+            const bool mine = is_cold && id == idc;
+            cold &= ~__ballot_sync(0xffffffffu, mine);
+            ++passes;
+            const uint32_t bc = dict_s + idc * (C::STRIDE_D * 8);
+            double Cc[NT][2];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { Cc[t][0] = 0.0; Cc[t][1] = 0.0; }
+#pragma unroll
+            for (int u = 0; u < KT; ++u)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) dmma884(Cc[t][0], Cc[t][1], D[u >> 1][u & 1], lds_f64(bc + (u * NT + t) * 256));
+            if (mine) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { N[t][0] = Cc[t][0]; N[t][1] = Cc[t][1]; }
+            }
+        }
+        if (ALL || active) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { D[t][0] = N[t][0] * (fa[t].x * fb[t].x); D[t][1] = N[t][1] * (fa[t].y * fb[t].y); }
+            scale += ex;
+        }
+    };
+    uint4 cur = make_uint4(0, 0, 0, 0), cur2 = cur;
+    if (nt > 0) { cur = tp[0]; cur2 = tp[1]; }
+    for (int blk = 0; blk * 8 < maxnt; ++blk) {
+        uint4 nxt = make_uint4(0, 0, 0, 0), nxt2 = nxt;
+        if ((blk + 1) * 8 < nt) { nxt = tp[2 * blk + 2]; nxt2 = tp[2 * blk + 3]; }
+        const int rem = nt - blk * 8;
+        const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, cur2.x, cur2.y, cur2.z, cur2.w};
+        if (__all_sync(0xffffffffu, rem >= 8)) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) step(w[b], true, std::true_type());
+        } else {
+#pragma unroll 1
+            for (int b = 0; b < 8; ++b) {
+                const uint32_t wb = b == 0 ? w[0] : (b == 1 ? w[1] : (b == 2 ? w[2] : (b == 3 ? w[3] : (b == 4 ? w[4] : (b == 5 ? w[5] : (b == 6 ? w[6] : w[7]))))));
+                step(wb, b < rem, std::false_type());
+            }
+        }
+        {   // exact power-of-two rescale of every chain (4 lanes each)
+            double sum = 0.0, mx = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double v0 = fabs(D[t][0]), v1 = fabs(D[t][1]);
+                sum += v0 + v1;
+                mx = fmax(mx, fmax(v0, v1));
+            }
+            sum += shfl_xor_f64(sum, 1); sum += shfl_xor_f64(sum, 2);
+            mx = fmax(mx, shfl_xor_f64(mx, 1)); mx = fmax(mx, shfl_xor_f64(mx, 2));
+            if (sum > 0.0 && sum < 1.7e308) {
+                const int e = exponent_of(mx);
+                const double f = pow2_neg(e);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { D[t][0] *= f; D[t][1] *= f; }
+                scale += e;
+            } else if (rem > 0) {
+                dead = true;
+                isnan = isnan || (sum != sum) || (sum > 0.0);
+            }
+        }
+        cur = nxt;
+        cur2 = nxt2;
+    }
+    if (lane == 0 && a.mma_passes) atomicAdd(a.mma_passes, (unsigned long long)passes);
+    if (a.nseg > 1 && seg < a.nseg - 1) {       // hand the state on to the next piece
+        if (have) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { __stcg(carry + t * 8 + 2 * L.q, D[t][0]); __stcg(carry + t * 8 + 2 * L.q + 1, D[t][1]); }
+            if (L.writer()) {
+                __stcg(carry + KP, (double)scale);
+                __stcg(carry + KP + 1, (double)((dead ? 1 : 0) | (isnan ? 2 : 0)));
+            }
+            __threadfence();
+        }
+        __syncwarp();                            // all four lanes of a chain have published their part
+        if (have && L.writer()) *((volatile int*)prog) = seg + 1;
+        return;
+    }
+    double sum = 0.0, mag = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const double2 wv = *reinterpret_cast<const double2*>(spi + t * 8 + 2 * L.q);
+        sum = fma(wv.x, D[t][0], fma(wv.y, D[t][1], sum));
+        mag += fabs(D[t][0]) + fabs(D[t][1]);
+    }
+    sum += shfl_xor_f64(sum, 1); sum += shfl_xor_f64(sum, 2);
+    mag += shfl_xor_f64(mag, 1); mag += shfl_xor_f64(mag, 2);
+    const bool bad = isnan || sum != sum || mag != mag;
+    if (a.vec_out) {
+        if (have) {
+            double* out = a.vec_out + ((size_t)n * a.nchunks + ch.out_index) * a.vec_stride;
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int st = 8 * t + 4 * e + L.q;
+                    if (st < K) out[st] = bad ? __longlong_as_double(0x7ff8000000000000LL) : (dead ? 0.0 : D[t][e]);
+                }
+            if (L.writer()) out[K] = (double)scale;
+        }
+        return;
+    }
+    double result;
+    if (dead || !(sum > 0.0)) result = bad ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
+    else result = log(sum) + (double)scale * LN2 + (double)ch.run_sites * __ldg(a.spec + (size_t)n * a.spec_stride + a.spec_stride - 1);
     if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
 }
 
@@ -709,13 +970,13 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     double* sbuf = spi + KP;                          // [THREADS/32][SBUF_PER_WARP]
     double* ptab = sbuf + (THREADS / 32) * C::SBUF_PER_WARP;            // spectral: [RUN_ROWS][KP]
     long long* dexp = reinterpret_cast<long long*>(ptab + ZipSmem<C, SPEC>::tab_doubles());   // [M] (64-bit: an entry can span millions of sites)
-    int* pexp = reinterpret_cast<int*>(dexp + M);     // spectral: [RUN_ROWS]
-    int* s_point = pexp + (SPEC ? RUN_ROWS : 0);
+    int* s_point = reinterpret_cast<int*>(dexp + M);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const typename C::Lane L(lane, warp, sbuf);
-    for (int x = tid; x < (THREADS / 32) * C::SBUF_PER_WARP; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
     const int NP = a.pcount ? *a.pcount : a.N;         // points served by this launch
+    if (NP <= 0) return;                               // (the plain-form pass of a spectral call is usually empty)
+    for (int x = tid; x < (THREADS / 32) * C::SBUF_PER_WARP; x += THREADS) sbuf[x] = 0.0;   // padding entries stay 0
     const int nunits = (a.nchunks + C::CPW - 1) / C::CPW * (a.nseg > 1 ? a.nseg : 1);
     int primary = blockIdx.x;          // next point of this CTA's own share
     int scan = NP > 0 ? (int)(((long long)blockIdx.x * 7919) % NP) : 0;   // where the search for points to help starts
@@ -744,13 +1005,28 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
         if (slot == -1) break;
         if (slot == -2) continue;
         const int n = a.plist ? a.plist[slot] : slot;
-        zip_build_dictionary<C, THREADS, SPEC>(a, n, dict, sE, spi, dexp, ptab, pexp);
-        for (; warp < a.active_warps;) {
-            int unit = 0;
-            if (lane == 0) unit = atomicAdd(a.point_next + slot, 1);
-            unit = __shfl_sync(0xffffffffu, unit, 0);
-            if (unit >= nunits) break;
-            zip_run_unit<C, SPEC>(a, n, unit, dict, sE, spi, dexp, ptab, pexp, L);
+        zip_build_dictionary<C, THREADS, SPEC>(a, n, dict, sE, spi, dexp, ptab);
+        if constexpr (C::MMA) {
+            double Bh[C::KT][C::NT];       // the hot entry's B fragments
+#pragma unroll
+            for (int u = 0; u < C::KT; ++u)
+#pragma unroll
+                for (int t = 0; t < C::NT; ++t) Bh[u][t] = dict[(size_t)a.hot_id * C::STRIDE_D + (u * C::NT + t) * 32 + lane];
+            for (; warp < a.active_warps;) {
+                int unit = 0;
+                if (lane == 0) unit = atomicAdd(a.point_next + slot, 1);
+                unit = __shfl_sync(0xffffffffu, unit, 0);
+                if (unit >= nunits) break;
+                zip_run_unit_mma<C>(a, n, unit, dict, sE, spi, dexp, ptab, Bh, L);
+            }
+        } else {
+            for (; warp < a.active_warps;) {
+                int unit = 0;
+                if (lane == 0) unit = atomicAdd(a.point_next + slot, 1);
+                unit = __shfl_sync(0xffffffffu, unit, 0);
+                if (unit >= nunits) break;
+                zip_run_unit<C, SPEC>(a, n, unit, dict, sE, spi, dexp, ptab, L);
+            }
         }
     }
 }
@@ -761,7 +1037,8 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
 //     C_r = diag(E[:,r]) T^T = W A W^-1,   A[i][j] = sqrt(E[i,r] E[j,r]) J[i][j] / sqrt(pi_i pi_j)   symmetric,
 //     A = Q Lambda Q^T  (cyclic Jacobi, K <= 64),   V = W Q,  V^-1 = Q^T W^-1,
 //     C_s = diag(E[:,s] / E[:,r]) C_r   =>   R_s = V^-1 C_s V = (Q^T diag(E[:,s]/E[:,r]) Q) Lambda,   R_r = Lambda.
-// Written per point (spec_stride doubles): lambda[K], wsum[K] = V^T 1 = Q^T w, b0[S][K] = V^-1 (pi o E[:,s]), R[S][K][K].
+// Written per point (spec_stride doubles): lambda[K], wsum[K] = V^T 1 = Q^T w, b0[S][K] = V^-1 (pi o E[:,s]), R[S][K][K],
+// ln(lambda_max) in the last slot.
 // A point is served by the spectral kernel only if all of this is sound: pi, E[:,r] > 0, J symmetric to 1e-13, Jacobi
 // converged, lambda_max > 0; such points are appended to ok_list, the others to bad_list (plain form of the kernel).
 // ------------------------------------------------------------------------------------------------
@@ -886,6 +1163,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
             double lmax = 0.0, lpos = 0.0;
             for (int k = 0; k < K; ++k) { lmax = fmax(lmax, fabs(A[k * LD + k])); lpos = fmax(lpos, A[k * LD + k]); }
             if (!flag[1] || !(lmax > 0.0) || !(lpos >= lmax) || !(lmax < 1.7e308)) flag[0] = 0;     // the dominant eigenvalue must be the positive one
+            else out[s.spec_stride - 1] = log(lmax);
         }
         __syncthreads();
     }
@@ -938,6 +1216,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
 struct ZipFoldItem {
     int start, first_cols, nfold, out_index;
     int src, dst;        // src: 0 = vec (kernel output), 1 = vec2 (level-1 output)
+    int run_sites;       // dst == 0, spectral form: run sites of the whole chunk (see ZipChunk)
+    int pad;
 };
 
 // Spectral form (spec != NULL): the vectors are coordinates in the eigenbasis of C_r -- entries of either sign, measured
@@ -1004,7 +1284,7 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
         double r;
         if (sum != sum) r = sum;
         else if (!(sum > 0.0)) r = -INFINITY;
-        else r = log(sum) + scale * LN2;
+        else r = log(sum) + scale * LN2 + (spec ? (double)it.run_sites * spec[(size_t)n * spec_stride + spec_stride - 1] : 0.0);
         chain_out[(size_t)n * out_stride + it.out_index] = r;
     }
 }

@@ -203,6 +203,10 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       every model of the reference guarantees, transitions.py:231-246); points that do not qualify are
  *                       served by the plain form in the same call.  0 = auto (where run tokens are >= 15 % fewer than
  *                       dictionary tokens), 1 = always, 2 = never.
+ * key "zip_mma":        MMA shape of the spectral form (state counts >= 7): the eight chains of a warp are the rows of
+ *                       mma.sync.m8n8k4.f64 tiles and the most frequent entry's matrix is held as B fragments in registers,
+ *                       so a step moves no matrix through shared memory; chains on other entries take one extra pass per
+ *                       distinct entry.  0 = auto (where one entry is >= 50 % of the run tokens), 1 = always, 2 = never.
  * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).
  * key "comm_fused", "comm_enabled": see the multi-GPU section above.
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
@@ -215,9 +219,13 @@ int imc_get_option(const char* key, int64_t* value_out);
 int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t imc_kernel_launches(void);
+/* MMA passes executed by this process so far (each = KT x NT mma.sync.m8n8k4.f64 of 512 flop per warp, KT = ceil(K/4),
+ * NT = ceil(K/8)): the executed FP64 tensor work behind bench.py's roofline.  Synchronises the device. */
+int imc_mma_passes(int64_t* passes_out);
 /* name of the forward kernel chosen by the last forward call on this thread
  * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls;
- * "zip-spectral", "zip-spectral-segmented", "zip-spectral-warp": the same three shapes over run tokens) */
+ * "zip-spectral", "zip-spectral-segmented", "zip-spectral-warp": the same three shapes over run tokens;
+ * "zip-spectral-mma", "zip-spectral-mma-segmented": the MMA shape of the spectral form) */
 const char* imc_last_forward_kernel(void);
 
 #ifdef __cplusplus

@@ -17,6 +17,7 @@ def _options():
     import imcoalhmm_b200 as m
     yield
     m.set_option("zip_spectral", 0)
+    m.set_option("zip_mma", 0)
     m.set_option("forward_kernel", 0)
 
 
@@ -41,10 +42,15 @@ def test_full_size_properties(full_c2):
     info = whole_set.zip_info(10)
     assert info["tokens"] * 100 < whole_set.total_sites            # > 100x compression on this alignment
     whole = whole_set.forward_batch(pis, Ts, Es)
-    assert m.last_forward_kernel() == "zip-spectral" and np.isfinite(whole).all()      # the automatic choice on this alignment
+    assert m.last_forward_kernel() == "zip-spectral-mma" and np.isfinite(whole).all()      # the automatic choice on this alignment
     assert whole_set.spectral_counts() == (256, 0)
     assert whole_set.run_info(10)["tokens"] * 250 < whole_set.total_sites  # > 250 sites per mat-vec
-    # the plain form (pair dictionary, no eigenbasis) on the same 1e8 sites
+    # the FMA shape of the spectral form, then the plain form (pair dictionary, no eigenbasis), on the same 1e8 sites
+    m.set_option("zip_mma", 2)
+    fma_form = whole_set.forward_batch(pis, Ts, Es)
+    assert m.last_forward_kernel() == "zip-spectral"
+    m.set_option("zip_mma", 0)
+    np.testing.assert_allclose(fma_form, whole, rtol=1e-12)
     m.set_option("zip_spectral", 2)
     plain_form = whole_set.forward_batch(pis, Ts, Es)
     assert m.last_forward_kernel() == "zip"
@@ -69,7 +75,7 @@ def test_full_size_properties(full_c2):
     np.testing.assert_allclose(bw, fw, rtol=1e-11)
     # single-point calls take the segmented route and must agree with the batch
     one = whole_set.forward(pis[3], Ts[3], Es[3])
-    assert m.last_forward_kernel() == "zip-spectral-segmented"
+    assert m.last_forward_kernel().startswith("zip-spectral") and m.last_forward_kernel().endswith("segmented")
     assert one == pytest.approx(whole[3], rel=1e-12)
 
 
@@ -97,7 +103,7 @@ def test_full_size_im_model_shard():
     mk = lambda cs: m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in cs])
     whole_set = mk(chunks)
     whole = whole_set.forward_batch(pis, Ts, Es)
-    assert m.last_forward_kernel() == "zip-spectral" and np.isfinite(whole).all()
+    assert m.last_forward_kernel() == "zip-spectral-mma" and np.isfinite(whole).all()
     m.set_option("zip_spectral", 2)
     plain_form = whole_set.forward_batch(pis[:64], Ts[:64], Es[:64])
     assert m.last_forward_kernel() == "zip"
@@ -113,6 +119,6 @@ def test_full_size_im_model_shard():
         m.set_option("forward_kernel", 0)
     np.testing.assert_allclose(plain, whole[:64], rtol=1e-11)
     one = whole_set.forward(pis[5], Ts[5], Es[5])
-    assert m.last_forward_kernel() in ("zip-spectral-warp", "zip-spectral-segmented")
+    assert m.last_forward_kernel() in ("zip-spectral-warp", "zip-spectral-segmented", "zip-spectral-mma-segmented")
     assert one == pytest.approx(whole[5], rel=1e-12)
     np.testing.assert_allclose(model.batched_log_likelihood(thetas[:32], whole_set), whole[:32], rtol=1e-12)

@@ -7,7 +7,7 @@ from conftest import golden_model, example_symbols, random_hmm
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-11
-OPTS = ("forward_kernel", "zip_ctas_per_sm", "zip_max_entries", "zip_lanes", "zip_segment_tokens", "zip_pipeline",
+OPTS = ("forward_kernel", "zip_ctas_per_sm", "zip_max_entries", "zip_lanes", "zip_segment_tokens", "zip_pipeline", "zip_mma",
         "zip_spectral", "zip_spectral_force_bad")
 
 
@@ -80,11 +80,17 @@ def test_reference_models_all_shapes(model):
     if K <= 24:
         shapes.append(dict(zip_segment_tokens=-1, zip_ctas_per_sm=2))
     shapes.append(dict(zip_max_entries=5, zip_segment_tokens=-1))
+    shapes = [dict(o, zip_mma=2) for o in shapes]                      # the FMA shapes ...
+    if K >= 7:                                                        # ... and the MMA form (tiles >= 8): whole chunks, pieces, segments
+        shapes += [dict(zip_mma=1, zip_segment_tokens=-1, zip_pipeline=1), dict(zip_mma=1, zip_segment_tokens=-1, zip_pipeline=5),
+                   dict(zip_mma=1, zip_segment_tokens=256), dict(zip_mma=1, zip_segment_tokens=-1, zip_max_entries=4), dict(zip_mma=0)]
     for opts in shapes:
-        for k in OPTS[1:6]:
+        for k in OPTS[1:7]:
             m.set_option(k, opts.get(k, 0))
         got = s.forward_batch(pis, Ts, Es)
         assert m.last_forward_kernel().startswith("zip-spectral"), m.last_forward_kernel()
+        if opts.get("zip_mma") == 1:
+            assert "mma" in m.last_forward_kernel(), m.last_forward_kernel()
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="%s %s" % (model, opts))
         assert s.spectral_counts() == (len(pis), 0)
         one = s.forward(pis[-1], Ts[-1], Es[-1])
@@ -106,6 +112,14 @@ def test_random_reversible_hmms_every_tile(K):
         np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d lanes=%d" % (K, lanes))
         assert s.spectral_counts() == (6, 0)
     m.set_option("zip_lanes", 0)
+    if K >= 7:
+        m.set_option("zip_mma", 1)
+        for seg in (-1, 128):
+            m.set_option("zip_segment_tokens", seg)
+            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d mma seg=%d" % (K, seg))
+            assert "mma" in m.last_forward_kernel() and s.spectral_counts() == (6, 0)
+        m.set_option("zip_mma", 0)
+        m.set_option("zip_segment_tokens", 0)
     np.testing.assert_allclose(s.forward_batch(pis[:1], Ts[:1], Es[:1]), want[:1], rtol=RTOL)     # chain-scarce shapes
 
 
@@ -124,9 +138,10 @@ def test_mixed_batch_reversible_and_not():
     want = oracle_batch(chunks, pis, Ts, Es)
     s = make_set(chunks)
     m.set_option("zip_spectral", 1)
-    for seg in (-1, 0, 512):
+    for seg, mma in ((-1, 2), (0, 2), (512, 2), (-1, 1), (512, 1), (0, 0)):
         m.set_option("zip_segment_tokens", seg)
-        np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="seg=%d" % seg)
+        m.set_option("zip_mma", mma)
+        np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="seg=%d mma=%d" % (seg, mma))
         ok, plain = s.spectral_counts()
         assert (ok, plain) == (7, 5)
     m.set_option("zip_spectral_force_bad", 1)

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "imc_model_destroy": (ctypes.c_int, [c_vp]),
     "imc_model_build_batch": (ctypes.c_int, [c_vp, ctypes.c_int, c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]),
     "imc_model_build_batch_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "imc_break_points": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_f64p]),
+    "imc_model_break_points": (ctypes.c_int, [c_vp, ctypes.c_int, c_f64p, c_f64p]),
     "imc_loglik_batch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_f64p, c_f64p, c_i32p]),
     "imc_loglik_batch_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "imc_statespace_describe": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),

@@ -169,6 +169,14 @@ extern "C" int imc_statespace_describe(int space, int* n_states, int* n_edges, i
     return IMC_OK;
 }
 
+// ---- break points (break_points.py:9-30, 60-78, 81-108).  The same expressions feed the models' constant tables below
+// (c_exp_a[i] = bp_exp_unit, c_psmc[i] = bp_psmc_unit at the defaults) and model_params_kernel's per-point arithmetic
+// (unit / coal_rate + offset; (i / n) * (end - start) + start).
+static inline double bp_exp_unit(int i, int n) { return -std::log1p(-(double)i / n); }                 // scipy expon.ppf(i / n)
+static inline double bp_psmc_unit(int i, int n, double t_max, double mu) {
+    return i == 0 ? 0.0 : 0.1 * (std::exp((double)i / n * std::log(1 + 10 * t_max * mu)) - 1.0);
+}
+
 extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams, imc_model** out) {
     using namespace imc;
     if (!out || (n_iparams > 0 && !iparams)) return fail(IMC_ERR_INVALID, "NULL argument");
@@ -184,7 +192,7 @@ extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams,
             m->interval_space.assign(m->K, SP_SINGLE);
             m->interval_epoch.assign(m->K, 0);
             m->initial_state = host_space(SP_ISO).i12;
-            for (int i = 0; i < m->K; ++i) m->c_exp_a.push_back(-std::log1p(-(double)i / m->K));
+            for (int i = 0; i < m->K; ++i) m->c_exp_a.push_back(bp_exp_unit(i, m->K));
             break;
         case MODEL_IM:              // iparams = {no_mig_states, no_ancestral_states}
             if (n_iparams != 2 || iparams[0] < 2 || iparams[1] < 1)
@@ -194,7 +202,7 @@ extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams,
             for (int i = 0; i < m->K; ++i) m->interval_space.push_back(i < m->n_mig ? SP_MIG : SP_SINGLE);
             m->interval_epoch.assign(m->K, 0);
             m->initial_state = host_space(SP_ISO).i12;
-            for (int i = 0; i < m->n_anc; ++i) m->c_exp_a.push_back(-std::log1p(-(double)i / m->n_anc));
+            for (int i = 0; i < m->n_anc; ++i) m->c_exp_a.push_back(bp_exp_unit(i, m->n_anc));
             break;
         case MODEL_PSMC_ISO:        // iparams = {est_split, n_epochs, intervals...}
         case MODEL_VARMIG: {        // iparams = {initial_configuration, n_epochs, intervals...}
@@ -220,7 +228,7 @@ extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams,
             }
             // psmc_break_points(K, t_max=15, mu=1e-9) with offset 0 (break_points.py:81-108)
             for (int i = 0; i < m->K; ++i)
-                m->c_psmc.push_back(i == 0 ? 0.0 : 0.1 * (std::exp((double)i / m->K * std::log(1 + 10 * 15 * 1e-9)) - 1.0));
+                m->c_psmc.push_back(bp_psmc_unit(i, m->K, 15, 1e-9));
             break;
         }
         case MODEL_IM_EPOCHS:       // iparams = {no_epochs, no_mig_states, no_ancestral_states}
@@ -231,7 +239,7 @@ extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams,
             for (int i = 0; i < m->K; ++i) m->interval_space.push_back(i < m->n_epochs * m->n_mig ? SP_MIG : SP_SINGLE);
             m->interval_epoch.assign(m->K, 0);
             m->initial_state = host_space(SP_ISO).i12;
-            for (int i = 0; i < m->n_epochs * m->n_anc; ++i) m->c_exp_a.push_back(-std::log1p(-(double)i / (m->n_epochs * m->n_anc)));
+            for (int i = 0; i < m->n_epochs * m->n_anc; ++i) m->c_exp_a.push_back(bp_exp_unit(i, m->n_epochs * m->n_anc));
             break;
         default:
             return bad("unknown model kind");
@@ -244,6 +252,20 @@ extern "C" int imc_model_create(int kind, const int32_t* iparams, int n_iparams,
     }
     m->p_stride = off;
     *out = m;
+    return IMC_OK;
+}
+
+
+extern "C" int imc_break_points(int kind, int no_intervals, double a, double b, double c, double* out) {
+    if (!out || no_intervals < 1) return fail(IMC_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < no_intervals; ++i) {
+        switch (kind) {
+            case 0: out[i] = bp_exp_unit(i, no_intervals) / a + b; break;                      // exp_break_points(n, coal_rate = a, offset = b)
+            case 1: out[i] = ((double)i / no_intervals) * (b - a) + a; break;                  // uniform_break_points(n, start = a, end = b)
+            case 2: out[i] = i == 0 ? c : c + bp_psmc_unit(i, no_intervals, a, b); break;      // psmc_break_points(n, t_max = a, mu = b, offset = c)
+            default: return fail(IMC_ERR_INVALID, "break point kind must be 0 (exp), 1 (uniform) or 2 (psmc)");
+        }
+    }
     return IMC_OK;
 }
 
@@ -397,6 +419,29 @@ extern "C" int imc_model_build_batch(imc_model* m, int N, const double* theta, d
     CUDA_TRY(cudaMemcpyAsync(E, m->d_E.p, sizeof(double) * N * K * 3, cudaMemcpyDeviceToHost, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, m->d_status.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return IMC_OK;
+}
+
+// the break points model_params_kernel computed for each parameter point (what <model>.py build_ctmc_system hands to the
+// CTMC system): out[N][K]; rows of invalid points (status 1) are NaN
+extern "C" int imc_model_break_points(imc_model* m, int N, const double* theta, double* out) {
+    if (!m) return fail(IMC_ERR_INVALID, "NULL model");
+    if (N <= 0) return N == 0 ? IMC_OK : fail(IMC_ERR_INVALID, "N < 0");
+    if (!theta || !out) return fail(IMC_ERR_INVALID, "NULL host pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = g_ctx.stream;
+    if ((rc = model_stage_theta(m, N, theta, st))) return rc;
+    const size_t K = m->K;
+    if ((rc = model_build_dev(m, N, (const double*)m->d_theta.p, (double*)m->d_pi.p, (double*)m->d_T.p, (double*)m->d_E.p,
+                              (int*)m->d_status.p, st))) return rc;
+    std::vector<int> status(N);
+    CUDA_TRY(cudaMemcpy2DAsync(out, sizeof(double) * K, m->d_scratch.p, sizeof(double) * 3 * K, sizeof(double) * K, (size_t)N,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status.data(), m->d_status.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int n = 0; n < N; ++n)
+        if (status[n] == 1) for (size_t i = 0; i < K; ++i) out[(size_t)n * K + i] = std::nan("");
     return IMC_OK;
 }
 

@@ -77,6 +77,15 @@ class Model(object):
         pi, T, E, _ = self.build_hidden_markov_models(np.asarray(parameters, dtype=np.float64)[None])
         return pi[0], T[0], E[0]
 
+    def break_points(self, thetas):
+        """The break points the model-build kernel computed on the device for thetas[N,P] -> float64[N,K] (what the
+        reference's build_ctmc_system gets from break_points.py); NaN rows for invalid parameter points."""
+        thetas = self._thetas(thetas)
+        out = np.empty((thetas.shape[0], self.no_states_total))
+        check(_lib.load().imc_model_break_points(self._handle, thetas.shape[0], thetas.ctypes.data_as(_lib.c_f64p),
+                                                 out.ctypes.data_as(_lib.c_f64p)))
+        return out
+
     def batched_log_likelihood(self, thetas, forwarder_set, return_status=False):
         """Fused theta -> logL on the device for thetas[N,P]; invalid rows give -inf (likelihood.py:29-30)."""
         thetas = self._thetas(thetas)

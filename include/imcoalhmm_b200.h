@@ -170,6 +170,13 @@ int imc_model_build_batch(imc_model* model, int N, const double* theta, double* 
                           int32_t* status);
 int imc_model_build_batch_dev(imc_model* model, int N, const double* d_theta, double* d_pi, double* d_T,
                               double* d_E, int32_t* d_status, void* stream);
+/* Break points (break_points.py:9-30 exp, :60-78 uniform, :81-108 psmc).  imc_break_points is the host form of the three
+ * functions -- kind 0: exp_break_points(n, coal_rate = a, offset = b); 1: uniform_break_points(n, start = a, end = b);
+ * 2: psmc_break_points(n, t_max = a, mu = b, offset = c) -- built from the same expressions as the models' constant
+ * tables; imc_model_break_points returns what the model-build kernel computed on the device for each parameter point
+ * (out[N][K]; NaN rows where status is 1). */
+int imc_break_points(int kind, int no_intervals, double a, double b, double c, double* out);
+int imc_model_break_points(imc_model* model, int N, const double* theta, double* out);
 /* fused theta -> logL (model build and forward on the device, no host round trip in between; replaces
  * Likelihood.__call__, likelihood.py:27-33, for N points).  out[n] = -inf where status[n] == 1, NaN where 2. */
 int imc_loglik_batch(imc_model* model, imc_seqset* set, int N, const double* theta, double* out, int32_t* status);

@@ -16,6 +16,9 @@ The edits:
   4. `from scipy import matrix` -> `from numpy import matrix`
   5. `x = map(ComputeThroughInterval(...), ...)` -> `x = list(map(...))`
   6. py2 print statements -> print() calls (only in demo `main()`s / log callback)
+  7. (with_hmm=True only) hmm.py: `np.array(map(int, ...))` -> `np.array(list(map(int, ...)))`; hmm.py is the 22-line
+     wrapper around the absent `ziphmm` module (hmm.py:7,16,20-21) -- importing it needs a `ziphmm` in sys.modules,
+     which is exactly how tests/test_reference_boundary.py runs the reference's own code against this package
 """
 import os
 import re
@@ -59,16 +62,18 @@ def convert(text):
     text = text.replace("from scipy import matrix", "from numpy import matrix")
     text = re.sub(r"= map\((ComputeThroughInterval\(.*?\),\s*range\([^\n]*?\))\)\n",
                   r"= list(map(\1))\n", text, flags=re.S)
+    text = text.replace("np.array(map(int, finp.read().split()), dtype=np.int32)",
+                        "np.array(list(map(int, finp.read().split())), dtype=np.int32)")
     return "".join(_fix_print(l) for l in text.splitlines(True))
 
 
-def build(out_dir=DEFAULT_OUT, reference_pkg=REFERENCE_PKG):
+def build(out_dir=DEFAULT_OUT, reference_pkg=REFERENCE_PKG, with_hmm=False):
     pkg_out = os.path.join(out_dir, "IMCoalHMM")
     if os.path.isdir(out_dir):
         shutil.rmtree(out_dir)
     os.makedirs(pkg_out)
     for name in sorted(os.listdir(reference_pkg)):
-        if not name.endswith(".py") or name in SKIP:
+        if not name.endswith(".py") or (name in SKIP and not (with_hmm and name == "hmm.py")):
             continue
         with open(os.path.join(reference_pkg, name)) as f:
             src = f.read()

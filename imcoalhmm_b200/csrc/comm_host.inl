@@ -27,6 +27,9 @@ struct PeerBox {
     void* local = nullptr;
     void* mapped[MAX_PEERS] = {};      // mapped[r] = rank r's mailbox in this process (mapped[rank] == local)
     unsigned* counter = nullptr;
+    unsigned* status = nullptr;        // pinned, mapped host word written by reduce_chains_peer_kernel on a timeout
+    unsigned* status_dev = nullptr;    // its device address
+    bool broken = false;               // a collective timed out: every later collective call fails until imc_comm_destroy
     size_t val_bytes() const { return sizeof(double) * 2 * (size_t)g_comm_nranks * nmax; }
 };
 static PeerBox g_peer;
@@ -62,36 +65,45 @@ static void peer_teardown() {
     }
     if (g_peer.local) cudaFree(g_peer.local);
     if (g_peer.counter) cudaFree(g_peer.counter);
+    if (g_peer.status) cudaFreeHost(g_peer.status);
     g_peer = PeerBox();
 }
 
 // Called by every rank right after the communicator exists.  Failure to map any peer (ranks on different nodes, IPC not
-// permitted) is not an error: all ranks then agree to keep the NCCL all-reduce.
+// permitted, "comm_fused" 0 on some rank, an allocation that failed) is not an error: all ranks then agree to keep the NCCL
+// all-reduce.  Every rank takes part in BOTH exchange rounds whatever happened locally -- a rank that left early would
+// leave the others blocked inside NCCL -- and carries its local verdict in an "ok" bit instead.
 static int peer_setup(int nranks, int rank) {
-    if (!g_ctx.opt_comm_fused || nranks > MAX_PEERS) return IMC_OK;
     cudaStream_t st = g_ctx.stream;
+    int ok = (g_ctx.opt_comm_fused && nranks <= MAX_PEERS) ? 1 : 0;
     g_peer.nmax = 1 << 16;
     const size_t bytes = g_peer.val_bytes() + 128 * (size_t)nranks;
-    int ok = 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
-    if (cudaMalloc(&g_peer.local, bytes) != cudaSuccess || cudaMalloc((void**)&g_peer.counter, sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(g_peer.local, 0, bytes) != cudaSuccess || cudaMemset(g_peer.counter, 0, sizeof(unsigned)) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine, g_peer.local) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    if (ok && (cudaMalloc(&g_peer.local, bytes) != cudaSuccess || cudaMalloc((void**)&g_peer.counter, sizeof(unsigned)) != cudaSuccess ||
+               cudaMemset(g_peer.local, 0, bytes) != cudaSuccess || cudaMemset(g_peer.counter, 0, sizeof(unsigned)) != cudaSuccess ||
+               cudaHostAlloc((void**)&g_peer.status, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess ||
+               cudaHostGetDevicePointer((void**)&g_peer.status_dev, g_peer.status, 0) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine, g_peer.local) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
         ok = 0;
         cudaGetLastError();
     }
-    // exchange the handles (and whether everybody has one) with the communicator itself
+    if (ok) *g_peer.status = 0u;
+    // round 1: exchange the handles (and whether everybody has one) with the communicator itself
     const size_t slot = sizeof(cudaIpcMemHandle_t) + 8;
     unsigned char* d_all = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_all, slot * nranks));
-    std::vector<unsigned char> h_all(slot * nranks, 0);
+    std::vector<unsigned char> h_all(slot * std::max(nranks, 1), 0);
+    int local_rc = IMC_OK;          // first local CUDA / NCCL failure; reported after both rounds
+    auto note = [&](bool good, const char* what) { if (!good && local_rc == IMC_OK) local_rc = fail(IMC_ERR_CUDA, "peer setup: %s failed", what); if (!good) ok = 0; };
+    note(cudaMalloc((void**)&d_all, slot * nranks) == cudaSuccess, "cudaMalloc");
     memcpy(h_all.data() + slot * rank, &mine, sizeof mine);
     h_all[slot * rank + sizeof mine] = (unsigned char)ok;
-    CUDA_TRY(cudaMemcpy(d_all + slot * rank, h_all.data() + slot * rank, slot, cudaMemcpyHostToDevice));
-    NCCL_TRY(g_nccl.AllGather(d_all + slot * rank, d_all, slot, ncclChar, g_comm, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaMemcpy(h_all.data(), d_all, slot * nranks, cudaMemcpyDeviceToHost));
+    if (d_all) {
+        note(cudaMemcpy(d_all + slot * rank, h_all.data() + slot * rank, slot, cudaMemcpyHostToDevice) == cudaSuccess, "cudaMemcpy");
+        note(g_nccl.AllGather(d_all + slot * rank, d_all, slot, ncclChar, g_comm, st) == ncclSuccess, "ncclAllGather");
+        note(cudaStreamSynchronize(st) == cudaSuccess, "cudaStreamSynchronize");
+        note(cudaMemcpy(h_all.data(), d_all, slot * nranks, cudaMemcpyDeviceToHost) == cudaSuccess, "cudaMemcpy");
+    }
     for (int r = 0; r < nranks; ++r) ok = ok && h_all[slot * r + sizeof mine];
     if (ok) {
         g_peer.mapped[rank] = g_peer.local;
@@ -106,14 +118,18 @@ static int peer_setup(int nranks, int rank) {
             }
         }
     }
-    // second round: did every rank map every mailbox?
-    int* d_ok = (int*)d_all;
-    CUDA_TRY(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
-    NCCL_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, g_comm, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_all);
-    if (!ok) { peer_teardown(); return IMC_OK; }
+    // round 2: did every rank map every mailbox?
+    if (d_all) {
+        int* d_ok = (int*)d_all;
+        note(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess, "cudaMemcpy");
+        note(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, g_comm, st) == ncclSuccess, "ncclAllReduce");
+        note(cudaStreamSynchronize(st) == cudaSuccess, "cudaStreamSynchronize");
+        int all_ok = 0;
+        note(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess, "cudaMemcpy");
+        ok = ok && all_ok;
+        cudaFree(d_all);
+    }
+    if (!ok) { peer_teardown(); return local_rc; }
     g_peer.active = true;
     return IMC_OK;
 }
@@ -175,9 +191,24 @@ extern "C" int imc_comm_info(int* nranks, int* rank, int* fused) {
 }
 
 // out[n] = sum over this rank's chains -- and, when the mailboxes are mapped, over all ranks in the same kernel
+static int comm_check() {      // a collective that timed out leaves the ranks out of step: nothing collective may follow
+    if (g_peer.active && !g_peer.broken && g_peer.status && (*((volatile unsigned*)g_peer.status) & 0x80000000u)) g_peer.broken = true;
+    if (g_peer.broken)
+        return fail(IMC_ERR_CUDA, "the fused all-reduce timed out waiting for rank %u (dead peer, or ranks issued different call sequences); "
+                                  "results of that call are NaN and the communicator is unusable: call imc_comm_destroy",
+                    g_peer.status ? (*g_peer.status & 0x7fffffffu) : 0u);
+    return IMC_OK;
+}
+
 static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out, cudaStream_t st) {
     g_reduced_over_ranks = false;
     if (g_comm && g_peer.active && g_ctx.opt_comm_enabled && N <= g_peer.nmax) {
+        int rc = comm_check();
+        if (rc) return rc;
+        // consecutive collectives of this process run in issue order whatever streams they were enqueued on (the mailbox
+        // halves and the block counter assume it)
+        static HandleSerial comm_serial;
+        CallGuard guard(comm_serial, st);
         PeerReduceArgs pa;
         pa.nranks = g_comm_nranks; pa.rank = g_comm_rank; pa.nmax = g_peer.nmax;
         pa.epoch = ++g_peer.epoch;
@@ -186,6 +217,8 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
             pa.flag[r] = (unsigned*)((unsigned char*)g_peer.mapped[r] + g_peer.val_bytes());
         }
         pa.counter = g_peer.counter;
+        pa.status = g_peer.status_dev;
+        pa.timeout_ns = (unsigned long long)std::max<long long>(1, g_ctx.opt_comm_timeout_ms) * 1000000ull;
         reduce_chains_peer_kernel<<<N, 256, 0, st>>>(chain, ns, d_out, pa);
         g_reduced_over_ranks = true;
     } else {
@@ -197,8 +230,20 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 }
 
 // this rank's partial log-likelihoods, then the sum over ranks when a communicator exists
+static const int MAX_POINTS_PER_LAUNCH = 32768;     // several kernels put the parameter point on gridDim.y (<= 65535)
+
 static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
                        double* d_out, cudaStream_t st) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    CallGuard guard(set->serial, st);
+    if (N > MAX_POINTS_PER_LAUNCH) {       // large batches (MCMC / swarm populations) run as slices, each with its own all-reduce
+        for (int n0 = 0; n0 < N; n0 += MAX_POINTS_PER_LAUNCH) {
+            const int nn = std::min(MAX_POINTS_PER_LAUNCH, N - n0);
+            int rc = forward_dev(set, nn, K, S, d_pi + (size_t)n0 * K, d_T + (size_t)n0 * K * K, d_E + (size_t)n0 * K * S, d_out + n0, st);
+            if (rc) return rc;
+        }
+        return IMC_OK;
+    }
     int rc = forward_local_dev(set, N, K, S, d_pi, d_T, d_E, d_out, st);
     if (rc || !g_comm || N <= 0 || !g_ctx.opt_comm_enabled || g_reduced_over_ranks) return rc;
     NCCL_TRY(g_nccl.AllReduce(d_out, d_out, (size_t)N, ncclDouble, ncclSum, g_comm, st));
@@ -227,6 +272,7 @@ extern "C" int imc_forward_batch(imc_seqset* set, int N, int K, int S, const dou
     if ((rc = set->d_E.reserve(nE * sizeof(double)))) return rc;
     if ((rc = set->d_out.reserve((size_t)N * sizeof(double)))) return rc;
     cudaStream_t st = g_ctx.stream;
+    CallGuard guard(set->serial, st);       // the staging buffers belong to this call until its results are on the host
     CUDA_TRY(cudaMemcpyAsync(set->d_pi.p, pi, npi * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(set->d_T.p, T, nT * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(set->d_E.p, E, nE * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -235,7 +281,7 @@ extern "C" int imc_forward_batch(imc_seqset* set, int N, int K, int S, const dou
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, set->d_out.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    return IMC_OK;
+    return g_comm ? comm_check() : IMC_OK;
 }
 
 extern "C" int imc_forward(imc_seqset* set, int K, int S, const double* pi, const double* T, const double* E,

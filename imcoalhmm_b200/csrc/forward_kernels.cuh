@@ -558,7 +558,15 @@ struct PeerReduceArgs {
     double* box[MAX_PEERS];         // val array of rank r's mailbox as mapped into this process
     unsigned* flag[MAX_PEERS];      // flag lines of rank r's mailbox: flag[r][32 * source]
     unsigned* counter;              // local: blocks of this launch that have delivered (left at 0)
+    unsigned* status;               // host-visible word: 0, or 0x80000000 | (rank that did not deliver in time)
+    unsigned long long timeout_ns;  // how long to wait for a peer's flag before giving up
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __global__ void __launch_bounds__(256) reduce_chains_peer_kernel(const double* chain_out, int nstreams, double* out, PeerReduceArgs pa) {
     __shared__ double sh[256];
@@ -588,10 +596,28 @@ __global__ void __launch_bounds__(256) reduce_chains_peer_kernel(const double* c
         for (int r = 0; r < pa.nranks; ++r)
             if (r != pa.rank) *((volatile unsigned*)(pa.flag[r] + 32 * pa.rank)) = pa.epoch;
     }
-    for (int r = 0; r < pa.nranks; ++r) {                         // every thread waits for every source itself
+    // Every thread waits for every source itself -- but not for ever: a peer that died, or that issued a different
+    // sequence of calls, would otherwise hang every GPU of the job.  On a timeout the results are NaN and the status word
+    // (host-visible) names the rank; the host turns that into IMC_ERR_CUDA and marks the communicator broken.
+    bool timed_out = false;
+    const unsigned long long t0 = global_timer_ns();
+    for (int r = 0; r < pa.nranks && !timed_out; ++r) {
         if (r == pa.rank) continue;
         const volatile unsigned* f = pa.flag[pa.rank] + 32 * r;
-        while ((int)(*f - pa.epoch) < 0) __nanosleep(64);
+        unsigned spins = 0;
+        while ((int)(*f - pa.epoch) < 0) {
+            __nanosleep(64);
+            if ((++spins & 1023u) == 0u && global_timer_ns() - t0 > pa.timeout_ns) {
+                timed_out = true;
+                if (tid == 0) *((volatile unsigned*)pa.status) = 0x80000000u | (unsigned)r;
+                break;
+            }
+        }
+    }
+    if (__syncthreads_or(timed_out ? 1 : 0)) {
+        for (int i = tid; i < N; i += 256) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+        if (tid == 0) { *pa.counter = 0u; __threadfence_system(); }
+        return;
     }
     __threadfence_system();
     const double* mine = pa.box[pa.rank] + row;

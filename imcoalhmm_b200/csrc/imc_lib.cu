@@ -16,7 +16,31 @@
 #include <mutex>
 #include <numeric>
 #include <dlfcn.h>
-#include <nccl.h>      // types and prototypes only: the library is resolved with dlopen when imc_comm_init is called
+// NCCL: types and prototypes only -- the library itself is resolved with dlopen when imc_comm_init is called.  Without the
+// development header the six entry points used are declared here (their ABI has been stable since NCCL 2.0), so that the
+// single-GPU library builds on machines that have no NCCL at all.
+#if defined(__has_include)
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define IMC_HAVE_NCCL_H 1
+#endif
+#endif
+#ifndef IMC_HAVE_NCCL_H
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclInt32 = 2, ncclInt = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5,
+               ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
+ncclResult_t ncclGetUniqueId(ncclUniqueId* uniqueId);
+ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank);
+ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype, ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream);
+ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream);
+ncclResult_t ncclCommDestroy(ncclComm_t comm);
+const char* ncclGetErrorString(ncclResult_t result);
+}
+#endif
 #include <sched.h>
 #include <string>
 #include <unistd.h>
@@ -68,6 +92,7 @@ struct Context {
     long long opt_zip_spectral_force_bad = 0;   // test switch: zip_spectral_kernel declares every point unfit (plain-form pass serves them)
     long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
     long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
+    long long opt_comm_timeout_ms = 30000;   // how long the fused all-reduce waits for a peer before it gives up (NaN + error)
 };
 static Context g_ctx;
 
@@ -120,6 +145,28 @@ struct DeviceBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// One call at a time per handle: the scratch buffers of a sequence set / model (chain sums, work counters, carry vectors,
+// pi / T / E staging) are per handle, so a second call -- from another host thread or on another stream -- must not start
+// before the first has finished with them.  The guard serialises the host side with a (recursive) mutex and the device
+// side with an event: every call waits for the event its predecessor recorded, whatever streams the two were issued on.
+struct HandleSerial {
+    std::recursive_mutex mu;
+    cudaEvent_t done = nullptr;
+};
+struct CallGuard {
+    HandleSerial& h;
+    cudaStream_t st;
+    CallGuard(HandleSerial& hs, cudaStream_t s) : h(hs), st(s) {
+        h.mu.lock();
+        if (h.done) cudaStreamWaitEvent(st, h.done, 0);
+    }
+    ~CallGuard() {
+        if (!h.done) cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming);
+        if (h.done) cudaEventRecord(h.done, st);
+        h.mu.unlock();
+    }
+};
+
 // device copy of the token streams derived for one dictionary size M (see zip_device)
 struct ZipSplit {                 // segmented variant of a ZipDevice's chunk list (same token buffer)
     int K = 0, seglen = 0, nchains = 0;
@@ -140,6 +187,7 @@ struct ZipDevice {
 };
 
 struct imc_seqset {
+    HandleSerial serial;
     int n_chunks = 0;
     int nsym = 0;
     long long total_sites = 0;
@@ -388,6 +436,7 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
         set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
         for (int i = 0; i < 2; ++i) { set->d_pnext[i].release(); set->d_vec[i].release(); set->d_prog[i].release(); }
         set->d_spec.release(); set->d_lists.release();
+        if (set->serial.done) cudaEventDestroy(set->serial.done);
     }
     for (ZipDevice* z : set->zip_dev) {
         if (mine) { z->tokens.release(); z->chunks.release(); z->pairs.release(); z->levels.release(); }
@@ -894,6 +943,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_mma_shape")) { if (value < 0 || value > 4) return fail(IMC_ERR_INVALID, "zip_mma_shape must be in [0, 4]"); g_ctx.opt_zip_mma_shape = value; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
+    if (!strcmp(key, "comm_timeout_ms")) { if (value < 1) return fail(IMC_ERR_INVALID, "comm_timeout_ms must be >= 1"); g_ctx.opt_comm_timeout_ms = value; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int imc_get_option(const char* key, int64_t* value_out) {
@@ -912,6 +962,7 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_mma_shape")) { *value_out = g_ctx.opt_zip_mma_shape; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
+    if (!strcmp(key, "comm_timeout_ms")) { *value_out = g_ctx.opt_comm_timeout_ms; return IMC_OK; }
     return fail(IMC_ERR_INVALID, "unknown option '%s'", key);
 }
 extern "C" int64_t imc_kernel_launches(void) { return g_launches.load(); }

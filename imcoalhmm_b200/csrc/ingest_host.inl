@@ -56,9 +56,32 @@ extern "C" int imc_seq_from_columns(const char* const* seqs, int n_seqs, int64_t
 }
 
 // FASTA: '>' starts a record, its name is the text up to the first whitespace; sequence lines are concatenated.
+struct FileCloser {          // closes the file on every exit path, exceptions included
+    FILE* f;
+    ~FileCloser() { if (f) fclose(f); }
+};
+
+// No C++ exception may cross the C ABI: the readers below run inside these wrappers (a header such as "999999999999 10" or
+// a file larger than memory must come back as an error code, not terminate the caller's process).
+static int read_fasta_impl(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs);
+static int read_phylip_impl(const char* path, bool sequential, bool relaxed, std::vector<std::string>& names, std::vector<std::string>& seqs);
 static int read_fasta(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+    try { return read_fasta_impl(path, names, seqs); }
+    catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of memory reading '%s'", path); }
+    catch (const std::exception& e) { return fail(IMC_ERR_IO, "reading '%s' failed: %s", path, e.what()); }
+    catch (...) { return fail(IMC_ERR_IO, "reading '%s' failed", path); }
+}
+static int read_phylip(const char* path, bool sequential, bool relaxed, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+    try { return read_phylip_impl(path, sequential, relaxed, names, seqs); }
+    catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of memory reading '%s'", path); }
+    catch (const std::exception& e) { return fail(IMC_ERR_IO, "reading '%s' failed: %s", path, e.what()); }
+    catch (...) { return fail(IMC_ERR_IO, "reading '%s' failed", path); }
+}
+
+static int read_fasta_impl(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
+    FileCloser closer{f};
     std::vector<char> buf(1 << 20);
     bool in_header = false, at_line_start = true;
     size_t got;
@@ -74,11 +97,10 @@ static int read_fasta(const char* path, std::vector<std::string>& names, std::ve
             if (at_line_start && ch == '>') { names.emplace_back(); seqs.emplace_back(); in_header = true; continue; }
             at_line_start = false;
             if (ch == ' ' || ch == '\t') continue;
-            if (seqs.empty()) { fclose(f); return fail(IMC_ERR_IO, "'%s' does not start with a FASTA header", path); }
+            if (seqs.empty()) return fail(IMC_ERR_IO, "'%s' does not start with a FASTA header", path);
             seqs.back().push_back(ch);
         }
     }
-    fclose(f);
     for (auto& n : names) {
         while (!n.empty() && (n.back() == '\r' || n.back() == ' ' || n.back() == '\t')) n.pop_back();
         const size_t sp = n.find_first_of(" \t");
@@ -92,7 +114,7 @@ static int read_fasta(const char* path, std::vector<std::string>& names, std::ve
 // order) or, sequential, each taxon's name followed by all of its data over as many lines as it takes.  Strict names
 // occupy the first 10 columns of the line; relaxed names end at the first blank.  Blanks inside the data are ignored;
 // '.' (match-first-row shorthand) is rejected, as BioPython does.
-static int read_phylip(const char* path, bool sequential, bool relaxed, std::vector<std::string>& names, std::vector<std::string>& seqs) {
+static int read_phylip_impl(const char* path, bool sequential, bool relaxed, std::vector<std::string>& names, std::vector<std::string>& seqs) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(IMC_ERR_IO, "cannot open '%s': %s", path, strerror(errno));
     std::string text;
@@ -120,6 +142,9 @@ static int read_phylip(const char* path, bool sequential, bool relaxed, std::vec
         char extra;
         if (sscanf(head.c_str(), " %lld %lld %c", &ntaxa, &nsites, &extra) != 2 || ntaxa < 1 || nsites < 0)
             return fail(IMC_ERR_IO, "'%s' does not start with a PHYLIP header (taxa, sites)", path);
+        // every taxon needs at least one line and every site at least one byte of the file
+        if (ntaxa > (long long)lines.size() - 1 || nsites > (long long)text.size())
+            return fail(IMC_ERR_IO, "'%s': header announces %lld taxa x %lld sites, more than the file can hold", path, ntaxa, nsites);
     }
     names.assign((size_t)ntaxa, std::string());
     seqs.assign((size_t)ntaxa, std::string());

@@ -145,6 +145,7 @@ struct imc_model {
     imc::ModelDev dev{};
     DeviceBuf d_static;                           // all static tables in one allocation
     DeviceBuf d_theta, d_params, d_scratch, d_status, d_pbuf, d_prebuf, d_pi, d_T, d_E, d_out;
+    HandleSerial serial;
 };
 
 extern "C" int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts /*[4] B,L,R,E*/,
@@ -279,6 +280,7 @@ extern "C" int imc_model_info(const imc_model* m, int* K, int* P) {
 extern "C" int imc_model_destroy(imc_model* m) {
     if (!m) return IMC_OK;
     if (g_ctx.pid == getpid()) {      // buffers may exist before the static tables were uploaded
+        if (m->serial.done) cudaEventDestroy(m->serial.done);
         for (DeviceBuf* b : {&m->d_static, &m->d_theta, &m->d_params, &m->d_scratch, &m->d_status, &m->d_pbuf,
                              &m->d_prebuf, &m->d_pi, &m->d_T, &m->d_E, &m->d_out}) b->release();
     }
@@ -344,6 +346,14 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
     int rc = model_upload(m);
     if (rc) return rc;
     const int K = m->K;
+    if (N > 32768) {        // model_expm_kernel puts the parameter point on gridDim.y: large batches run as slices
+        for (int n0 = 0; n0 < N; n0 += 32768) {
+            const int nn = std::min(32768, N - n0);
+            if ((rc = model_build_dev(m, nn, d_theta + (size_t)n0 * m->P, d_pi + (size_t)n0 * K, d_T + (size_t)n0 * K * K,
+                                      d_E + (size_t)n0 * K * 3, d_status + n0, st))) return rc;
+        }
+        return IMC_OK;
+    }
     if ((rc = m->d_params.reserve(sizeof(double) * (size_t)N * PointParams::size(K)))) return rc;
     if ((rc = m->d_scratch.reserve(sizeof(double) * (size_t)N * 3 * K))) return rc;
     if ((rc = m->d_pbuf.reserve(sizeof(double) * (size_t)N * m->p_stride))) return rc;
@@ -385,6 +395,7 @@ extern "C" int imc_model_build_batch_dev(imc_model* m, int N, const double* d_th
     if (!m) return fail(IMC_ERR_INVALID, "NULL model");
     if (N <= 0) return N == 0 ? IMC_OK : fail(IMC_ERR_INVALID, "N < 0");
     if (!d_theta || !d_pi || !d_T || !d_E || !d_status) return fail(IMC_ERR_INVALID, "NULL device pointer");
+    CallGuard guard(m->serial, (cudaStream_t)stream);
     return model_build_dev(m, N, d_theta, d_pi, d_T, d_E, d_status, (cudaStream_t)stream);
 }
 
@@ -410,6 +421,7 @@ extern "C" int imc_model_build_batch(imc_model* m, int N, const double* theta, d
     int rc = ensure_device();
     if (rc) return rc;
     cudaStream_t st = g_ctx.stream;
+    CallGuard guard(m->serial, st);
     if ((rc = model_stage_theta(m, N, theta, st))) return rc;
     const size_t K = m->K;
     if ((rc = model_build_dev(m, N, (const double*)m->d_theta.p, (double*)m->d_pi.p, (double*)m->d_T.p, (double*)m->d_E.p,
@@ -428,9 +440,11 @@ extern "C" int imc_model_break_points(imc_model* m, int N, const double* theta, 
     if (!m) return fail(IMC_ERR_INVALID, "NULL model");
     if (N <= 0) return N == 0 ? IMC_OK : fail(IMC_ERR_INVALID, "N < 0");
     if (!theta || !out) return fail(IMC_ERR_INVALID, "NULL host pointer");
+    if (N > 32768) return fail(IMC_ERR_UNSUPPORTED, "at most 32768 parameter points per imc_model_break_points call");
     int rc = ensure_device();
     if (rc) return rc;
     cudaStream_t st = g_ctx.stream;
+    CallGuard guard(m->serial, st);
     if ((rc = model_stage_theta(m, N, theta, st))) return rc;
     const size_t K = m->K;
     if ((rc = model_build_dev(m, N, (const double*)m->d_theta.p, (double*)m->d_pi.p, (double*)m->d_T.p, (double*)m->d_E.p,
@@ -457,6 +471,7 @@ extern "C" int imc_loglik_batch_dev(imc_model* m, imc_seqset* set, int N, const 
     int rc = ensure_device();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    CallGuard guard(m->serial, st);          // the model's pi / T / E staging is in use until the forward has read it
     const size_t K = m->K;
     if ((rc = m->d_pi.reserve(sizeof(double) * N * K))) return rc;
     if ((rc = m->d_T.reserve(sizeof(double) * N * K * K))) return rc;
@@ -481,10 +496,11 @@ extern "C" int imc_loglik_batch(imc_model* m, imc_seqset* set, int N, const doub
     int rc = ensure_device();
     if (rc) return rc;
     cudaStream_t st = g_ctx.stream;
+    CallGuard guard(m->serial, st);
     if ((rc = model_stage_theta(m, N, theta, st))) return rc;
     if ((rc = imc_loglik_batch_dev(m, set, N, (const double*)m->d_theta.p, (double*)m->d_out.p, (int32_t*)m->d_status.p, st))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, m->d_out.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, m->d_status.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    return IMC_OK;
+    return g_comm ? comm_check() : IMC_OK;
 }

@@ -76,6 +76,13 @@ int imc_seq_symbol_counts(const imc_seq* seq, int64_t* counts);
 int imc_seq_symbols(const imc_seq* seq, uint8_t* out, int64_t capacity);
 int imc_seq_destroy(imc_seq* seq);
 
+/* ---- concurrency -------------------------------------------------------------------------------------------------
+ * A handle (imc_seqset, imc_model) owns per-handle scratch on the device, so its calls are serialised: every call on a
+ * handle first waits -- on the host with a mutex, on the device with an event -- for the previous call on the SAME handle,
+ * whatever thread or CUDA stream that call came from.  Calls on different handles run concurrently.  With a communicator
+ * the collective calls of a process are likewise executed in issue order, and all ranks must issue the same sequence.
+ * Errors are per thread (imc_last_error). */
+
 /* ---- sequence sets: the list of forwarders a Likelihood sums over (likelihood.py:22-25,33), packed into
  * the interleaved 2-bit layout the kernels stream from HBM.  Host-only until the first forward call. */
 typedef struct imc_seqset imc_seqset;
@@ -216,6 +223,9 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       distinct entry.  0 = auto (where one entry is >= 50 % of the run tokens), 1 = always, 2 = never.
  * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).
  * key "comm_fused", "comm_enabled": see the multi-GPU section above.
+ * key "comm_timeout_ms": how long the fused all-reduce waits for a peer's partial sums (default 30000).  On a timeout the call's
+ *                       results are NaN, the synchronous entry points return IMC_ERR_CUDA naming the rank, and every later
+ *                       collective call fails until imc_comm_destroy: a dead or out-of-step rank is an error, not a hang.
  * key "dmma_mtiles":    M-tiles (of 8 chains) per warp for the DMMA kernel (1, 2 or 4; 0 = auto).
  * key "fold_emission":  1 fold the most frequent symbol's emission column into the register copy
  *                       of T where E[:,s0] > 0; 0 (default; measured faster on B200) = always multiply by the emission row. */

@@ -55,6 +55,31 @@ def _rank(rank, world, tmp, lengths):
         results.append(np.concatenate([a, b, [c], d, e]))
         m._lib.comm_destroy()
     assert m._lib.comm_info() == {"nranks": 1, "rank": 0, "fused": False}
+    # ---- a rank that does not show up is an error after the timeout, not a hang: rank 1 skips one collective call ----
+    m.set_option("comm_fused", 1)
+    m.set_option("comm_timeout_ms", 400)
+    _connect(m, rank, world, os.path.join(tmp, "nccl_id_timeout"))
+    timed_out = -1
+    if m._lib.comm_info()["fused"]:
+        ok = fset.forward_batch(pis[:6], Ts[:6], Es[:6])                      # both ranks: fine
+        assert np.isfinite(ok).all()
+        if rank == 0:
+            t0 = time.time()
+            try:
+                fset.forward_batch(pis[:6], Ts[:6], Es[:6])                   # rank 1 never issues this call
+                timed_out = 0
+            except m.IMCError as e:
+                timed_out = 1 if ("timed out" in str(e) and time.time() - t0 < 20) else 0
+            try:
+                fset.forward_batch(pis[:6], Ts[:6], Es[:6])                   # the communicator is unusable from here on
+                timed_out = 0
+            except m.IMCError:
+                pass
+        else:
+            time.sleep(3.0)
+    m._lib.comm_destroy()
+    m.set_option("comm_timeout_ms", 30000)
+    np.save(os.path.join(tmp, "timeout%d.npy" % rank), np.array([timed_out]))
     np.save(os.path.join(tmp, "out%d.npy" % rank), np.stack(results))
     np.save(os.path.join(tmp, "fused%d.npy" % rank), np.array(fused))
 
@@ -97,3 +122,5 @@ def test_native_allreduce_sums_over_two_gpus(tmp_path):
         np.testing.assert_array_equal(outs[r][0], outs[r][1])             # both collectives add the same two numbers
     np.testing.assert_array_equal(outs[0][:, :19], outs[1][:, :19])       # and every rank holds the same bits
     print("fused all-reduce used:", bool(fused[0][0]))
+    if fused[0][0]:
+        assert int(np.load(tmp_path / "timeout0.npy")[0]) == 1             # rank 0 got IMC_ERR_CUDA "timed out", twice

@@ -167,3 +167,17 @@ def test_phylip_readers_match_fasta(tmp_path):
         m.Forwarder.from_alignment(str(tmp_path / "missing.phy"), "phylip")
     with pytest.raises(m.IMCError):
         m.Forwarder.from_alignment(str(fa), "nexus")
+
+
+def test_hostile_headers_are_errors_not_crashes(tmp_path):
+    """A PHYLIP header that announces more than the file can hold must come back as an error code (a C++
+    exception crossing the C ABI would terminate the caller)."""
+    import imcoalhmm_b200 as m
+    p = tmp_path / "huge.phy"
+    p.write_text("999999999999 10\nA         ACGTACGTAC\nB         ACGTACGTAC\n")
+    with pytest.raises(ValueError):
+        m.Forwarder.from_alignment(str(p), "phylip")
+    q = tmp_path / "sites.phy"
+    q.write_text("2 999999999999\nA         ACGTACGTAC\nB         ACGTACGTAC\n")
+    with pytest.raises(ValueError):
+        m.Forwarder.from_alignment(str(q), "phylip-sequential")

@@ -170,3 +170,26 @@ def test_maximum_likelihood_estimate_recovers_simulated_parameters():
     assert lik(mle) >= lik(truth) - 1e-6
     assert np.all(np.abs(np.log(mle / truth)) < 0.5)
     assert len(log.getvalue().splitlines()) > 5 and len(log.getvalue().splitlines()[0].split("\t")) == 3
+
+
+def test_batches_larger_than_a_grid_dimension():
+    """N > 65535 parameter points (MCMC / swarm populations are passed straight through): the library slices the batch."""
+    import imcoalhmm_b200 as m
+    from conftest import example_symbols
+    obs = example_symbols()
+    fset = m.ForwarderSet([m.Forwarder.from_symbols(obs[:3000], 3)])
+    model = m.IsolationModel(4)
+    rng = np.random.default_rng(3)
+    N = 70001
+    thetas = np.array([1e-3, 2000.0, 0.4]) * np.exp(0.05 * rng.standard_normal((N, 3)))
+    thetas[12345, 1] = -1.0
+    out = model.batched_log_likelihood(thetas, fset)
+    assert out.shape == (N,) and out[12345] == -np.inf
+    pick = [0, 1, 32767, 32768, 32769, 65535, 65536, 70000]
+    want = model.batched_log_likelihood(thetas[pick], fset)
+    np.testing.assert_allclose(out[pick], want, rtol=1e-12)
+    pi, T, E, st = model.build_hidden_markov_models(thetas)
+    assert st[12345] == 1 and (np.delete(st, 12345) == 0).all()
+    np.testing.assert_allclose(fset.forward_batch(pi[pick], T[pick], E[pick]), want, rtol=1e-12)
+    big = fset.forward_batch(pi[:66000], T[:66000], E[:66000])
+    np.testing.assert_allclose(big[[0, 40000, 65999]], model.batched_log_likelihood(thetas[[0, 40000, 65999]], fset), rtol=1e-12)

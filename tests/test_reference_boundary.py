@@ -22,6 +22,8 @@ import pytest
 
 from conftest import GOLDEN, ROOT, example_symbols
 
+pytestmark = pytest.mark.filterwarnings("ignore")      # numpy.matrix deprecation noise from the reference's own modules
+
 REFERENCE = "/root/reference/src/IMCoalHMM"
 SHIM = "/tmp/imcoalhmm_ref_shim_boundary"
 needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference sources are not on this machine")

@@ -201,6 +201,7 @@ static int comm_check() {      // a collective that timed out leaves the ranks o
 }
 
 static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out, cudaStream_t st) {
+    NvtxRange nvtx_reduce("imc: chain reduction (+ fused all-reduce)");
     g_reduced_over_ranks = false;
     if (g_comm && g_peer.active && g_ctx.opt_comm_enabled && N <= g_peer.nmax) {
         int rc = comm_check();
@@ -235,6 +236,7 @@ static const int MAX_POINTS_PER_LAUNCH = 32768;     // several kernels put the p
 static int forward_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
                        double* d_out, cudaStream_t st) {
     if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    NvtxRange nvtx_fwd("imc: forward");
     CallGuard guard(set->serial, st);
     if (N > MAX_POINTS_PER_LAUNCH) {       // large batches (MCMC / swarm populations) run as slices, each with its own all-reduce
         for (int n0 = 0; n0 < N; n0 += MAX_POINTS_PER_LAUNCH) {

@@ -48,6 +48,23 @@ const char* ncclGetErrorString(ncclResult_t result);
 
 #include "tokenizer.inl"
 
+// NVTX ranges around the stages of a call (model build / spectral preparation / forward passes / reduction), so that
+// Nsight Systems timelines read as the design does.  Header-only (nvtx3); a no-op unless a tool is attached.
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define IMC_HAVE_NVTX 1
+#endif
+#endif
+struct NvtxRange {
+#ifdef IMC_HAVE_NVTX
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char*) {}
+#endif
+};
+
 using namespace imc;
 
 // ------------------------------------------------------------------------------------------ errors
@@ -575,6 +592,7 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // set->d_chain[n][chunk] for the points served.
 static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E, bool spec,
                     const int* plist, const int* pcount, const double* d_spec, int spec_stride, cudaStream_t st) {
+    NvtxRange nvtx_pass(spec ? "imc: zip pass (spectral form)" : "imc: zip pass (plain form)");
     int rc;
     const int ns = (int)set->streams.size(), pass = spec ? 0 : 1;
     const int avail = spec ? set->run_merges.size() : set->merges.size();
@@ -798,6 +816,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)2 * N + 2)))) return rc;
         int* lists = (int*)set->d_lists.p;
         CUDA_TRY(cudaMemsetAsync(lists, 0, sizeof(int) * 2, st));
+        NvtxRange nvtx_spec("imc: spectral forward (prepare + passes)");
         ZipSpecArgs sa;
         sa.N = N; sa.K = K; sa.S = S; sa.run_sym = set->fold_sym;
         sa.pi = d_pi; sa.T = d_T; sa.E = d_E;

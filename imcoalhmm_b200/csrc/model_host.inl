@@ -343,6 +343,7 @@ static int model_upload(imc_model* m) {
 static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d_pi, double* d_T, double* d_E,
                            int* d_status, cudaStream_t st) {
     using namespace imc;
+    NvtxRange nvtx_build("imc: model build (theta -> pi, T, E)");
     int rc = model_upload(m);
     if (rc) return rc;
     const int K = m->K;

@@ -19,6 +19,16 @@
 #pragma once
 #include "forward_kernels.cuh"
 #include <type_traits>
+#include <cassert>
+
+// -DIMC_DEBUG_BOUNDS: device-side checks of every data-dependent index (token ids, power-table rows, chunk and list
+// indices).  compute-sanitizer is closed on the development pool, so this build + tools/sanitize_case.py is the memory-safety
+// evidence (profiles/r02_bounds_checked_run.txt).
+#ifdef IMC_DEBUG_BOUNDS
+#define IMC_ASSERT(x) assert(x)
+#else
+#define IMC_ASSERT(x) ((void)0)
+#endif
 
 namespace imc {
 
@@ -164,6 +174,7 @@ struct ZipCfg8 {
         const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the four, remainder row pr
         const uint32_t myw = cj == 0 ? w[0] : (cj == 1 ? w[1] : (cj == 2 ? w[2] : w[3]));
         const int myid = myw & 0xffu;
+        IMC_ASSERT(!SPEC || (myw >> (8 + RUN_LO_BITS)) < (1u << RUN_HI_BITS));
         const double2* rp = reinterpret_cast<const double2*>(dict + (size_t)myid * STRIDE_D) + FULL * CP * 8 + L.q;
         double2 rm[CP];
 #pragma unroll
@@ -218,6 +229,7 @@ struct ZipCfg8 {
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
             const double* pa = ptab + ra * PT;
             const double* pb = ptab + rb * PT;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
@@ -304,6 +316,7 @@ struct ZipCfg4 {
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
             const double* pa = ptab + ra * PT + L.g;
             const double* pb = ptab + rb * PT + L.g;
             const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
@@ -374,6 +387,7 @@ struct ZipCfg32 {
         if (!PRED || active) {
             const int id = w & 0xffu;
             const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
+            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
             const double* pa = ptab + ra * PT + L.q;
             const double* pb = ptab + rb * PT + L.q;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
@@ -583,9 +597,11 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
     }
     const int ci = quad * C::CPW + L.grp;
     const bool have = ci < a.nchunks;
+    IMC_ASSERT(n >= 0 && n < a.N && quad * C::CPW < a.nchunks);
     const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
     const int tok0 = seg * a.seglen;
     const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
+    IMC_ASSERT(ch.ntok >= 0 && ch.first_sym < a.S && ch.first_sym >= -a.K && ch.first_run <= RUN_MAX);
     const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + (size_t)tok0 * (SPEC ? 4 : 1));
     int maxnt = nt;
 #pragma unroll
@@ -671,6 +687,7 @@ __device__ __forceinline__ void zip_run_unit(const ZipArgs& a, int n, int unit, 
                     } else {
 #pragma unroll C::UNROLL
                         for (int b = 0; b < 4; ++b) {
+                            IMC_ASSERT((int)(wv & 0xffu) < a.M);
                             C::template step<false, false>(al, dict, dexp, ptab, wv & 0xffu, L, buf, tscale, true);
                             wv >>= 8;
                             buf ^= 1;
@@ -770,9 +787,11 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
     }
     const int ci = quad * C::CPW + L.grp;
     const bool have = ci < a.nchunks;
+    IMC_ASSERT(n >= 0 && n < a.N && quad * C::CPW < a.nchunks);
     const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
     const int tok0 = seg * a.seglen;
     const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
+    IMC_ASSERT(ch.ntok >= 0 && ch.first_sym < a.S && ch.first_sym >= -a.K && ch.first_run <= RUN_MAX && hot < a.M);
     const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + (size_t)tok0 * 4);
     int maxnt = nt;
 #pragma unroll
@@ -829,6 +848,7 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         constexpr bool ALL = decltype(all_tag)::value;
         if (!ALL && !active) wb = 0u;
         const int id = wb & 0xffu;
+        IMC_ASSERT(id < a.M && (wb >> (8 + RUN_LO_BITS)) < (1u << RUN_HI_BITS));
         const uint32_t pa = ptab_s + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = ptab_s + (RUN_LO_ROWS + (wb >> (8 + RUN_LO_BITS))) * (PT * 8);
         double2 fa[NT], fb[NT];            // (lambda / lambda_max)^n of this token for the lane's states: independent of the products below
 #pragma unroll
@@ -1005,6 +1025,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
         if (slot == -1) break;
         if (slot == -2) continue;
         const int n = a.plist ? a.plist[slot] : slot;
+        IMC_ASSERT(slot >= 0 && slot < NP && n >= 0 && n < a.N);
         zip_build_dictionary<C, THREADS, SPEC>(a, n, dict, sE, spi, dexp, ptab);
         if constexpr (C::MMA) {
             double Bh[C::KT][C::NT];       // the hot entry's B fragments
@@ -1232,6 +1253,7 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
     if (pcount && list_base + (int)blockIdx.y >= *pcount) return;
     const int n = plist ? plist[list_base + blockIdx.y] : blockIdx.y, j = threadIdx.x;
     const ZipFoldItem it = items[blockIdx.x];
+    IMC_ASSERT(it.nfold >= 0 && it.start >= 0 && it.first_cols >= 0 && (it.src == 0 ? it.first_cols + it.nfold * K <= nvec : it.first_cols + it.nfold * K <= nvec2));
     const double* base = it.src == 0 ? vec + (size_t)n * nvec * vec_stride : vec2 + (size_t)n * nvec2 * vec_stride;
     const double* v0 = base + (size_t)it.start * vec_stride;
     double alpha = j < K ? v0[j] : 0.0;

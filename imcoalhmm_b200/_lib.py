@@ -47,6 +47,7 @@ _SIGNATURES = {
     "imc_seq_symbols": (ctypes.c_int, [c_vp, c_u8p, ctypes.c_int64]),
     "imc_seq_destroy": (ctypes.c_int, [c_vp]),
     "imc_seqset_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "imc_seqset_create_parts": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "imc_seqset_destroy": (ctypes.c_int, [c_vp]),
     "imc_seqset_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), c_i64p, c_i64p]),
     "imc_seqset_zip_info": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),

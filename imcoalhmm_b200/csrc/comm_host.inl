@@ -230,6 +230,42 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
     return IMC_OK;
 }
 
+// Parts mode (one long chunk cut over the ranks, SURVEY 8e "fewer chunks than GPUs"): the passes have folded this rank's parts
+// into set->d_parts; write the parts' run-site counts behind them, all-gather the blocks of all ranks (one ncclAllGather: the
+// only collective of such a call) and fold alpha <- P_part alpha over all parts in order.  Every rank ends with the same
+// logL[N] of the whole chunk.  A single process may hold all parts (no communicator needed): the gather is then the block itself.
+static int parts_finish(imc_seqset* set, int N, int K, const double* d_spec, int spec_stride, const int* okflag, double* d_out,
+                        cudaStream_t st) {
+    const int ns = (int)set->streams.size();
+    const int nranks = set->parts_total / ns;
+    const size_t vecs = (size_t)N * ns * K * (K + 1), block = vecs + ns;
+    std::vector<double> rs(ns, 0.0);
+    {
+        // run sites of every local part (stream k holds chunk set_chunk_of_stream(k)); taken from the spectral streams
+        ZipPlan plan;
+        ZipDevice* z = nullptr;
+        if (d_spec && zip_plan(K, set->nsym, set->run_merges.size(), &plan, 0, true) == IMC_OK && zip_device(set, plan.M, &z, true) == IMC_OK)
+            for (const ZipChunk& ch : z->host_chunks) rs[ch.continues - set->part_first] = (double)ch.run_sites;
+    }
+    CUDA_TRY(cudaMemcpyAsync((double*)set->d_parts.p + vecs, rs.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));        // rs is a stack buffer; parts-mode calls are rare and long
+    const double* gathered = (const double*)set->d_parts.p;
+    if (nranks > 1) {
+        if (!g_comm || g_comm_nranks != nranks || g_comm_rank * ns != set->part_first)
+            return fail(IMC_ERR_INVALID, "parts mode: this set holds parts %d..%d of %d, which needs a communicator of %d ranks with this process as rank %d",
+                        set->part_first, set->part_first + ns - 1, set->parts_total, nranks, set->part_first / ns);
+        int rc = set->d_gather.reserve(sizeof(double) * block * nranks);
+        if (rc) return rc;
+        NCCL_TRY(g_nccl.AllGather(set->d_parts.p, set->d_gather.p, block, ncclDouble, g_comm, st));
+        gathered = (const double*)set->d_gather.p;
+    }
+    zip_fold_parts_kernel<<<N, 64, 0, st>>>(gathered, block, N, K, ns, set->parts_total, d_spec, spec_stride, okflag, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    g_reduced_over_ranks = true;       // the result already is the whole chunk's: no all-reduce on top
+    return IMC_OK;
+}
+
 // this rank's partial log-likelihoods, then the sum over ranks when a communicator exists
 static const int MAX_POINTS_PER_LAUNCH = 32768;     // several kernels put the parameter point on gridDim.y (<= 65535)
 

@@ -186,7 +186,7 @@ struct CallGuard {
 
 // device copy of the token streams derived for one dictionary size M (see zip_device)
 struct ZipSplit {                 // segmented variant of a ZipDevice's chunk list (same token buffer)
-    int K = 0, seglen = 0, nchains = 0;
+    int K = 0, seglen = 0, nchains = 0, parts_local = 0;
     int n_level1 = 0, n_final = 0, nvec2 = 0;     // fold items of the two levels, vectors written by level 1
     DeviceBuf chunks, items1, items2;
 };
@@ -205,6 +205,10 @@ struct ZipDevice {
 
 struct imc_seqset {
     HandleSerial serial;
+    // parts mode (imc_seqset_create_parts): the chunks of this set are consecutive PARTS part_first .. of ONE long chunk that
+    // is cut into parts_total parts over the ranks of the communicator; 0 = ordinary set of independent chunks
+    int parts_total = 0, part_first = 0;
+    DeviceBuf d_parts, d_gather;           // this rank's block of part vectors; the all-gathered blocks
     int n_chunks = 0;
     int nsym = 0;
     long long total_sites = 0;
@@ -361,11 +365,13 @@ extern "C" int imc_seq_destroy(imc_seq* seq) {
 }
 
 // ------------------------------------------------------------------------------------------ sequence sets
-extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset** out) {
+static int seqset_create_impl(const imc_seq* const* seqs, int C, int part_first, int parts_total, imc_seqset** out) {
     if (!out || C < 0 || (C > 0 && !seqs)) return fail(IMC_ERR_INVALID, "bad arguments");
     imc_seqset* set = new (std::nothrow) imc_seqset;
     if (!set) return fail(IMC_ERR_NOMEM, "out of memory");
     set->n_chunks = C;
+    set->parts_total = parts_total;
+    set->part_first = part_first;
     std::vector<int> order;
     for (int c = 0; c < C; ++c) {
         if (!seqs[c]) { delete set; return fail(IMC_ERR_INVALID, "seqs[%d] is NULL", c); }
@@ -373,9 +379,10 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
         if (seqs[c]->nsym != set->nsym) { delete set; return fail(IMC_ERR_INVALID, "chunks disagree on nsym (%d vs %d)", seqs[c]->nsym, set->nsym); }
         if (seqs[c]->sym.size() > 0x7fffffffULL) { delete set; return fail(IMC_ERR_UNSUPPORTED, "chunk %d has more than 2^31-1 sites; split it", c); }
         set->total_sites += (long long)seqs[c]->sym.size();
+        if (parts_total > 0 && seqs[c]->sym.empty()) { delete set; return fail(IMC_ERR_INVALID, "part %d of a cut chunk is empty", part_first + c); }
         if (!seqs[c]->sym.empty()) order.push_back(c);   // an empty chunk contributes logL = 0
     }
-    set->packable = set->nsym <= 3;
+    set->packable = set->nsym <= 3 && parts_total == 0;      // the per-site kernels know nothing of parts
     {
         long long counts[256] = {0};
         for (int c : order) for (uint8_t v : seqs[c]->sym) counts[v]++;
@@ -396,7 +403,7 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
             for (int start = 0; start < stride && budget > 0; ++start)
                 for (int c = start; c < C && budget > 0; c += stride) {
                     const auto& sy = seqs[c]->sym;
-                    if (sy.size() < 2) continue;
+                    if (sy.size() < 2) continue;      // (a later part's position 0 is skipped in the sample like any chunk's: harmless)
                     const long long share = budget_total / std::min(32, std::max(1, C));
                     const size_t take = (size_t)std::min<long long>({(long long)sy.size() - 1, budget, share});
                     sample.emplace_back(sy.begin() + 1, sy.begin() + 1 + take);
@@ -419,8 +426,10 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
         if (!parallel_for(ns, [&](int k) {
                 const auto& sy = seqs[order[k]]->sym;
                 set->first_sym[k] = sy[0];
-                zip_encode(set->merges, sy.data() + 1, sy.size() - 1, set->tok_full[k]);
-                run_encode(set->run_merges, sy.data() + 1, sy.size() - 1, set->fold_sym, &set->first_run[k], set->run_tok_full[k]);
+                // a later part of a cut chunk has no start of its own: its position 0 is an ordinary site of the stream
+                const size_t skip = (parts_total > 0 && part_first + order[k] > 0) ? 0 : 1;
+                zip_encode(set->merges, sy.data() + skip, sy.size() - skip, set->tok_full[k]);
+                run_encode(set->run_merges, sy.data() + skip, sy.size() - skip, set->fold_sym, &set->first_run[k], set->run_tok_full[k]);
             })) throw std::bad_alloc();
         for (int k = 0; k < ns; ++k) {
             set->zip_tokens_full += (long long)set->tok_full[k].size();
@@ -445,6 +454,16 @@ extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset**
     return IMC_OK;
 }
 
+extern "C" int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset** out) {
+    return seqset_create_impl(seqs, C, 0, 0, out);
+}
+
+extern "C" int imc_seqset_create_parts(const imc_seq* const* parts, int n_local, int part_first, int parts_total, imc_seqset** out) {
+    if (n_local < 1 || parts_total < 1 || part_first < 0 || part_first + n_local > parts_total || parts_total % n_local != 0 || part_first % n_local != 0)
+        return fail(IMC_ERR_INVALID, "parts: every rank holds the same number n_local of consecutive parts (first = rank * n_local) of parts_total");
+    return seqset_create_impl(parts, n_local, part_first, parts_total, out);
+}
+
 extern "C" int imc_seqset_destroy(imc_seqset* set) {
     if (!set) return IMC_OK;
     const bool mine = g_ctx.pid == getpid();
@@ -452,7 +471,7 @@ extern "C" int imc_seqset_destroy(imc_seqset* set) {
         set->d_words.release(); set->d_streams.release(); set->d_chain.release();
         set->d_pi.release(); set->d_T.release(); set->d_E.release(); set->d_out.release();
         for (int i = 0; i < 2; ++i) { set->d_pnext[i].release(); set->d_vec[i].release(); set->d_prog[i].release(); }
-        set->d_spec.release(); set->d_lists.release();
+        set->d_spec.release(); set->d_lists.release(); set->d_parts.release(); set->d_gather.release();
         if (set->serial.done) cudaEventDestroy(set->serial.done);
     }
     for (ZipDevice* z : set->zip_dev) {
@@ -590,6 +609,8 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // choice among whole chunks / pipelined pieces / one warp per chain / segments, the launch and (segmented) the folds.
 // spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
 // set->d_chain[n][chunk] for the points served.
+static const int MAX_POINTS_PARTS = 32768;
+
 static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E, bool spec,
                     const int* plist, const int* pcount, const double* d_spec, int spec_stride, cudaStream_t st) {
     NvtxRange nvtx_pass(spec ? "imc: zip pass (spectral form)" : "imc: zip pass (plain form)");
@@ -625,7 +646,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     {
         const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
         const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
-        const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64;
+        const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64 && set->parts_total == 0;
         if (scarce && (seglen == 0 || g_ctx.opt_zip_lanes == 0)) {
             const double c = 1.4 * K * K / 16.0 + 5.0;
             const double lat = (plan.lanes == 4 ? 49.0 : 36.0) * K, lat32 = 80.0 + 14.5 * K;
@@ -693,7 +714,14 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     }
     DeviceBuf& d_vec = set->d_vec[pass];
     DeviceBuf& d_prog = set->d_prog[pass];
-    if (seglen > 0 && K <= 64) {
+    const bool parts = set->parts_total > 0;
+    if (parts) {      // parts of one long chunk: always segments (a later part has no start of its own), folded into set->d_parts
+        if (K > 64) return fail(IMC_ERR_UNSUPPORTED, "parts mode supports K <= 64");
+        if (seglen <= 0) seglen = std::max<long long>(256, std::min<long long>(4096, z->max_ntok / 64));
+        seglen = (seglen + 15) / 16 * 16;
+        if ((rc = zip_split(z, K, (int)seglen, &split, ns, set->part_first))) return rc;
+        if ((rc = d_vec.reserve(sizeof(double) * (size_t)N * (size_t)split->nchains * (K + 1)))) return rc;
+    } else if (seglen > 0 && K <= 64) {
         seglen = (seglen + 15) / 16 * 16;
         if (seglen < z->max_ntok) {
             if ((rc = zip_split(z, K, (int)seglen, &split))) return rc;
@@ -743,7 +771,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
     if (split) {
-        double* vec2 = za.vec_out + (size_t)N * split->nchains * za.vec_stride;
+        double* vec2 = parts ? (double*)set->d_parts.p : za.vec_out + (size_t)N * split->nchains * za.vec_stride;
         for (int n0 = 0; n0 < N; n0 += 65535) {      // gridDim.y <= 65535
             const int nn = std::min(N - n0, 65535);
             // without a list blockIdx.y is the point itself: shift the per-point bases instead
@@ -755,15 +783,20 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
                 CUDA_TRY(cudaGetLastError());
                 g_launches += 1;
             }
-            zip_fold_kernel<<<dim3(split->n_final, nn), 64, 0, st>>>(za.vec_out + voff * split->nchains * za.vec_stride, split->nchains,
-                vec2 + voff * split->nvec2 * za.vec_stride, split->nvec2, za.vec_stride, (const ZipFoldItem*)split->items2.p, K,
-                za.chain_out + voff * za.out_stride, za.out_stride, d_spec ? d_spec + voff * spec_stride : nullptr, spec_stride, plist, pcount, n0);
-            CUDA_TRY(cudaGetLastError());
-            g_launches += 1;
+            if (split->n_final > 0) {
+                zip_fold_kernel<<<dim3(split->n_final, nn), 64, 0, st>>>(za.vec_out + voff * split->nchains * za.vec_stride, split->nchains,
+                    vec2 + voff * split->nvec2 * za.vec_stride, split->nvec2, za.vec_stride, (const ZipFoldItem*)split->items2.p, K,
+                    za.chain_out + voff * za.out_stride, za.out_stride, d_spec ? d_spec + voff * spec_stride : nullptr, spec_stride, plist, pcount, n0);
+                CUDA_TRY(cudaGetLastError());
+                g_launches += 1;
+            }
         }
     }
     return IMC_OK;
 }
+
+static int parts_finish(imc_seqset* set, int N, int K, const double* d_spec, int spec_stride, const int* okflag, double* d_out,
+                        cudaStream_t st);     // comm_host.inl: all-gather of the part blocks + zip_fold_parts_kernel
 
 static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E,
                              double* d_out, cudaStream_t st) {
@@ -780,6 +813,10 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
     if ((rc = set->d_chain.reserve(sizeof(double) * (size_t)N * ns))) return rc;
 
     int which = (int)g_ctx.opt_forward_kernel;
+    if (set->parts_total > 0) {
+        if (!zip_supported(K)) return fail(IMC_ERR_UNSUPPORTED, "parts mode runs on the zip kernel (K <= 40), not K = %d", K);
+        which = KERNEL_ZIP;
+    }
     if (which == KERNEL_AUTO) {
         ZipPlan probe;
         // zip wherever its dictionary fits; large alphabets x large K that do not fit fall back to the per-site kernels
@@ -799,6 +836,13 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         // every chain result is written by exactly one of the passes below; a slot nobody writes must read as NaN, never as
         // the previous call's value
         CUDA_TRY(cudaMemsetAsync(set->d_chain.p, 0xff, sizeof(double) * (size_t)N * ns, st));
+        const bool parts = set->parts_total > 0;
+        if (parts) {        // block of this rank: vec[N][ns * K][K + 1], then run_sites[ns]
+            if (N > MAX_POINTS_PARTS) return fail(IMC_ERR_UNSUPPORTED, "parts mode: at most %d parameter points per call", MAX_POINTS_PARTS);
+            const size_t vecs = (size_t)N * ns * K * (K + 1);
+            if ((rc = set->d_parts.reserve(sizeof(double) * (vecs + ns)))) return rc;
+            CUDA_TRY(cudaMemsetAsync(set->d_parts.p, 0xff, sizeof(double) * vecs, st));
+        }
         // Spectral form where the run symbol's runs carry most of the compression: zip_spectral_kernel diagonalises C_r of
         // every point and sorts the points into those it could serve (ok list) and the others (plain form, bad list).
         bool use_spec = g_ctx.opt_zip_spectral == 1;
@@ -809,11 +853,12 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         if (!use_spec) {
             g_last_kernel = "zip";
             if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, false, nullptr, nullptr, nullptr, 0, st))) return rc;
+            if (parts) return parts_finish(set, N, K, nullptr, 0, nullptr, d_out, st);
             return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
         }
         const int sstride = 2 * K + S * K + S * K * K + 1;
         if ((rc = set->d_spec.reserve(sizeof(double) * (size_t)N * sstride))) return rc;
-        if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)2 * N + 2)))) return rc;
+        if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)3 * N + 2)))) return rc;
         int* lists = (int*)set->d_lists.p;
         CUDA_TRY(cudaMemsetAsync(lists, 0, sizeof(int) * 2, st));
         NvtxRange nvtx_spec("imc: spectral forward (prepare + passes)");
@@ -821,7 +866,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         sa.N = N; sa.K = K; sa.S = S; sa.run_sym = set->fold_sym;
         sa.pi = d_pi; sa.T = d_T; sa.E = d_E;
         sa.spec = (double*)set->d_spec.p; sa.spec_stride = sstride;
-        sa.counts = lists; sa.ok_list = lists + 2; sa.bad_list = lists + 2 + N;
+        sa.counts = lists; sa.ok_list = lists + 2; sa.bad_list = lists + 2 + N; sa.okflag = lists + 2 + 2 * N;
         sa.force_bad = g_ctx.opt_zip_spectral_force_bad ? 1 : 0;
         sa.point_base = 0;
         {
@@ -845,6 +890,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         g_last_kernel = "zip-spectral";
         if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, true, sa.ok_list, sa.counts, sa.spec, sstride, st))) return rc;
         if ((rc = zip_pass(set, N, K, S, d_pi, d_T, d_E, false, sa.bad_list, sa.counts + 1, nullptr, 0, st))) return rc;
+        if (parts) return parts_finish(set, N, K, sa.spec, sstride, sa.okflag, d_out, st);
         return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
     }
     if (!set->packable)

@@ -116,6 +116,12 @@ static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_overrid
     return IMC_OK;
 }
 
+// chunk index (as given at creation) of stream k
+static int set_chunk_of_stream(const imc_seqset* set, int k) {
+    for (int c = 0; c < set->n_chunks; ++c) if (set->stream_of_chunk[c] == k) return c;
+    return 0;
+}
+
 // token streams over the first M dictionary ids, level-ordered, on the device (cached per M and form)
 static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out);
 static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false) {
@@ -156,7 +162,7 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
         long long rs = chunks[i].first_run;
         if (spec) for (uint32_t t : rtok[k]) rs += t >> 8;
         chunks[i].run_sites = (int)rs;
-        chunks[i].pad = 0;
+        chunks[i].continues = set->parts_total > 0 ? set->part_first + set_chunk_of_stream(set, k) : 0;     // global part index (0: has its own start)
         off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
     std::vector<uint8_t> flat((size_t)off, 0);
@@ -202,30 +208,47 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
     return IMC_OK;
 }
 
-// chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen)
-static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out);
-static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out) {
-    try { return zip_split_build(z, K, seglen, out); }
+// chunk list of z cut into segments of seglen tokens (a multiple of 16) for a K-state model, cached per (K, seglen).
+// parts_local > 0: the chunks are parts part_first .. part_first + parts_local - 1 of ONE long chunk (parts mode): every
+// part is folded into vec2 only -- part 0 into one vector, a later part (all of whose segments start from unit vectors)
+// into the K columns of its transfer matrix, vector c of local part lp at index lp * K + c -- and zip_fold_parts_kernel
+// finishes the job after the all-gather.
+static int zip_split_build(ZipDevice* z, int K, int seglen, int parts_local, int part_first, ZipSplit** out);
+static int zip_split(ZipDevice* z, int K, int seglen, ZipSplit** out, int parts_local = 0, int part_first = 0) {
+    try { return zip_split_build(z, K, seglen, parts_local, part_first, out); }
     catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while cutting chunks into segments"); }
 }
-static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
-    for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen) { *out = sp; return IMC_OK; }
+static int zip_split_build(ZipDevice* z, int K, int seglen, int parts_local, int part_first, ZipSplit** out) {
+    for (ZipSplit* sp : z->splits) if (sp->K == K && sp->seglen == seglen && sp->parts_local == parts_local) { *out = sp; return IMC_OK; }
     std::vector<ZipChunk> chains;
     std::vector<ZipFoldItem> items1, items2;
     int nvec2 = 0;
+    if (parts_local > 0) nvec2 = parts_local * K;
     for (const ZipChunk& ch : z->host_chunks) {
         const int nseg = std::max(1, (ch.ntok + seglen - 1) / seglen);
         const int first_chain = (int)chains.size();
+        const bool cont = parts_local > 0 && ch.continues > 0;
         for (int sg = 0; sg < nseg; ++sg) {
             ZipChunk c = ch;
             c.tok_off = ch.tok_off + (long long)sg * seglen * (z->spec ? 4 : 1);
             c.ntok = std::max(0, std::min(seglen, ch.ntok - sg * seglen));
-            for (int col = 0; col < (sg == 0 ? 1 : K); ++col) {
-                c.first_sym = sg == 0 ? ch.first_sym : -1 - col;
+            const bool own_start = sg == 0 && !cont;
+            for (int col = 0; col < (own_start ? 1 : K); ++col) {
+                c.first_sym = own_start ? ch.first_sym : -1 - col;
                 c.first_run = sg == 0 ? ch.first_run : 0;
                 c.out_index = (int)chains.size();
                 chains.push_back(c);
             }
+        }
+        if (parts_local > 0) {
+            const int lp = ch.continues - part_first;         // local part index
+            if (!cont) {      // part 0: segment 0 is one chain, segment s >= 1 column c at first_chain + 1 + (s-1) K + c
+                items1.push_back({first_chain, first_chain + 1, nseg - 1, lp * K, 0, 1, 0, 0});
+            } else {          // later part: segment s column c at first_chain + s K + c; one fold per start column
+                for (int col = 0; col < K; ++col)
+                    items1.push_back({first_chain + col, first_chain + K, nseg - 1, lp * K + col, 0, 1, 0, 0});
+            }
+            continue;
         }
         // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
         if (nseg <= 32) {
@@ -250,7 +273,7 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, ZipSplit** out) {
     std::stable_sort(sorted.begin(), sorted.end(), [](const ZipChunk& x, const ZipChunk& y) { return x.ntok > y.ntok; });
     ZipSplit* sp = new (std::nothrow) ZipSplit;
     if (!sp) return fail(IMC_ERR_NOMEM, "out of memory");
-    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size();
+    sp->K = K; sp->seglen = seglen; sp->nchains = (int)sorted.size(); sp->parts_local = parts_local;
     sp->n_level1 = (int)items1.size(); sp->n_final = (int)items2.size(); sp->nvec2 = nvec2;
     int rc;
     if ((rc = sp->chunks.reserve(sizeof(ZipChunk) * sorted.size())) ||

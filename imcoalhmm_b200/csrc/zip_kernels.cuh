@@ -47,7 +47,8 @@ struct ZipChunk {
     int out_index;       // column of chain_out this chunk writes
     int first_run;       // spectral form: sites of the run symbol between position 0 and the first token (<= RUN_MAX)
     int run_sites;       // spectral form: first_run + the runs of all tokens; the result gets run_sites * ln(lambda_max)
-    int pad;
+    int continues;       // 1: this is a later part of a chunk cut across ranks -- no start of its own (position 0 is an ordinary
+                         // site, all of its segments run from unit vectors); see zip_fold_parts_kernel
 };
 
 struct ZipArgs {
@@ -1069,6 +1070,7 @@ struct ZipSpecArgs {
     double* spec; int spec_stride;
     int* ok_list; int* bad_list;
     int* counts;            // [2]: points in ok_list, bad_list (zeroed before the launch)
+    int* okflag;            // [N]: 1 where the point went to ok_list
     int force_bad;          // experiment switch: send every point to the plain form
     int point_base;         // index of this launch's first point in the caller's batch (the lists hold batch indices)
 };
@@ -1226,6 +1228,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
     if (tid == 0) {
         if (flag[0]) s.ok_list[atomicAdd(s.counts, 1)] = s.point_base + n;
         else s.bad_list[atomicAdd(s.counts + 1, 1)] = s.point_base + n;
+        s.okflag[s.point_base + n] = flag[0] ? 1 : 0;
     }
 }
 
@@ -1308,6 +1311,76 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
         else if (!(sum > 0.0)) r = -INFINITY;
         else r = log(sum) + scale * LN2 + (spec ? (double)it.run_sites * spec[(size_t)n * spec_stride + spec_stride - 1] : 0.0);
         chain_out[(size_t)n * out_stride + it.out_index] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One long chunk cut into consecutive PARTS that live on different ranks (fewer chunks than GPUs): every part is
+// run in segmented mode; part 0 folds its segments into a vector, every later part into the K columns of its transfer
+// matrix (zip_fold_kernel, dst == 1).  The per-rank blocks are all-gathered and this kernel folds alpha <- P_part alpha over
+// the parts in order, for one parameter point per CTA (64 threads, K <= 64).
+//   gathered: [rank][block] with block = double vec[N][n_local * K][K + 1], then run_sites[n_local]
+//   part p lives on rank p / n_local as local part p % n_local; its vector c of point n is vec[n][(p % n_local) * K + c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) zip_fold_parts_kernel(const double* gathered, size_t block_doubles, int N, int K, int n_local,
+                                                            int n_parts, const double* spec, int spec_stride, const int* okflag,
+                                                            double* out) {
+    __shared__ double w[64];
+    __shared__ double red[2];
+    __shared__ int s_e[2];
+    const int n = blockIdx.x, j = threadIdx.x, vs = K + 1;
+    const bool sp = spec && (!okflag || okflag[n]);
+    auto vec_of = [&](int part, int c) {
+        return gathered + (size_t)(part / n_local) * block_doubles + ((size_t)n * n_local * K + (size_t)(part % n_local) * K + c) * vs;
+    };
+    const double* v0 = vec_of(0, 0);
+    double alpha = j < K ? v0[j] : 0.0;
+    double scale = v0[K];
+    double run_sites = 0.0;
+    for (int p = 0; p < n_parts; ++p) run_sites += gathered[(size_t)(p / n_local) * block_doubles + (size_t)N * n_local * K * vs + (p % n_local)];
+    for (int p = 1; p < n_parts; ++p) {
+        const double* cj = vec_of(p, j < K ? j : 0);
+        const double ec = j < K ? cj[K] : 0.0;
+        bool matters = j < K && alpha != 0.0;
+        if (matters) {
+            bool any = false;
+            for (int r = 0; r < K; ++r) any = any || cj[r] != 0.0;
+            matters = any;
+        }
+        int e = matters ? (int)ec : -0x40000000;
+        for (int m = 16; m >= 1; m >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, m));
+        if ((j & 31) == 0) s_e[j >> 5] = e;
+        __syncthreads();
+        const int emax = max(s_e[0], s_e[1]);
+        const int d = (int)ec - emax;
+        w[j] = matters ? (d < -1000 ? 0.0 : alpha * pow2_neg(-d)) : 0.0;
+        __syncthreads();
+        double acc = 0.0;
+        if (j < K)
+            for (int c = 0; c < K; ++c) acc = fma(w[c], vec_of(p, c)[j], acc);
+        double sum = sp ? fabs(acc) : acc;
+        for (int m = 16; m >= 1; m >>= 1) sum = sp ? fmax(sum, shfl_xor_f64(sum, m)) : sum + shfl_xor_f64(sum, m);
+        __syncthreads();
+        if ((j & 31) == 0) red[j >> 5] = sum;
+        __syncthreads();
+        sum = sp ? fmax(red[0], red[1]) : red[0] + red[1];
+        int en = 0;
+        if (sum > 0.0 && sum < 1.7e308) { en = exponent_of(sum); acc *= pow2_neg(en); }
+        alpha = acc;
+        scale += (emax > -0x40000000 ? (double)emax : 0.0) + (double)en;
+        __syncthreads();
+    }
+    double sum = sp ? (j < K ? spec[(size_t)n * spec_stride + K + j] * alpha : 0.0) : alpha;
+    for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_f64(sum, m);
+    if ((j & 31) == 0) red[j >> 5] = sum;
+    __syncthreads();
+    if (j == 0) {
+        sum = red[0] + red[1];
+        double r;
+        if (sum != sum) r = sum;
+        else if (!(sum > 0.0)) r = -INFINITY;
+        else r = log(sum) + scale * LN2 + (sp ? run_sites * spec[(size_t)n * spec_stride + spec_stride - 1] : 0.0);
+        out[n] = r;
     }
 }
 

@@ -87,7 +87,9 @@ class ForwarderSet(object):
     forward(pi, T, E) == sum(f.forward(pi, T, E) for f in forwarders)   (likelihood.py:33)
     """
 
-    def __init__(self, forwarders):
+    def __init__(self, forwarders, parts=None):
+        """parts=(part_first, parts_total): the forwarders are consecutive PARTS of one long chunk that is cut over the
+        ranks of the library's communicator (fewer chunks than GPUs; include/imcoalhmm_b200.h: imc_seqset_create_parts)."""
         if isinstance(forwarders, Forwarder):
             forwarders = [forwarders]
         self.forwarders = list(forwarders)
@@ -95,7 +97,10 @@ class ForwarderSet(object):
         lib = _lib.load()
         arr = (_lib.c_vp * max(1, len(self._seqs)))(*[s.handle for s in self._seqs])
         h = _lib.c_vp()
-        check(lib.imc_seqset_create(arr, len(self._seqs), ctypes.byref(h)))
+        if parts is not None:
+            check(lib.imc_seqset_create_parts(arr, len(self._seqs), int(parts[0]), int(parts[1]), ctypes.byref(h)))
+        else:
+            check(lib.imc_seqset_create(arr, len(self._seqs), ctypes.byref(h)))
         self._handle = h
         n, sites, nbytes = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
         check(lib.imc_seqset_info(h, ctypes.byref(n), ctypes.byref(sites), ctypes.byref(nbytes)))

@@ -88,6 +88,14 @@ int imc_seq_destroy(imc_seq* seq);
 typedef struct imc_seqset imc_seqset;
 
 int imc_seqset_create(const imc_seq* const* seqs, int C, imc_seqset** out);
+/* Fewer chunks than GPUs: ONE long chunk cut into parts_total consecutive parts, every rank holding n_local of
+ * them (parts[i] = part part_first + i, part_first = rank * n_local).  A forward / loglik call on such a set is collective
+ * over a communicator of parts_total / n_local ranks: every part runs in segmented mode -- part 0 from pi, every later part
+ * from the K unit vectors, which yields its K x K transfer matrix --, the per-rank blocks (float64 [N][n_local K][K+1]) are
+ * exchanged with ONE ncclAllGather, and every rank folds alpha <- P_part alpha over the parts in order: the log-likelihood of
+ * the whole chunk, the same bits on every rank.  With parts_total == n_local a single process holds all parts and no
+ * communicator is needed.  K <= 40, at most 32768 parameter points per call. */
+int imc_seqset_create_parts(const imc_seq* const* parts, int n_local, int part_first, int parts_total, imc_seqset** out);
 int imc_seqset_destroy(imc_seqset* set);
 /* any output may be NULL */
 int imc_seqset_info(const imc_seqset* set, int* n_chunks, int64_t* total_sites, int64_t* packed_bytes);

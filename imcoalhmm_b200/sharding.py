@@ -8,13 +8,30 @@ are summed by ONE all-reduce (NCCL over NVLink on the GPUs; gloo in the CPU test
 import numpy as np
 
 
-def partition_chunks(lengths, world_size):
-    """Contiguous blocks [(start, end), ...] of chunk indices, one per rank, balanced by total sites.
+def chunk_cost(symbols):
+    """What a chunk costs the compressed forward kernel, up to a constant: the number of mat-vecs it is walked in.  In the
+    run-token form (csrc/tokenizer.inl) that is one per maximal stretch of a non-run symbol -- every lone mismatch, every block
+    of missing data -- however many matching sites lie in between; the sites themselves cost nothing.  O(L) in numpy."""
+    sym = np.asarray(symbols)
+    if sym.size == 0:
+        return 0
+    run_sym = int(np.argmax(np.bincount(sym.astype(np.int64), minlength=3)))
+    other = sym != run_sym
+    starts = other & np.concatenate([[True], sym[1:] != sym[:-1]])
+    return int(starts.sum()) + 1
 
+
+def partition_chunks(lengths, world_size, weights=None):
+    """Contiguous blocks [(start, end), ...] of chunk indices, one per rank, balanced by total weight.
+
+    weights defaults to the chunk lengths (sites); pass `[chunk_cost(c) for c in chunks]` to balance what the GPU time is
+    proportional to -- mat-vecs, not sites: two alignments of equal length differ in cost by their divergence.
     Greedy prefix split at the ideal cumulative boundaries; every rank gets a (possibly empty) block and the
     blocks tile range(len(lengths)) in order, so chunk order -- and therefore the summation order inside a rank --
     is preserved."""
-    lengths = np.asarray(lengths, dtype=np.int64)
+    lengths = np.asarray(lengths if weights is None else weights, dtype=np.int64)
+    if weights is not None and len(weights) != len(np.atleast_1d(lengths)):
+        raise ValueError("one weight per chunk")
     n = lengths.size
     if world_size < 1:
         raise ValueError("world_size must be >= 1")

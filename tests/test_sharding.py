@@ -98,3 +98,22 @@ def test_library_comm_single_rank_is_a_no_op():
         dist.destroy_process_group()
     _lib.comm_destroy()                      # harmless without a communicator
     assert _lib.comm_info()["nranks"] == 1
+
+
+def test_partition_by_cost_balances_mat_vecs_not_sites():
+    """GPU time follows the number of run tokens (one mat-vec per non-matching stretch), not the number of sites: equal-length
+    chunks of different divergence are balanced by `weights=chunk_cost`."""
+    from imcoalhmm_b200.sharding import chunk_cost, partition_chunks
+    rng = np.random.default_rng(0)
+    chunks = [rng.choice(3, size=20000, p=[1 - d - 0.001, d, 0.001]).astype(np.uint8) for d in (0.001, 0.001, 0.001, 0.001, 0.02, 0.02)]
+    cost = [chunk_cost(c) for c in chunks]
+    assert cost[4] > 5 * cost[0]
+    # cost counts maximal stretches: 0 0 1 1 0 2 2 2 0 1 -> three stretches (+1)
+    assert chunk_cost(np.array([0, 0, 1, 1, 0, 2, 2, 2, 0, 1], dtype=np.uint8)) == 4
+    assert chunk_cost(np.zeros(0, dtype=np.uint8)) == 0
+    by_sites = partition_chunks([len(c) for c in chunks], 2)
+    by_cost = partition_chunks([len(c) for c in chunks], 2, weights=cost)
+    assert by_sites == [(0, 3), (3, 6)]
+    load = lambda blocks: [sum(cost[a:b]) for a, b in blocks]
+    assert max(load(by_cost)) < max(load(by_sites))
+    assert by_cost[0][1] >= 4 and by_cost[0][0] == 0 and by_cost[-1][1] == 6

@@ -646,7 +646,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     {
         const int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
         const long long slots = (long long)sms * plan.ctas_per_sm * (plan.threads / plan.lanes);
-        const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 256 && K <= 64 && set->parts_total == 0;
+        const bool scarce = (long long)N * ns * 4 <= slots && z->max_ntok >= 64 && K <= 64 && set->parts_total == 0;
         if (scarce && (seglen == 0 || g_ctx.opt_zip_lanes == 0)) {
             const double c = 1.4 * K * K / 16.0 + 5.0;
             const double lat = (plan.lanes == 4 ? 49.0 : 36.0) * K, lat32 = 80.0 + 14.5 * K;
@@ -665,7 +665,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             long long best_seg = -1;
             int best_lanes = plan.lanes;
             if (seglen == 0) {
-                for (long long sl = 256; sl < z->max_ntok; sl *= 2) {        // (c)
+                for (long long sl = 64; sl < z->max_ntok; sl *= 2) {        // (c)
                     const double t = cost_seg(sl);
                     if (t < 0.8 * best) { best = t; best_seg = sl; }
                 }

@@ -1122,61 +1122,77 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
     if (tid == 0 && !(red[1] <= 1e-13 * red[0])) flag[0] = 0;
     __syncthreads();
     if (flag[0]) {
-        // ---- cyclic Jacobi with the round-robin ordering: m - 1 rounds of m / 2 disjoint rotations per sweep
-        const int m = (K + 1) & ~1, half = m / 2;
+        // ---- cyclic Jacobi with the round-robin ordering: m - 1 rounds of m / 2 disjoint rotations per sweep.  Warp w takes
+        // the pairs w, w + nwarps, ...; lane j the column (row) j, j + 32: no integer division in the loops.
+        const int m = (K + 1) & ~1, half = m / 2, nwarps = SPEC_THREADS / 32, warp = tid >> 5, lane = tid & 31;
         const double tiny = 1e-300;
+        auto pair_of = [&](int round, int pr, int& p, int& q) {     // (m-1, round) for pr == 0, else ((round + pr), (round - pr)) mod (m-1)
+            int a1 = round + pr, a2 = round - pr;
+            if (a1 >= m - 1) a1 -= m - 1;
+            if (a2 < 0) a2 += m - 1;
+            p = pr == 0 ? m - 1 : a1;
+            q = pr == 0 ? round : a2;
+            if (p > q) { const int t = p; p = q; q = t; }
+        };
         for (int sweep = 0; sweep < 30; ++sweep) {
             double off = 0.0;
-            for (int x = tid; x < K * K; x += SPEC_THREADS) { const int i = x / K, j = x - i * K; if (i != j) off = fmax(off, fabs(A[i * LD + j])); }
+            for (int i = warp; i < K; i += nwarps)
+                for (int j = lane; j < K; j += 32) if (i != j) off = fmax(off, fabs(A[i * LD + j]));
             for (int mm = 16; mm >= 1; mm >>= 1) off = fmax(off, shfl_xor_f64(off, mm));
             if (tid == 0) red[2] = 0.0;
             __syncthreads();
-            if ((tid & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(red + 2), (unsigned long long)__double_as_longlong(off));
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(red + 2), (unsigned long long)__double_as_longlong(off));
             __syncthreads();
-            if (red[2] <= 1e-18 * red[0]) { if (tid == 0) flag[1] = 1; break; }
+            // off-diagonal residual r: A = Q Lambda Q^T holds to r, which moves logL by about r x sites (1e-16 x 1e6 sites = 1e-10
+            // absolute, 5e-15 of a typical |logL|); rounding noise keeps r near 1e-17 however many sweeps follow
+            if (red[2] <= 1e-16 * red[0]) { if (tid == 0) flag[1] = 1; break; }
             for (int round = 0; round < m - 1; ++round) {
-                // pair x of this round: (m-1, round) for x == 0, else ((round + x) mod (m-1), (round - x) mod (m-1))
                 if (tid < half) {
-                    int p = tid == 0 ? m - 1 : (round + tid) % (m - 1), q = tid == 0 ? round : (round - tid + (m - 1)) % (m - 1);
-                    if (p > q) { const int t = p; p = q; q = t; }
+                    int p, q;
+                    pair_of(round, tid, p, q);
                     double c = 1.0, sn = 0.0;
                     if (q < K) {
                         const double apq = A[p * LD + q], app = A[p * LD + p], aqq = A[q * LD + q];
                         if (fabs(apq) > tiny) {
                             const double th = (aqq - app) / (2.0 * apq);
                             const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-                            c = 1.0 / sqrt(t * t + 1.0);
+                            c = rsqrt(t * t + 1.0);
                             sn = t * c;
                         }
                     }
                     rot[2 * tid] = c; rot[2 * tid + 1] = sn;
                 }
                 __syncthreads();
-                for (int x = tid; x < half * K; x += SPEC_THREADS) {          // rows: A <- J^T A
-                    const int pr = x / K, j = x - pr * K;
-                    int p = pr == 0 ? m - 1 : (round + pr) % (m - 1), q = pr == 0 ? round : (round - pr + (m - 1)) % (m - 1);
-                    if (p > q) { const int t = p; p = q; q = t; }
+                for (int pr = warp; pr < half; pr += nwarps) {                 // rows: A <- J^T A
+                    int p, q;
+                    pair_of(round, pr, p, q);
                     if (q >= K) continue;
                     const double c = rot[2 * pr], sn = rot[2 * pr + 1];
-                    const double ap = A[p * LD + j], aq = A[q * LD + j];
-                    A[p * LD + j] = c * ap - sn * aq;
-                    A[q * LD + j] = sn * ap + c * aq;
+                    if (sn == 0.0) continue;
+                    for (int j = lane; j < K; j += 32) {
+                        const double ap = A[p * LD + j], aq = A[q * LD + j];
+                        A[p * LD + j] = c * ap - sn * aq;
+                        A[q * LD + j] = sn * ap + c * aq;
+                    }
                 }
                 __syncthreads();
-                for (int x = tid; x < half * K; x += SPEC_THREADS) {          // columns: A <- A J, Q <- Q J
-                    const int pr = x / K, i = x - pr * K;
-                    int p = pr == 0 ? m - 1 : (round + pr) % (m - 1), q = pr == 0 ? round : (round - pr + (m - 1)) % (m - 1);
-                    if (p > q) { const int t = p; p = q; q = t; }
+                for (int pr = warp; pr < half; pr += nwarps) {                 // columns: A <- A J, Q <- Q J
+                    int p, q;
+                    pair_of(round, pr, p, q);
                     if (q >= K) continue;
                     const double c = rot[2 * pr], sn = rot[2 * pr + 1];
-                    const double ap = A[i * LD + p], aq = A[i * LD + q];
-                    double np = c * ap - sn * aq, nq = sn * ap + c * aq;
-                    if (sn != 0.0) { if (i == p) nq = 0.0; if (i == q) np = 0.0; }     // the annihilated pair, exactly
-                    A[i * LD + p] = np;
-                    A[i * LD + q] = nq;
-                    const double vp = Q[i * LD + p], vq = Q[i * LD + q];
-                    Q[i * LD + p] = c * vp - sn * vq;
-                    Q[i * LD + q] = sn * vp + c * vq;
+                    if (sn == 0.0) continue;
+                    for (int i = lane; i < K; i += 32) {
+                        const double ap = A[i * LD + p], aq = A[i * LD + q];
+                        double np = c * ap - sn * aq, nq = sn * ap + c * aq;
+                        if (i == p) nq = 0.0;                                  // the annihilated pair, exactly
+                        if (i == q) np = 0.0;
+                        A[i * LD + p] = np;
+                        A[i * LD + q] = nq;
+                        const double vp = Q[i * LD + p], vq = Q[i * LD + q];
+                        Q[i * LD + p] = c * vp - sn * vq;
+                        Q[i * LD + q] = sn * vp + c * vq;
+                    }
                 }
                 __syncthreads();
             }

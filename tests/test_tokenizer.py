@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import GOLDEN, ROOT
 from oracle import forward as F
 
 
@@ -81,3 +81,49 @@ def test_other_alphabets_and_degenerate_inputs(nsym):
     pairs = fset.zip_pairs()
     for c, chunk in enumerate(chunks):
         assert np.array_equal(expand(fset.zip_tokens(c), pairs, nsym), chunk[1:].astype(np.uint8))
+
+
+def _expand_run_tokens(first_run, words, pairs, nsym, run_sym):
+    table = [[s] for s in range(nsym)]
+    for left, right in pairs:
+        table.append(table[left] + table[right])
+    out = [run_sym] * first_run
+    for w in words.tolist():
+        out.extend(table[w & 0xff])
+        out.extend([run_sym] * (w >> 8))
+    return np.array(out, dtype=np.uint8)
+
+
+def test_run_tokens_round_trip_and_contract():
+    """The second re-encoding (spectral form): first_run sites of the run symbol, then words id | n << 8; any dictionary
+    cap expands back to the symbols bit for bit; runs longer than 4095 continue through entries of the run symbol itself;
+    pairs are learned over the entries only (the left part carries no run)."""
+    import imcoalhmm_b200 as m
+    rng = np.random.default_rng(42)
+    obs = np.load(os.path.join(GOLDEN, "example_pair.npz"))["symbols"]
+    long_run = rng.choice(3, size=30000, p=[0.955, 0.005, 0.04]).astype(np.uint8)
+    long_run[2000:14000] = 0                                   # 12 000 matching sites in a row
+    chunks = [obs[:30000], obs[30000:], long_run, np.zeros(5000, dtype=np.uint8), np.array([1], dtype=np.uint8),
+              np.array([2, 0, 0], dtype=np.uint8), np.zeros(0, dtype=np.uint8)]
+    s = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])
+    info = s.run_info()
+    assert info["run_sym"] == 0 and 3 <= info["ids_available"] <= 256
+    pairs = s.run_pairs()
+    assert pairs.shape == (info["ids_available"] - 3, 2) and (pairs < np.arange(3, info["ids_available"])[:, None]).all()
+    for ids in (None, 3, 4, min(9, info["ids_available"]), info["ids_available"]):
+        for c, chunk in enumerate(chunks):
+            first_run, words = s.run_tokens(c, ids)
+            assert first_run <= 4095 and ((words >> 8) <= 4095).all()
+            if ids is not None:
+                assert ((words & 0xff) < ids).all()
+            if len(chunk) == 0:
+                assert first_run == 0 and words.size == 0
+                continue
+            back = _expand_run_tokens(first_run, words, pairs, 3, 0)
+            assert np.array_equal(back, chunk[1:]), (ids, c)
+    # the all-matching chunk is one leading run plus one continuation token; the long run costs two continuation entries
+    first_run, words = s.run_tokens(3)
+    assert first_run == 4095 and words.size == 1 and (words[0] & 0xff) == 0 and (words[0] >> 8) == 5000 - 1 - 4095 - 1
+    # far fewer tokens than the pair dictionary on alignment-like data: one per mismatch or missing-data block
+    k10 = s.run_info(10)
+    assert k10["tokens"] * 2 < s.zip_info(10)["tokens"] * 3 and k10["tokens"] * 15 < s.total_sites

@@ -106,6 +106,7 @@ struct Context {
     long long opt_zip_spectral = 0;    // spectral form of the zip kernel (run tokens): 0 = auto, 1 = always, 2 = never
     long long opt_zip_mma = 0;         // MMA form of the spectral kernel: 0 = auto, 1 = always (tiles >= 8), 2 = never
     long long opt_zip_mma_shape = 0;   // launch shape of the MMA form: 0 = auto, 1..4 see zip_plan_k
+    long long opt_zip_run2 = 0;        // two-run form of the MMA shape: 0 = auto (fewer expected DMMA passes), 1 = always, 2 = never
     long long opt_zip_spectral_force_bad = 0;   // test switch: zip_spectral_kernel declares every point unfit (plain-form pass serves them)
     long long opt_comm_fused = 1;      // map peer mailboxes at imc_comm_init and all-reduce inside the reduction kernel
     long long opt_comm_enabled = 1;    // 0: forward / loglik calls return this rank's partial sums although a communicator exists
@@ -196,6 +197,8 @@ struct ZipDevice {
     bool spec = false;                        // run tokens (32-bit words) for the spectral form of the kernel
     int hot_id = 0;                           // spec: the most frequent entry and its share of the tokens
     double hot_share = 0.0;
+    bool run2 = false;                        // two-run form (nsym + 2 base entries, second power table)
+    double est_passes = 1.0;                  // expected MMA passes per warp-step: 1 + sum over cold ids of P(some chain of 8 is on it)
     long long total_tokens = 0;
     int max_ntok = 0;
     std::vector<ZipChunk> host_chunks;        // sorted by ntok, descending
@@ -228,6 +231,13 @@ struct imc_seqset {
     std::vector<std::vector<uint32_t>> run_tok_full;   // per stream, over all run_merges.size() ids
     std::vector<int> first_run;                        // per stream
     long long zip_tokens_full = 0, run_tokens_full = 0;   // stream lengths over the full dictionaries (which form compresses better)
+    // two-run form (tokenizer.inl; built on first use): second run symbol, its own pair dictionary over nsym + 2 base ids
+    int run2_state = 0;                                // 0 = not looked at yet, 1 = available, -1 = nothing to gain / not possible
+    int run_sym2 = -1;
+    ZipMerges run2_merges;
+    std::vector<std::vector<uint32_t>> run2_tok_full;
+    std::vector<int> run2_first_run;
+    std::vector<long long> run2_sites;
     // device side (lazy)
     bool uploaded = false;
     DeviceBuf d_words, d_streams, d_chain, d_pi, d_T, d_E, d_out;
@@ -610,6 +620,7 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
 // set->d_chain[n][chunk] for the points served.
 static const int MAX_POINTS_PARTS = 32768;
+static thread_local bool g_want_run2 = false;      // two-run form wanted for the spectral pass of the current call
 
 static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E, bool spec,
                     const int* plist, const int* pcount, const double* d_spec, int spec_stride, cudaStream_t st) {
@@ -629,7 +640,8 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     if (spec && zip_mma_tile(zip_tile(K)) && g_ctx.opt_zip_mma != 2 && g_ctx.opt_zip_lanes == 0) {
         ZipPlan mp;
         ZipDevice* mz = nullptr;
-        if (zip_plan(K, S, avail, &mp, 0, true, true) == IMC_OK && zip_device(set, mp.M, &mz, true) == IMC_OK &&
+        const bool r2 = g_want_run2 && set->run2_state == 1;          // two-run form: decided by forward_local_dev before the preparation kernel
+        if (zip_plan(K, S, r2 ? set->run2_merges.size() : avail, &mp, 0, true, true, r2) == IMC_OK && zip_device(set, mp.M, &mz, true, r2) == IMC_OK &&
             (g_ctx.opt_zip_mma == 1 || mz->hot_share >= 0.5)) {
             plan = mp; z = mz; mma = true;
         }
@@ -704,6 +716,8 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     za.plist = plist; za.pcount = pcount;
     za.spec = d_spec; za.spec_stride = spec_stride;
     za.hot_id = z->hot_id;
+    za.nbase = S + (z->run2 ? 2 : 0);
+    za.run2 = z->run2 ? 1 : 0;
     za.mma_passes = nullptr;
     if (mma) {
         if (!g_mma_passes) {
@@ -763,8 +777,8 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
         za.vec_stride = K + 1;
     }
     if (spec || !plist) {
-        g_last_kernel = spec ? (split ? (mma ? "zip-spectral-mma-segmented" : "zip-spectral-segmented")
-                                      : (plan.lanes == 32 ? "zip-spectral-warp" : (mma ? "zip-spectral-mma" : "zip-spectral")))
+        g_last_kernel = spec ? (split ? (mma ? (z->run2 ? "zip-spectral-mma2-segmented" : "zip-spectral-mma-segmented") : "zip-spectral-segmented")
+                                      : (plan.lanes == 32 ? "zip-spectral-warp" : (mma ? (z->run2 ? "zip-spectral-mma2" : "zip-spectral-mma") : "zip-spectral")))
                              : (split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip"));
     }
     if ((rc = launch_zip(za, plan, st))) return rc;
@@ -856,7 +870,20 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
             if (parts) return parts_finish(set, N, K, nullptr, 0, nullptr, d_out, st);
             return launch_chain_reduce((const double*)set->d_chain.p, ns, N, d_out, st);
         }
-        const int sstride = 2 * K + S * K + S * K * K + 1;
+        // Two-run form of the MMA shape (the second run symbol -- missing data -- diagonalised as well): worth it where the
+        // dictionary that fits is small (K >= 32), judged by the expected DMMA work = tokens x passes per warp-step.
+        bool run2 = false;
+        if (g_ctx.opt_zip_run2 != 2 && !parts && zip_mma_tile(zip_tile(K)) && g_ctx.opt_zip_mma != 2 && g_ctx.opt_zip_lanes == 0) {
+            if ((rc = seqset_run2_prepare(set))) return rc;
+            ZipPlan p1, p2;
+            ZipDevice *z1 = nullptr, *z2 = nullptr;
+            if (set->run2_state == 1 && zip_plan(K, S, set->run_merges.size(), &p1, 0, true, true, false) == IMC_OK &&
+                zip_device(set, p1.M, &z1, true, false) == IMC_OK && zip_plan(K, S, set->run2_merges.size(), &p2, 0, true, true, true) == IMC_OK &&
+                zip_device(set, p2.M, &z2, true, true) == IMC_OK)
+                run2 = g_ctx.opt_zip_run2 == 1 || (double)z2->total_tokens * z2->est_passes < 0.93 * (double)z1->total_tokens * z1->est_passes;
+        }
+        g_want_run2 = run2;
+        const int sstride = zip_spec_stride(K, S, run2);
         if ((rc = set->d_spec.reserve(sizeof(double) * (size_t)N * sstride))) return rc;
         if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)3 * N + 2)))) return rc;
         int* lists = (int*)set->d_lists.p;
@@ -864,6 +891,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         NvtxRange nvtx_spec("imc: spectral forward (prepare + passes)");
         ZipSpecArgs sa;
         sa.N = N; sa.K = K; sa.S = S; sa.run_sym = set->fold_sym;
+        sa.run_sym2 = run2 ? set->run_sym2 : -1;
         sa.pi = d_pi; sa.T = d_T; sa.E = d_E;
         sa.spec = (double*)set->d_spec.p; sa.spec_stride = sstride;
         sa.counts = lists; sa.ok_list = lists + 2; sa.bad_list = lists + 2 + N; sa.okflag = lists + 2 + 2 * N;
@@ -871,7 +899,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         sa.point_base = 0;
         {
             static size_t attr_max = 0;
-            const size_t sm = zip_spec_smem(K);
+            const size_t sm = zip_spec_smem(K, run2);
             if (sm > 48 * 1024 && sm > attr_max) {
                 CUDA_TRY(cudaFuncSetAttribute(zip_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 attr_max = sm;
@@ -1006,6 +1034,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_spectral_force_bad")) { g_ctx.opt_zip_spectral_force_bad = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "zip_mma")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_mma must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_mma = value; return IMC_OK; }
     if (!strcmp(key, "zip_mma_shape")) { if (value < 0 || value > 4) return fail(IMC_ERR_INVALID, "zip_mma_shape must be in [0, 4]"); g_ctx.opt_zip_mma_shape = value; return IMC_OK; }
+    if (!strcmp(key, "zip_run2")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_run2 must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_run2 = value; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { g_ctx.opt_comm_enabled = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "comm_timeout_ms")) { if (value < 1) return fail(IMC_ERR_INVALID, "comm_timeout_ms must be >= 1"); g_ctx.opt_comm_timeout_ms = value; return IMC_OK; }
@@ -1025,6 +1054,7 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_spectral_force_bad")) { *value_out = g_ctx.opt_zip_spectral_force_bad; return IMC_OK; }
     if (!strcmp(key, "zip_mma")) { *value_out = g_ctx.opt_zip_mma; return IMC_OK; }
     if (!strcmp(key, "zip_mma_shape")) { *value_out = g_ctx.opt_zip_mma_shape; return IMC_OK; }
+    if (!strcmp(key, "zip_run2")) { *value_out = g_ctx.opt_zip_run2; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }
     if (!strcmp(key, "comm_enabled")) { *value_out = g_ctx.opt_comm_enabled; return IMC_OK; }
     if (!strcmp(key, "comm_timeout_ms")) { *value_out = g_ctx.opt_comm_timeout_ms; return IMC_OK; }

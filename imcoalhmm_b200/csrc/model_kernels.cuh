@@ -451,12 +451,20 @@ __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const doub
                 for (int e = 0; e < Sn.nE; ++e) s += Pi[(size_t)S.B[b] * n2 + Sn.E[e]];
                 part += u[S.B[b]] * s;
             }
-            red[tid] = part;
+            // fixed-shape tree (warp shuffles, then the warps' sums in order): deterministic, and not 128 serial reads by thread 0
+#pragma unroll
+            for (int mk = 16; mk >= 1; mk >>= 1) {
+                int lo = __double2loint(part), hi = __double2hiint(part);
+                lo = __shfl_xor_sync(0xffffffffu, lo, mk);
+                hi = __shfl_xor_sync(0xffffffffu, hi, mk);
+                part += __hiloint2double(hi, lo);
+            }
+            if ((tid & 31) == 0) red[tid >> 5] = part;
         }
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
-            for (int x = 0; x < nt; ++x) s += red[x];
+            for (int x = 0; x < (nt >> 5); ++x) s += red[x];
             J[i * K + i] = s;
         }
         // up_through_i[l] = sum_b u[b] P_i[b][Ln[l]]

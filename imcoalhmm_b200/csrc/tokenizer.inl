@@ -215,6 +215,55 @@ static void run_expand(const ZipMerges& mg, const std::vector<uint32_t>& in, int
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-run form.  Where shared memory holds only a dozen dictionary entries (K >= 32), a block of the SECOND run symbol r2
+// (missing data: runs of mean length 100) costs three or four power-of-two entries.  With C_r2 diagonalised as well
+// (zip_spectral_kernel), a run of m >= RUN2_MIN sites of r2 becomes two tokens over two FIXED extra base entries,
+//     (nsym     | m << 8 | RUN_TABLE2_BIT)   "B^-1, then Lambda2^m"      and      (nsym + 1 | n << 8)   "B, then n sites of r",
+// whatever m is; shorter runs of r2 stay ordinary entries.  The alphabet of this encoding is nsym + 2 base ids.
+// ------------------------------------------------------------------------------------------------
+constexpr int RUN2_MIN = 3;
+
+static void run2_tokenize(const uint8_t* sym, size_t n, int nsym, int run_sym, int run_sym2, int* first_run, std::vector<uint32_t>& out,
+                          long long* run2_sites) {
+    out.clear();
+    *run2_sites = 0;
+    size_t t = 0;
+    while (t < n && sym[t] == run_sym && (int)t < RUN_MAX) ++t;
+    *first_run = (int)t;
+    auto take_run = [&]() { int r = 0; while (t < n && sym[t] == run_sym && r < RUN_MAX) { ++t; ++r; } return r; };
+    while (t < n) {
+        if (sym[t] == run_sym2) {
+            size_t e = t;
+            while (e < n && sym[e] == run_sym2) ++e;
+            size_t m = e - t;
+            if (m >= (size_t)RUN2_MIN) {
+                while (m > 0) {                 // blocks longer than RUN_MAX: several (B^-1, B) pairs
+                    const int mm = (int)std::min<size_t>(m, RUN_MAX);
+                    out.push_back(run_word(nsym, mm) | RUN_TABLE2_BIT);
+                    *run2_sites += mm;
+                    m -= mm;
+                    t += mm;
+                    out.push_back(run_word(nsym + 1, m == 0 ? take_run() : 0));
+                }
+                continue;
+            }
+        }
+        const int id = sym[t++];
+        out.push_back(run_word(id, take_run()));
+    }
+}
+
+static void run2_encode(const ZipMerges& mg, const uint8_t* sym, size_t n, int nsym, int run_sym, int run_sym2, int* first_run,
+                        std::vector<uint32_t>& out, long long* run2_sites) {
+    run2_tokenize(sym, n, nsym, run_sym, run_sym2, first_run, out, run2_sites);
+    size_t len = out.size();
+    for (size_t i = 0; i < mg.pairs.size() && len >= 2; ++i)
+        len = run_replace(out.data(), len, mg.pairs[i][0], mg.pairs[i][1], (uint32_t)(mg.nsym + i));
+    out.resize(len);
+    out.shrink_to_fit();
+}
+
 // fn(i) for i in [0, n) on the host cores of the affinity mask; returns false if any call threw (out of memory)
 template <typename F>
 static bool parallel_for(int n, F&& fn) {

@@ -18,7 +18,7 @@ static int zip_tile(int K) {
 }
 static bool zip_supported(int K) { return K >= 1 && zip_tile(K) != 0; }
 
-struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; bool spec, mma; };
+struct ZipPlan { int lanes, threads, ctas_per_sm, M; size_t smem; bool spec, mma, run2; };
 #ifndef IMC_ZIP8_THREADS
 #define IMC_ZIP8_THREADS 512     // threads of the single-CTA-per-SM shape with 8 lanes per chain, K <= 24 (experiment builds: 640, 768)
 #endif
@@ -40,9 +40,10 @@ static thread_local int g_plan_chunks = 0;     // chunks of the set being planne
 static unsigned long long* g_mma_passes = nullptr;      // device counter (ZipArgs::mma_passes)
 
 template <int K, bool SPEC>
-static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, bool mma) {
+static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, bool mma, bool run2) {
     ZipPlan p;
     p.mma = false;
+    p.run2 = false;
     if constexpr (SPEC && K >= 8) {
         if (mma) {
             // shapes: 1 = one CTA of 512 threads per SM (256 for K >= 32), 2 = two CTAs of 256, 3 = four CTAs of 256 threads
@@ -60,11 +61,12 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, b
             p.ctas_per_sm = shape == 1 ? 1 : (shape == 2 ? 2 : 4);
             p.threads = shape == 1 ? (K <= 24 ? 512 : 256) : (shape == 4 ? 128 : 256);
             const size_t budget = (ZIP_SMEM_SM - 1024 * (p.ctas_per_sm - 1)) / p.ctas_per_sm;
-            p.M = std::min(avail_ids, ZipSmem<C, true>::max_entries(budget, S, p.threads));
+            p.run2 = run2;
+            p.M = std::min(avail_ids, ZipSmem<C, true>::max_entries(budget, S, p.threads, run2));
             if (g_ctx.opt_zip_max_entries > 0) p.M = std::min<int>(p.M, (int)g_ctx.opt_zip_max_entries);
-            p.M = std::max(p.M, S);
+            p.M = std::max(p.M, S + (run2 ? 2 : 0));
             p.spec = true;
-            p.smem = ZipSmem<C, true>::bytes(p.M, S, p.threads);
+            p.smem = ZipSmem<C, true>::bytes(p.M, S, p.threads, run2);
             return p;
         }
     }
@@ -104,10 +106,10 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, b
 }
 
 // spec: plan for the spectral form (run tokens, power table in shared memory) over avail_ids run-dictionary ids
-static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0, bool spec = false, bool mma = false) {
+static int zip_plan(int K, int S, int avail_ids, ZipPlan* out, int lanes_override = 0, bool spec = false, bool mma = false, bool run2 = false) {
     const int want = (int)g_ctx.opt_zip_ctas_per_sm, lanes = lanes_override ? lanes_override : (int)g_ctx.opt_zip_lanes;
     switch (zip_tile(K)) {
-#define X(k) case k: *out = spec ? zip_plan_k<k, true>(S, avail_ids, want, lanes, mma) : zip_plan_k<k, false>(S, avail_ids, want, lanes, false); break;
+#define X(k) case k: *out = spec ? zip_plan_k<k, true>(S, avail_ids, want, lanes, mma, run2 && mma) : zip_plan_k<k, false>(S, avail_ids, want, lanes, false, false); break;
         ZIP_K_LIST(X)
 #undef X
         default: return fail(IMC_ERR_UNSUPPORTED, "zip kernel is not instantiated for K = %d", K);
@@ -122,23 +124,71 @@ static int set_chunk_of_stream(const imc_seqset* set, int k) {
     return 0;
 }
 
+// Two-run form, prepared on first use: pick the second run symbol (the one with the most sites in runs of >= RUN2_MIN among
+// the symbols other than the run symbol), learn its pair dictionary over nsym + 2 base ids on a sample, encode every chunk.
+static int seqset_run2_prepare(imc_seqset* set) {
+    if (set->run2_state != 0) return IMC_OK;
+    set->run2_state = -1;
+    const int ns = (int)set->streams.size(), nsym = set->nsym;
+    if (nsym < 2 || nsym + 2 > 200 || ns == 0 || set->parts_total > 0) return IMC_OK;
+    try {
+        std::vector<std::vector<uint8_t>> syms(ns);
+        if (!parallel_for(ns, [&](int k) { zip_expand(set->merges, set->tok_full[k], nsym, syms[k]); })) throw std::bad_alloc();
+        std::vector<long long> inruns(nsym, 0);
+        for (int k = 0; k < ns; ++k) {
+            const auto& sy = syms[k];
+            for (size_t t = 0; t < sy.size();) {
+                size_t e = t;
+                while (e < sy.size() && sy[e] == sy[t]) ++e;
+                if (sy[t] != set->fold_sym && e - t >= (size_t)RUN2_MIN) inruns[sy[t]] += (long long)(e - t);
+                t = e;
+            }
+        }
+        const int r2 = (int)(std::max_element(inruns.begin(), inruns.end()) - inruns.begin());
+        if (inruns[r2] == 0) return IMC_OK;
+        set->run_sym2 = r2;
+        set->run2_tok_full.resize(ns);
+        set->run2_first_run.assign(ns, 0);
+        set->run2_sites.assign(ns, 0);
+        {
+            std::vector<std::vector<uint32_t>> sample;
+            long long budget = 16LL << 20;
+            const int stride = std::max(1, ns / 32);
+            for (int k = 0; k < ns && budget > 0; k += stride) {
+                int fr; long long r2s;
+                sample.emplace_back();
+                run2_tokenize(syms[k].data(), syms[k].size(), nsym, set->fold_sym, r2, &fr, sample.back(), &r2s);
+                budget -= (long long)syms[k].size();
+            }
+            set->run2_merges = run_learn(sample, nsym + 2, 256, 16);
+        }
+        if (!parallel_for(ns, [&](int k) {
+                run2_encode(set->run2_merges, syms[k].data(), syms[k].size(), nsym, set->fold_sym, r2, &set->run2_first_run[k],
+                            set->run2_tok_full[k], &set->run2_sites[k]);
+            })) throw std::bad_alloc();
+    } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while preparing the two-run encoding"); }
+    set->run2_state = 1;
+    return IMC_OK;
+}
+
 // token streams over the first M dictionary ids, level-ordered, on the device (cached per M and form)
-static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out);
-static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false) {
-    try { return zip_device_build(set, M, spec, out); }
+static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDevice** out);
+static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false, bool run2 = false) {
+    try { return zip_device_build(set, M, spec, run2, out); }
     catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams"); }
 }
-static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) {
-    for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec) { *out = z; return IMC_OK; }
+static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDevice** out) {
+    for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec && z->run2 == run2) { *out = z; return IMC_OK; }
     const int ns = (int)set->streams.size();
-    const ZipMerges& mg = spec ? set->run_merges : set->merges;
+    const ZipMerges& mg = run2 ? set->run2_merges : (spec ? set->run_merges : set->merges);
+    const std::vector<std::vector<uint32_t>>& rfull = run2 ? set->run2_tok_full : set->run_tok_full;
     ZipLevels zl = zip_levels(mg, M);
     const size_t tsz = spec ? 4 : 1, align = spec ? 32 : 16;      // bytes per token; streams padded to whole blocks + one block of slack
     std::vector<std::vector<uint8_t>> tok(spec ? 0 : ns);
     std::vector<std::vector<uint32_t>> rtok(spec ? ns : 0);
     if (!parallel_for(ns, [&](int k) {
             if (spec) {
-                run_expand(mg, set->run_tok_full[k], M, rtok[k]);
+                run_expand(mg, rfull[k], M, rtok[k]);
                 for (auto& t : rtok[k]) t = (t & ~0xffu) | zl.perm[t & 0xffu];
             } else {
                 zip_expand(mg, set->tok_full[k], M, tok[k]);
@@ -158,10 +208,12 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
         chunks[i].ntok = (int)ntok(k);
         chunks[i].first_sym = set->first_sym[k];
         chunks[i].out_index = k;
-        chunks[i].first_run = spec ? set->first_run[k] : 0;
+        chunks[i].first_run = spec ? (run2 ? set->run2_first_run[k] : set->first_run[k]) : 0;
         long long rs = chunks[i].first_run;
-        if (spec) for (uint32_t t : rtok[k]) rs += t >> 8;
+        if (spec) for (uint32_t t : rtok[k]) if (!(t & RUN_TABLE2_BIT)) rs += (t >> 8) & RUN_MAX;
         chunks[i].run_sites = (int)rs;
+        chunks[i].run2_sites = run2 ? (int)set->run2_sites[k] : 0;
+        chunks[i].pad = 0;
         chunks[i].continues = set->parts_total > 0 ? set->part_first + set_chunk_of_stream(set, k) : 0;     // global part index (0: has its own start)
         off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
@@ -181,7 +233,11 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, ZipDevice** out) 
         for (int k = 0; k < ns; ++k) for (uint32_t t : rtok[k]) hist[t & 0xffu]++;
         z->hot_id = (int)(std::max_element(hist.begin(), hist.end()) - hist.begin());
         z->hot_share = total > 0 ? (double)hist[z->hot_id] / (double)total : 0.0;
+        z->est_passes = 1.0;
+        for (int id = 0; id < 256; ++id)
+            if (id != z->hot_id && hist[id] > 0) z->est_passes += 1.0 - std::pow(1.0 - (double)hist[id] / (double)total, 8.0);
     }
+    z->run2 = run2;
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
     z->max_ntok = ns ? chunks[0].ntok : 0;
@@ -252,7 +308,7 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, int parts_local, int
         }
         // segment s >= 1, column c sits at first_chain + 1 + (s-1)*K + c
         if (nseg <= 32) {
-            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0, ch.run_sites, 0});
+            items2.push_back({first_chain, first_chain + 1, nseg - 1, ch.out_index, 0, 0, ch.run_sites, ch.run2_sites});
         } else {        // two levels: groups of gs segments folded in parallel, then the groups
             const int gs = (int)std::ceil(std::sqrt((double)nseg)), ngroups = (nseg + gs - 1) / gs;
             const int base2 = nvec2;
@@ -265,7 +321,7 @@ static int zip_split_build(ZipDevice* z, int K, int seglen, int parts_local, int
                         items1.push_back({first_chain + 1 + (s0 - 1) * K + col, first_chain + 1 + s0 * K, s1 - s0 - 1, nvec2++, 0, 1, 0, 0});
                 }
             }
-            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0, ch.run_sites, 0});
+            items2.push_back({base2, base2 + 1, ngroups - 1, ch.out_index, 1, 0, ch.run_sites, ch.run2_sites});
         }
     }
     // the kernel takes chunks in list order, longest first: full segments first, tails last (out_index keeps identity)

@@ -38,6 +38,8 @@ constexpr int RUN_LO_BITS = 6, RUN_HI_BITS = 6;
 constexpr int RUN_LO_ROWS = 1 << RUN_LO_BITS, RUN_LO_MASK = RUN_LO_ROWS - 1;
 constexpr int RUN_ROWS = RUN_LO_ROWS + (1 << RUN_HI_BITS);
 constexpr int RUN_MAX = (1 << (RUN_LO_BITS + RUN_HI_BITS)) - 1;
+constexpr int RUN_HI_MASK = (1 << RUN_HI_BITS) - 1;
+constexpr uint32_t RUN_TABLE2_BIT = 1u << 20;      // word bit: the run of this token is of the SECOND run symbol (two-run form)
 
 struct ZipChunk {
     long long tok_off;   // byte offset of the chunk's first token (16-byte aligned, 16 readable bytes past the end)
@@ -47,7 +49,9 @@ struct ZipChunk {
     int out_index;       // column of chain_out this chunk writes
     int first_run;       // spectral form: sites of the run symbol between position 0 and the first token (<= RUN_MAX)
     int run_sites;       // spectral form: first_run + the runs of all tokens; the result gets run_sites * ln(lambda_max)
-    int continues;       // 1: this is a later part of a chunk cut across ranks -- no start of its own (position 0 is an ordinary
+    int run2_sites;      // two-run form: sites in the spectrally treated runs of the second run symbol (x ln(lambda2_max))
+    int pad;
+    int continues;       // > 0: this is a later part of a chunk cut across ranks -- no start of its own (position 0 is an ordinary
                          // site, all of its segments run from unit vectors); see zip_fold_parts_kernel
 };
 
@@ -86,6 +90,8 @@ struct ZipArgs {
     const double* spec;
     int spec_stride;
     int hot_id;                  // MMA form: the most frequent entry of the streams (its matrix lives in registers)
+    int nbase;                   // spectral form: base entries read from `spec` (S, or S + 2 in the two-run form: + B^-1, B)
+    int run2;                    // two-run form: a second power table (of the second run symbol's eigenvalues) is in use
     unsigned long long* mma_passes;   // MMA form: passes (of KT x NT DMMAs each) executed, for the roofline (one atomic per work unit)
 };
 
@@ -175,7 +181,7 @@ struct ZipCfg8 {
         const int cj = L.q >> 1, pr = L.q & 1;          // this lane serves token cj of the four, remainder row pr
         const uint32_t myw = cj == 0 ? w[0] : (cj == 1 ? w[1] : (cj == 2 ? w[2] : w[3]));
         const int myid = myw & 0xffu;
-        IMC_ASSERT(!SPEC || (myw >> (8 + RUN_LO_BITS)) < (1u << RUN_HI_BITS));
+        IMC_ASSERT(!SPEC || (myw >> 20) == 0u);
         const double2* rp = reinterpret_cast<const double2*>(dict + (size_t)myid * STRIDE_D) + FULL * CP * 8 + L.q;
         double2 rm[CP];
 #pragma unroll
@@ -183,7 +189,7 @@ struct ZipCfg8 {
         scale += dexp[myid];       // every lane pair books the exponent of ITS token; zip_run_unit adds the four pairs up
         double frem = 1.0;
         if (SPEC) {
-            const int ra = (myw >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (myw >> (8 + RUN_LO_BITS));
+            const int ra = (myw >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + ((myw >> (8 + RUN_LO_BITS)) & RUN_HI_MASK);
             frem = ptab[ra * PT + 8 * FULL + pr] * ptab[rb * PT + 8 * FULL + pr];
         }
 #pragma unroll
@@ -192,7 +198,7 @@ struct ZipCfg8 {
             double* sb = L.sb0 + buf * KP;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
             const double* pa = ptab + ((w[b] >> 8) & RUN_LO_MASK) * PT + L.q;
-            const double* pb = ptab + (RUN_LO_ROWS + (w[b] >> (8 + RUN_LO_BITS))) * PT + L.q;
+            const double* pb = ptab + (RUN_LO_ROWS + ((w[b] >> (8 + RUN_LO_BITS)) & RUN_HI_MASK)) * PT + L.q;
 #pragma unroll
             for (int k = 0; k < FULL; ++k) {
                 double s0 = 0.0, s1 = 0.0;
@@ -229,8 +235,8 @@ struct ZipCfg8 {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const int id = w & 0xffu;
-            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + ((w >> (8 + RUN_LO_BITS)) & RUN_HI_MASK);
+            IMC_ASSERT((w >> 20) == 0u || !SPEC);
             const double* pa = ptab + ra * PT;
             const double* pb = ptab + rb * PT;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
@@ -316,8 +322,8 @@ struct ZipCfg4 {
         double* sb = L.sb0 + (NBUF == 2 ? buf * KP : 0);
         if (!PRED || active) {
             const int id = w & 0xffu;
-            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + ((w >> (8 + RUN_LO_BITS)) & RUN_HI_MASK);
+            IMC_ASSERT((w >> 20) == 0u || !SPEC);
             const double* pa = ptab + ra * PT + L.g;
             const double* pb = ptab + rb * PT + L.g;
             const char* mb = reinterpret_cast<const char*>(dict + (size_t)id * STRIDE_D);
@@ -387,8 +393,8 @@ struct ZipCfg32 {
         double* sb = L.sb0 + buf * KP;
         if (!PRED || active) {
             const int id = w & 0xffu;
-            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + (w >> (8 + RUN_LO_BITS));
-            IMC_ASSERT(rb < RUN_ROWS || !SPEC);
+            const int ra = (w >> 8) & RUN_LO_MASK, rb = RUN_LO_ROWS + ((w >> (8 + RUN_LO_BITS)) & RUN_HI_MASK);
+            IMC_ASSERT((w >> 20) == 0u || !SPEC);
             const double* pa = ptab + ra * PT + L.q;
             const double* pb = ptab + rb * PT + L.q;
             const double2* mp = reinterpret_cast<const double2*>(dict + (size_t)id * STRIDE_D) + L.q;
@@ -460,12 +466,12 @@ struct ZipSmem {
     // doubles in front of the exchange buffers: plain form E[K][S], spectral form the start vectors b0[S][KP]
     __host__ __device__ static constexpr int se_doubles(int S) { return ((SPEC ? C::KP : C::K) * S + 1) & ~1; }   // keeps what follows 16-byte aligned
     __host__ __device__ static constexpr int tab_doubles() { return SPEC ? RUN_ROWS * C::PT : 0; }
-    static size_t bytes(int M, int S, int threads) {
-        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP + tab_doubles();
+    static size_t bytes(int M, int S, int threads, bool run2 = false) {
+        size_t d = (size_t)M * C::STRIDE_D + (size_t)se_doubles(S) + C::KP + (size_t)(threads / 32) * C::SBUF_PER_WARP + tab_doubles() * (run2 ? 2 : 1);
         return d * sizeof(double) + (size_t)M * sizeof(long long) + 4 * sizeof(int);   // dexp[M], s_point[2] + s_best
     }
-    static int max_entries(size_t budget, int S, int threads) {
-        const size_t fixed = bytes(0, S, threads);
+    static int max_entries(size_t budget, int S, int threads, bool run2 = false) {
+        const size_t fixed = bytes(0, S, threads, run2);
         if (budget <= fixed) return 0;
         const size_t m = (budget - fixed) / (C::STRIDE_D * sizeof(double) + sizeof(long long));
         return (int)(m > 256 ? 256 : m);
@@ -529,13 +535,26 @@ __device__ __forceinline__ void zip_build_dictionary(const ZipArgs& a, int n, do
             const double p = row < RUN_LO_ROWS ? (double)row : (double)((row - RUN_LO_ROWS) << RUN_LO_BITS);
             ptab[row * C::PT + C::slot(k)] = p == 0.0 ? 1.0 : pow(sp[k] / lmax, p);
         }
+        if (a.run2) {          // the same table for the eigenvalues of the second run symbol, right behind the first
+            const double* l2 = sp + 2 * K + S * K + (size_t)a.nbase * K * K;
+            double* ptab2 = ptab + RUN_ROWS * C::PT;
+            double l2max = 0.0;
+            for (int k = 0; k < K; ++k) l2max = fmax(l2max, fabs(l2[k]));
+            for (int x = tid; x < RUN_ROWS * C::PT; x += THREADS) ptab2[x] = 0.0;
+            __syncthreads();
+            for (int x = tid; x < RUN_ROWS * K; x += THREADS) {
+                const int row = x / K, k = x - row * K;
+                const double p = row < RUN_LO_ROWS ? (double)row : (double)((row - RUN_LO_ROWS) << RUN_LO_BITS);
+                ptab2[row * C::PT + C::slot(k)] = p == 0.0 ? 1.0 : pow(l2[k] / l2max, p);
+            }
+        }
     } else {
         for (int x = tid; x < K * S; x += THREADS) sE[x] = Eg[x];
         for (int x = tid; x < KP; x += THREADS) spi[x] = x < K ? pig[x] : 0.0;
     }
     __syncthreads();
     for (int lv = -1; lv < a.nlevels; ++lv) {
-        const int lo = lv < 0 ? 0 : a.level_start[lv], hi = lv < 0 ? S : a.level_start[lv + 1];
+        const int lo = lv < 0 ? 0 : a.level_start[lv], hi = lv < 0 ? (SPEC ? a.nbase : S) : a.level_start[lv + 1];
         for (int e = lo + warp; e < hi; e += NW) {
             double* D = dict + (size_t)e * C::STRIDE_D;
             double mx = 0.0;
@@ -849,8 +868,9 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         constexpr bool ALL = decltype(all_tag)::value;
         if (!ALL && !active) wb = 0u;
         const int id = wb & 0xffu;
-        IMC_ASSERT(id < a.M && (wb >> (8 + RUN_LO_BITS)) < (1u << RUN_HI_BITS));
-        const uint32_t pa = ptab_s + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = ptab_s + (RUN_LO_ROWS + (wb >> (8 + RUN_LO_BITS))) * (PT * 8);
+        IMC_ASSERT(id < a.M && (wb >> 21) == 0u && (a.run2 || !(wb & RUN_TABLE2_BIT)));
+        const uint32_t tab = ptab_s + ((wb >> 20) & 1u) * (RUN_ROWS * PT * 8);      // the first or the second run symbol's table
+        const uint32_t pa = tab + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = tab + (RUN_LO_ROWS + ((wb >> (8 + RUN_LO_BITS)) & RUN_HI_MASK)) * (PT * 8);
         double2 fa[NT], fb[NT];            // (lambda / lambda_max)^n of this token for the lane's states: independent of the products below
 #pragma unroll
         for (int t = 0; t < NT; ++t) { fa[t] = lds_f64x2(pa + t * 64); fb[t] = lds_f64x2(pb + t * 64); }
@@ -971,7 +991,8 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
     }
     double result;
     if (dead || !(sum > 0.0)) result = bad ? __longlong_as_double(0x7ff8000000000000LL) : -INFINITY;
-    else result = log(sum) + (double)scale * LN2 + (double)ch.run_sites * __ldg(a.spec + (size_t)n * a.spec_stride + a.spec_stride - 1);
+    else result = log(sum) + (double)scale * LN2 + (double)ch.run_sites * __ldg(a.spec + (size_t)n * a.spec_stride + a.spec_stride - 1)
+                  + (double)ch.run2_sites * __ldg(a.spec + (size_t)n * a.spec_stride + a.spec_stride - 2);
     if (have && L.writer()) a.chain_out[(size_t)n * a.out_stride + ch.out_index] = result;
 }
 
@@ -990,7 +1011,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
     double* spi = sE + ZipSmem<C, SPEC>::se_doubles(S);     // [KP] pi / wsum
     double* sbuf = spi + KP;                          // [THREADS/32][SBUF_PER_WARP]
     double* ptab = sbuf + (THREADS / 32) * C::SBUF_PER_WARP;            // spectral: [RUN_ROWS][KP]
-    long long* dexp = reinterpret_cast<long long*>(ptab + ZipSmem<C, SPEC>::tab_doubles());   // [M] (64-bit: an entry can span millions of sites)
+    long long* dexp = reinterpret_cast<long long*>(ptab + ZipSmem<C, SPEC>::tab_doubles() * (SPEC && a.run2 ? 2 : 1));   // [M] (64-bit: an entry can span millions of sites)
     int* s_point = reinterpret_cast<int*>(dexp + M);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1066,6 +1087,7 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct ZipSpecArgs {
     int N, K, S, run_sym;
+    int run_sym2;           // two-run form: the second run symbol, or -1
     const double* pi; const double* T; const double* E;
     double* spec; int spec_stride;
     int* ok_list; int* bad_list;
@@ -1076,36 +1098,28 @@ struct ZipSpecArgs {
 };
 
 constexpr int SPEC_THREADS = 128;
-static inline size_t zip_spec_smem(int K) { return sizeof(double) * ((size_t)2 * K * (K + 1) + 6 * (size_t)K + 8) + sizeof(int) * 4; }
+static inline int zip_spec_stride(int K, int S, bool run2) { return 2 * K + S * K + (S + (run2 ? 2 : 0)) * K * K + K + 2; }
+static inline size_t zip_spec_smem(int K, bool run2) {
+    return sizeof(double) * ((size_t)(run2 ? 4 : 2) * K * (K + 1) + 7 * (size_t)K + 16) + sizeof(int) * 4;
+}
 
-__global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs s) {
-    extern __shared__ __align__(16) unsigned char spsm_raw[];
-    const int K = s.K, S = s.S, LD = K + 1, tid = threadIdx.x, n = blockIdx.x;
-    double* A = reinterpret_cast<double*>(spsm_raw);     // [K][LD]
-    double* Q = A + (size_t)K * LD;                      // [K][LD]
-    double* w = Q + (size_t)K * LD;                      // [K]
-    double* rot = w + K;                                 // [K/2+1][2] cosine, sine of the round's rotations
-    double* dsc = rot + 2 * (K / 2 + 1);                 // [K] E[:,s] / E[:,r]
-    double* red = dsc + K;                               // [4] reductions
-    int* flag = reinterpret_cast<int*>(red + 4 + 2 * K); // [2]
-    const double* Tg = s.T + (size_t)n * K * K;
-    const double* Eg = s.E + (size_t)n * K * S;
-    const double* pig = s.pi + (size_t)n * K;
-    double* out = s.spec + (size_t)n * s.spec_stride;
-    const int r = s.run_sym;
-    if (tid == 0) { flag[0] = s.force_bad ? 0 : 1; flag[1] = 0; red[0] = 0.0; red[1] = 0.0; }
+// Symmetric form A = sqrt(E_i E_j) J_ij / sqrt(pi_i pi_j) of C_sym = diag(E[:,sym]) T^T in shared memory, its checks, and its
+// diagonalisation A = Q diag(A) Q^T by cyclic Jacobi.  All threads of the CTA; flag[0] is cleared where the point does not qualify.
+__device__ void zip_spec_diagonalise(const ZipSpecArgs& s, const double* pig, const double* Tg, const double* Eg, int sym,
+                                     double* A, double* Q, double* w, double* rot, double* red, int* flag) {
+    const int K = s.K, S = s.S, LD = K + 1, tid = threadIdx.x;
+    if (tid == 0) { flag[1] = 0; red[0] = 0.0; red[1] = 0.0; }
     __syncthreads();
     for (int i = tid; i < K; i += SPEC_THREADS) {
-        const double v = pig[i] * Eg[i * S + r];
+        const double v = pig[i] * Eg[i * S + sym];
         if (!(v > 0.0) || !(v < 1.7e308) || !(pig[i] > 0.0)) flag[0] = 0;
         w[i] = sqrt(v);
     }
     __syncthreads();
-    // A and its asymmetry
     double amax = 0.0, asym = 0.0;
     for (int x = tid; x < K * K; x += SPEC_THREADS) {
         const int i = x / K, j = x - i * K;
-        const double gi = Eg[i * S + r] / w[i], gj = Eg[j * S + r] / w[j];          // sqrt(E_i / pi_i)
+        const double gi = Eg[i * S + sym] / w[i], gj = Eg[j * S + sym] / w[j];          // sqrt(E_i / pi_i)
         const double aij = gi * gj * (pig[i] * Tg[i * K + j]), aji = gi * gj * (pig[j] * Tg[j * K + i]);
         A[i * LD + j] = 0.5 * (aij + aji);
         Q[i * LD + j] = i == j ? 1.0 : 0.0;
@@ -1121,98 +1135,141 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
     __syncthreads();
     if (tid == 0 && !(red[1] <= 1e-13 * red[0])) flag[0] = 0;
     __syncthreads();
-    if (flag[0]) {
-        // ---- cyclic Jacobi with the round-robin ordering: m - 1 rounds of m / 2 disjoint rotations per sweep.  Warp w takes
-        // the pairs w, w + nwarps, ...; lane j the column (row) j, j + 32: no integer division in the loops.
-        const int m = (K + 1) & ~1, half = m / 2, nwarps = SPEC_THREADS / 32, warp = tid >> 5, lane = tid & 31;
-        const double tiny = 1e-300;
-        auto pair_of = [&](int round, int pr, int& p, int& q) {     // (m-1, round) for pr == 0, else ((round + pr), (round - pr)) mod (m-1)
-            int a1 = round + pr, a2 = round - pr;
-            if (a1 >= m - 1) a1 -= m - 1;
-            if (a2 < 0) a2 += m - 1;
-            p = pr == 0 ? m - 1 : a1;
-            q = pr == 0 ? round : a2;
-            if (p > q) { const int t = p; p = q; q = t; }
-        };
-        for (int sweep = 0; sweep < 30; ++sweep) {
-            double off = 0.0;
-            for (int i = warp; i < K; i += nwarps)
-                for (int j = lane; j < K; j += 32) if (i != j) off = fmax(off, fabs(A[i * LD + j]));
-            for (int mm = 16; mm >= 1; mm >>= 1) off = fmax(off, shfl_xor_f64(off, mm));
-            if (tid == 0) red[2] = 0.0;
-            __syncthreads();
-            if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(red + 2), (unsigned long long)__double_as_longlong(off));
-            __syncthreads();
-            // off-diagonal residual r: A = Q Lambda Q^T holds to r, which moves logL by about r x sites (1e-16 x 1e6 sites = 1e-10
-            // absolute, 5e-15 of a typical |logL|); rounding noise keeps r near 1e-17 however many sweeps follow
-            if (red[2] <= 1e-16 * red[0]) { if (tid == 0) flag[1] = 1; break; }
-            for (int round = 0; round < m - 1; ++round) {
-                if (tid < half) {
-                    int p, q;
-                    pair_of(round, tid, p, q);
-                    double c = 1.0, sn = 0.0;
-                    if (q < K) {
-                        const double apq = A[p * LD + q], app = A[p * LD + p], aqq = A[q * LD + q];
-                        if (fabs(apq) > tiny) {
-                            const double th = (aqq - app) / (2.0 * apq);
-                            const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-                            c = rsqrt(t * t + 1.0);
-                            sn = t * c;
-                        }
-                    }
-                    rot[2 * tid] = c; rot[2 * tid + 1] = sn;
-                }
-                __syncthreads();
-                for (int pr = warp; pr < half; pr += nwarps) {                 // rows: A <- J^T A
-                    int p, q;
-                    pair_of(round, pr, p, q);
-                    if (q >= K) continue;
-                    const double c = rot[2 * pr], sn = rot[2 * pr + 1];
-                    if (sn == 0.0) continue;
-                    for (int j = lane; j < K; j += 32) {
-                        const double ap = A[p * LD + j], aq = A[q * LD + j];
-                        A[p * LD + j] = c * ap - sn * aq;
-                        A[q * LD + j] = sn * ap + c * aq;
+    if (!flag[0]) return;
+    // ---- cyclic Jacobi with the round-robin ordering: m - 1 rounds of m / 2 disjoint rotations per sweep.  Warp w takes
+    // the pairs w, w + nwarps, ...; lane j the column (row) j, j + 32: no integer division in the loops.
+    const int m = (K + 1) & ~1, half = m / 2, nwarps = SPEC_THREADS / 32, warp = tid >> 5, lane = tid & 31;
+    const double tiny = 1e-300;
+    auto pair_of = [&](int round, int pr, int& p, int& q) {     // (m-1, round) for pr == 0, else ((round + pr), (round - pr)) mod (m-1)
+        int a1 = round + pr, a2 = round - pr;
+        if (a1 >= m - 1) a1 -= m - 1;
+        if (a2 < 0) a2 += m - 1;
+        p = pr == 0 ? m - 1 : a1;
+        q = pr == 0 ? round : a2;
+        if (p > q) { const int t = p; p = q; q = t; }
+    };
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int i = warp; i < K; i += nwarps)
+            for (int j = lane; j < K; j += 32) if (i != j) off = fmax(off, fabs(A[i * LD + j]));
+        for (int mm = 16; mm >= 1; mm >>= 1) off = fmax(off, shfl_xor_f64(off, mm));
+        if (tid == 0) red[2] = 0.0;
+        __syncthreads();
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(red + 2), (unsigned long long)__double_as_longlong(off));
+        __syncthreads();
+        // off-diagonal residual r: A = Q Lambda Q^T holds to r, which moves logL by about r x sites (1e-16 x 1e6 sites = 1e-10
+        // absolute, 5e-15 of a typical |logL|); rounding noise keeps r near 1e-17 however many sweeps follow
+        if (red[2] <= 1e-16 * red[0]) { if (tid == 0) flag[1] = 1; break; }
+        for (int round = 0; round < m - 1; ++round) {
+            if (tid < half) {
+                int p, q;
+                pair_of(round, tid, p, q);
+                double c = 1.0, sn = 0.0;
+                if (q < K) {
+                    const double apq = A[p * LD + q], app = A[p * LD + p], aqq = A[q * LD + q];
+                    if (fabs(apq) > tiny) {
+                        const double th = (aqq - app) / (2.0 * apq);
+                        const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                        c = rsqrt(t * t + 1.0);
+                        sn = t * c;
                     }
                 }
-                __syncthreads();
-                for (int pr = warp; pr < half; pr += nwarps) {                 // columns: A <- A J, Q <- Q J
-                    int p, q;
-                    pair_of(round, pr, p, q);
-                    if (q >= K) continue;
-                    const double c = rot[2 * pr], sn = rot[2 * pr + 1];
-                    if (sn == 0.0) continue;
-                    for (int i = lane; i < K; i += 32) {
-                        const double ap = A[i * LD + p], aq = A[i * LD + q];
-                        double np = c * ap - sn * aq, nq = sn * ap + c * aq;
-                        if (i == p) nq = 0.0;                                  // the annihilated pair, exactly
-                        if (i == q) np = 0.0;
-                        A[i * LD + p] = np;
-                        A[i * LD + q] = nq;
-                        const double vp = Q[i * LD + p], vq = Q[i * LD + q];
-                        Q[i * LD + p] = c * vp - sn * vq;
-                        Q[i * LD + q] = sn * vp + c * vq;
-                    }
-                }
-                __syncthreads();
+                rot[2 * tid] = c; rot[2 * tid + 1] = sn;
             }
+            __syncthreads();
+            for (int pr = warp; pr < half; pr += nwarps) {                 // rows: A <- J^T A
+                int p, q;
+                pair_of(round, pr, p, q);
+                if (q >= K) continue;
+                const double c = rot[2 * pr], sn = rot[2 * pr + 1];
+                if (sn == 0.0) continue;
+                for (int j = lane; j < K; j += 32) {
+                    const double ap = A[p * LD + j], aq = A[q * LD + j];
+                    A[p * LD + j] = c * ap - sn * aq;
+                    A[q * LD + j] = sn * ap + c * aq;
+                }
+            }
+            __syncthreads();
+            for (int pr = warp; pr < half; pr += nwarps) {                 // columns: A <- A J, Q <- Q J
+                int p, q;
+                pair_of(round, pr, p, q);
+                if (q >= K) continue;
+                const double c = rot[2 * pr], sn = rot[2 * pr + 1];
+                if (sn == 0.0) continue;
+                for (int i = lane; i < K; i += 32) {
+                    const double ap = A[i * LD + p], aq = A[i * LD + q];
+                    double np = c * ap - sn * aq, nq = sn * ap + c * aq;
+                    if (i == p) nq = 0.0;                                  // the annihilated pair, exactly
+                    if (i == q) np = 0.0;
+                    A[i * LD + p] = np;
+                    A[i * LD + q] = nq;
+                    const double vp = Q[i * LD + p], vq = Q[i * LD + q];
+                    Q[i * LD + p] = c * vp - sn * vq;
+                    Q[i * LD + q] = sn * vp + c * vq;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0) {
-            double lmax = 0.0, lpos = 0.0;
-            for (int k = 0; k < K; ++k) { lmax = fmax(lmax, fabs(A[k * LD + k])); lpos = fmax(lpos, A[k * LD + k]); }
-            if (!flag[1] || !(lmax > 0.0) || !(lpos >= lmax) || !(lmax < 1.7e308)) flag[0] = 0;     // the dominant eigenvalue must be the positive one
-            else out[s.spec_stride - 1] = log(lmax);
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    if (tid == 0) {
+        double lmax = 0.0, lpos = 0.0;
+        for (int k = 0; k < K; ++k) { lmax = fmax(lmax, fabs(A[k * LD + k])); lpos = fmax(lpos, A[k * LD + k]); }
+        if (!flag[1] || !(lmax > 0.0) || !(lpos >= lmax) || !(lmax < 1.7e308)) flag[0] = 0;     // the dominant eigenvalue must be the positive one
+        red[3] = lmax;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spectral preparation, one CTA per parameter point.  With r the run symbol, J = diag(pi) T symmetric (every model
+// of the reference builds T from a symmetric joint matrix, transitions.py:231-246) and w = sqrt(E[:,r] o pi):
+//     C_r = diag(E[:,r]) T^T = W A W^-1,   A[i][j] = sqrt(E[i,r] E[j,r]) J[i][j] / sqrt(pi_i pi_j)   symmetric,
+//     A = Q Lambda Q^T  (cyclic Jacobi, K <= 64),   V = W Q,  V^-1 = Q^T W^-1,
+//     C_s = diag(E[:,s] / E[:,r]) C_r   =>   R_s = V^-1 C_s V = (Q^T diag(E[:,s]/E[:,r]) Q) Lambda,   R_r = Lambda.
+// Written per point (spec_stride doubles): lambda[K], wsum[K] = V^T 1 = Q^T w, b0[S][K] = V^-1 (pi o E[:,s]), R[nbase][K][K],
+// lambda2[K], ln(lambda2_max), ln(lambda_max) (the last two slots).
+// Two-run form (run_sym2 >= 0, nbase = S + 2): the second run symbol r2 (missing data in a pairwise alignment) is
+// diagonalised the same way, C_r2 = V2 Lambda2 V2^-1; in the basis of r a run of m sites of r2 is B Lambda2^m B^-1 with
+// B = V^-1 V2 = Q^T diag(w2 / w) Q2, so the two extra base entries R[S] = B^-1 and R[S+1] = B turn ANY such run into two
+// fixed matrices and a diagonal.
+// A point is served by the spectral kernel only if all of this is sound: pi, E[:,r] > 0, J symmetric to 1e-13, Jacobi
+// converged, lambda_max > 0; such points are appended to ok_list, the others to bad_list (plain form of the kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs s) {
+    extern __shared__ __align__(16) unsigned char spsm_raw[];
+    const int K = s.K, S = s.S, LD = K + 1, tid = threadIdx.x, n = blockIdx.x;
+    const bool run2 = s.run_sym2 >= 0;
+    const int nbase = S + (run2 ? 2 : 0);
+    double* A = reinterpret_cast<double*>(spsm_raw);     // [K][LD]
+    double* Q = A + (size_t)K * LD;                      // [K][LD]
+    double* A2 = Q + (size_t)K * LD;                     // two-run form: the same for the second run symbol
+    double* Q2 = A2 + (run2 ? (size_t)K * LD : 0);
+    double* w = Q2 + (run2 ? (size_t)K * LD : 0);        // [K]
+    double* w2 = w + K;                                  // [K]
+    double* rot = w2 + K;                                // [K/2+1][2] cosine, sine of the round's rotations
+    double* dsc = rot + 2 * (K / 2 + 1);                 // [K] E[:,s] / E[:,r]
+    double* red = dsc + K;                               // [4] reductions
+    int* flag = reinterpret_cast<int*>(red + 4 + 2 * K); // [2]
+    const double* Tg = s.T + (size_t)n * K * K;
+    const double* Eg = s.E + (size_t)n * K * S;
+    const double* pig = s.pi + (size_t)n * K;
+    double* out = s.spec + (size_t)n * s.spec_stride;
+    const int r = s.run_sym;
+    if (tid == 0) flag[0] = s.force_bad ? 0 : 1;
+    __syncthreads();
+    if (flag[0]) zip_spec_diagonalise(s, pig, Tg, Eg, r, A, Q, w, rot, red, flag);
+    __syncthreads();
+    double* lam2_out = out + 2 * K + (size_t)S * K + (size_t)nbase * K * K;
     if (flag[0]) {
         double* lam = out;
         double* wsum = out + K;
         double* b0 = out + 2 * K;
         double* R = out + 2 * K + (size_t)S * K;
+        if (tid == 0) { out[s.spec_stride - 1] = log(red[3]); out[s.spec_stride - 2] = 0.0; }
         for (int k = tid; k < K; k += SPEC_THREADS) {
             lam[k] = A[k * LD + k];
+            lam2_out[k] = 1.0;
             double acc = 0.0;
             for (int i = 0; i < K; ++i) acc = fma(Q[i * LD + k], w[i], acc);
             wsum[k] = acc;
@@ -1241,6 +1298,28 @@ __global__ void __launch_bounds__(SPEC_THREADS) zip_spectral_kernel(ZipSpecArgs 
             }
         }
     }
+    __syncthreads();
+    if (flag[0] && run2) {
+        zip_spec_diagonalise(s, pig, Tg, Eg, s.run_sym2, A2, Q2, w2, rot, red, flag);
+        __syncthreads();
+        if (flag[0]) {
+            double* Binv = out + 2 * K + (size_t)S * K + (size_t)S * K * K;
+            double* B = Binv + (size_t)K * K;
+            if (tid == 0) out[s.spec_stride - 2] = log(red[3]);
+            for (int k = tid; k < K; k += SPEC_THREADS) lam2_out[k] = A2[k * LD + k];
+            for (int x = tid; x < K * K; x += SPEC_THREADS) {
+                const int i = x / K, j = x - i * K;
+                double b = 0.0, bi = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    b = fma(Q[k * LD + i] * (w2[k] / w[k]), Q2[k * LD + j], b);        // B = Q^T diag(w2 / w) Q2
+                    bi = fma(Q2[k * LD + i] * (w[k] / w2[k]), Q[k * LD + j], bi);      // B^-1 = Q2^T diag(w / w2) Q
+                }
+                B[x] = b;
+                Binv[x] = bi;
+            }
+        }
+    }
+    __syncthreads();
     if (tid == 0) {
         if (flag[0]) s.ok_list[atomicAdd(s.counts, 1)] = s.point_base + n;
         else s.bad_list[atomicAdd(s.counts + 1, 1)] = s.point_base + n;
@@ -1257,7 +1336,7 @@ struct ZipFoldItem {
     int start, first_cols, nfold, out_index;
     int src, dst;        // src: 0 = vec (kernel output), 1 = vec2 (level-1 output)
     int run_sites;       // dst == 0, spectral form: run sites of the whole chunk (see ZipChunk)
-    int pad;
+    int run2_sites;
 };
 
 // Spectral form (spec != NULL): the vectors are coordinates in the eigenbasis of C_r -- entries of either sign, measured
@@ -1325,7 +1404,8 @@ __global__ void __launch_bounds__(64) zip_fold_kernel(const double* vec, int nve
         double r;
         if (sum != sum) r = sum;
         else if (!(sum > 0.0)) r = -INFINITY;
-        else r = log(sum) + scale * LN2 + (spec ? (double)it.run_sites * spec[(size_t)n * spec_stride + spec_stride - 1] : 0.0);
+        else r = log(sum) + scale * LN2 + (spec ? (double)it.run_sites * spec[(size_t)n * spec_stride + spec_stride - 1]
+                                                   + (double)it.run2_sites * spec[(size_t)n * spec_stride + spec_stride - 2] : 0.0);
         chain_out[(size_t)n * out_stride + it.out_index] = r;
     }
 }

@@ -229,6 +229,12 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       mma.sync.m8n8k4.f64 tiles and the most frequent entry's matrix is held as B fragments in registers,
  *                       so a step moves no matrix through shared memory; chains on other entries take one extra pass per
  *                       distinct entry.  0 = auto (where one entry is >= 50 % of the run tokens), 1 = always, 2 = never.
+ * key "zip_run2":       two-run form of the MMA shape: the second run symbol (missing data in a pairwise alignment) is
+ *                       diagonalised too, so that a block of m such sites costs two fixed matrices (B^-1, B) and a diagonal
+ *                       instead of a product of power-of-two dictionary entries.  0 = auto (where it lowers the expected
+ *                       number of DMMA passes: state counts whose dictionary hardly fits, K >= 32), 1 = always, 2 = never.
+ * key "zip_mma_shape":  launch shape of the MMA form: 0 = auto, 1 = one CTA of 512 threads per SM (256 for K >= 32),
+ *                       2 = two CTAs of 256, 3 = four CTAs of 256 threads with 64 registers (K <= 12), 4 = four CTAs of 128.
  * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).
  * key "comm_fused", "comm_enabled": see the multi-GPU section above.
  * key "comm_timeout_ms": how long the fused all-reduce waits for a peer's partial sums (default 30000).  On a timeout the call's
@@ -250,7 +256,8 @@ int imc_mma_passes(int64_t* passes_out);
 /* name of the forward kernel chosen by the last forward call on this thread
  * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls;
  * "zip-spectral", "zip-spectral-segmented", "zip-spectral-warp": the same three shapes over run tokens;
- * "zip-spectral-mma", "zip-spectral-mma-segmented": the MMA shape of the spectral form) */
+ * "zip-spectral-mma", "zip-spectral-mma-segmented": the MMA shape of the spectral form; "zip-spectral-mma2...": its
+ * two-run form) */
 const char* imc_last_forward_kernel(void);
 
 #ifdef __cplusplus

@@ -7,7 +7,7 @@ from conftest import golden_model, example_symbols, random_hmm
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-11
-OPTS = ("forward_kernel", "zip_ctas_per_sm", "zip_max_entries", "zip_lanes", "zip_segment_tokens", "zip_pipeline", "zip_mma",
+OPTS = ("forward_kernel", "zip_ctas_per_sm", "zip_max_entries", "zip_lanes", "zip_segment_tokens", "zip_pipeline", "zip_mma", "zip_run2",
         "zip_spectral", "zip_spectral_force_bad")
 
 
@@ -84,13 +84,20 @@ def test_reference_models_all_shapes(model):
     if K >= 7:                                                        # ... and the MMA form (tiles >= 8): whole chunks, pieces, segments
         shapes += [dict(zip_mma=1, zip_segment_tokens=-1, zip_pipeline=1), dict(zip_mma=1, zip_segment_tokens=-1, zip_pipeline=5),
                    dict(zip_mma=1, zip_segment_tokens=256), dict(zip_mma=1, zip_segment_tokens=-1, zip_max_entries=4), dict(zip_mma=0)]
+        shapes = [dict(o, zip_run2=2) for o in shapes]
+        # the two-run form (missing-data blocks through B^-1, Lambda2^m, B): whole chunks, pieces, segments, a tiny dictionary
+        shapes += [dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_pipeline=1), dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_pipeline=5),
+                   dict(zip_mma=1, zip_run2=1, zip_segment_tokens=256), dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_max_entries=5),
+                   dict(zip_run2=0)]
     for opts in shapes:
-        for k in OPTS[1:7]:
+        for k in OPTS[1:8]:
             m.set_option(k, opts.get(k, 0))
         got = s.forward_batch(pis, Ts, Es)
         assert m.last_forward_kernel().startswith("zip-spectral"), m.last_forward_kernel()
         if opts.get("zip_mma") == 1:
             assert "mma" in m.last_forward_kernel(), m.last_forward_kernel()
+        if opts.get("zip_run2") == 1:
+            assert "mma2" in m.last_forward_kernel(), m.last_forward_kernel()
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="%s %s" % (model, opts))
         assert s.spectral_counts() == (len(pis), 0)
         one = s.forward(pis[-1], Ts[-1], Es[-1])
@@ -114,11 +121,14 @@ def test_random_reversible_hmms_every_tile(K):
     m.set_option("zip_lanes", 0)
     if K >= 7:
         m.set_option("zip_mma", 1)
-        for seg in (-1, 128):
+        for seg, r2 in ((-1, 2), (128, 2), (-1, 1), (128, 1)):
             m.set_option("zip_segment_tokens", seg)
-            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d mma seg=%d" % (K, seg))
+            m.set_option("zip_run2", r2)
+            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d mma seg=%d run2=%d" % (K, seg, r2))
             assert "mma" in m.last_forward_kernel() and s.spectral_counts() == (6, 0)
+            assert ("mma2" in m.last_forward_kernel()) == (r2 == 1)
         m.set_option("zip_mma", 0)
+        m.set_option("zip_run2", 0)
         m.set_option("zip_segment_tokens", 0)
     np.testing.assert_allclose(s.forward_batch(pis[:1], Ts[:1], Es[:1]), want[:1], rtol=RTOL)     # chain-scarce shapes
 
@@ -138,9 +148,10 @@ def test_mixed_batch_reversible_and_not():
     want = oracle_batch(chunks, pis, Ts, Es)
     s = make_set(chunks)
     m.set_option("zip_spectral", 1)
-    for seg, mma in ((-1, 2), (0, 2), (512, 2), (-1, 1), (512, 1), (0, 0)):
+    for seg, mma, r2 in ((-1, 2, 0), (0, 2, 0), (512, 2, 0), (-1, 1, 2), (512, 1, 2), (-1, 1, 1), (512, 1, 1), (0, 0, 0)):
         m.set_option("zip_segment_tokens", seg)
         m.set_option("zip_mma", mma)
+        m.set_option("zip_run2", r2)
         np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="seg=%d mma=%d" % (seg, mma))
         ok, plain = s.spectral_counts()
         assert (ok, plain) == (7, 5)

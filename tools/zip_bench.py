@@ -75,6 +75,7 @@ def main():
         mma = f[5] if len(f) > 5 else 0
         m.set_option("zip_mma", mma)
         m.set_option("zip_mma_shape", f[6] if len(f) > 6 else 0)
+        m.set_option("zip_run2", f[7] if len(f) > 7 else 0)
         m.set_option("forward_kernel", 4)
         m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)

@@ -21,8 +21,9 @@ chunk of the (per-rank) shard, logL[N_theta] out.  Rank 0 prints ONE JSON line.
              zipHMM-style forward (oracle/forward_oracle.c, float64); the first 16 points use the (pi,T,E) the
              REFERENCE's own build_hidden_markov_model produced (tests/golden), the others the GPU model build.
   secondary  (default run on one GPU only) the same measurement + parity for the shapes the north star names:
-             c3_1gpu (IM model K=20 shard of configs[2]), ns_1gpu (north-star shard), c5_1gpu (K=40 shard), and the
-             drop-in latency of ONE Likelihood(theta) call on the reference's example alignment (c1).
+             c3_1gpu (IM model K=20 shard of configs[2]), ns_1gpu (north-star shard), c4_1gpu (4096 MCMC proposals per
+             step on a 375 Mbp shard), c5_1gpu (K=40 shard), and the drop-in latency of ONE Likelihood(theta) call on
+             the reference's example alignment (c1).
   cpu_baseline  the CPU oracle's zipHMM-style forward (OpenMP over all host cores) on a bounded sample of the same
              workload -- a reported baseline, not the target.
 """
@@ -74,7 +75,7 @@ WORKLOADS = {
                desc="configs[0]: isolation model K=10 on the reference's example alignment (hg18 vs pantro2, 65 255 sites), "
                     "one Likelihood(theta) call at a time"),
 }
-SECONDARY = ("c3_1gpu", "ns_1gpu", "c5_1gpu")
+SECONDARY = ("c3_1gpu", "ns_1gpu", "c4_1gpu", "c5_1gpu")
 
 
 def thetas_around(default, n, seed=7, scale=0.1):
@@ -779,7 +780,7 @@ def main():
         share = args.secondary_budget_s / len(SECONDARY)
         for name in SECONDARY:
             try:
-                r = measure_workload(g, name, WORKLOADS[name], chunk_factory, steps=5, warmup=3, parity_budget_s=share,
+                r = measure_workload(g, name, WORKLOADS[name], chunk_factory, steps=3 if name == "c4_1gpu" else 5, warmup=3, parity_budget_s=share,
                                      e2e=False, parity=not args.no_parity)
                 rf = r["roofline"]
                 sec[name] = {"workload": WORKLOADS[name]["desc"], "ms_per_step": r["ms_per_step"], "value": r["value"],

@@ -46,14 +46,16 @@ for name, n in (("isolation_k10", 3), ("im_k10_10", 2), ("psmc_iso_split_4x10", 
                  dict(zip_spectral=1, zip_mma=2, zip_segment_tokens=-1), dict(zip_spectral=1, zip_mma=2, zip_pipeline=3, zip_segment_tokens=-1),
                  dict(zip_spectral=1, zip_mma=2, zip_segment_tokens=64), dict(zip_spectral=1, zip_mma=1, zip_segment_tokens=-1),
                  dict(zip_spectral=1, zip_mma=1, zip_pipeline=3, zip_segment_tokens=-1), dict(zip_spectral=1, zip_mma=1, zip_segment_tokens=64),
+                 dict(zip_spectral=1, zip_mma=1, zip_run2=1, zip_segment_tokens=-1), dict(zip_spectral=1, zip_mma=1, zip_run2=1, zip_pipeline=3, zip_segment_tokens=-1),
+                 dict(zip_spectral=1, zip_mma=1, zip_run2=1, zip_segment_tokens=64),
                  dict(forward_kernel=1), dict(forward_kernel=3)):
-        for k in ("forward_kernel", "zip_spectral", "zip_mma", "zip_lanes", "zip_pipeline", "zip_segment_tokens"):
-            m.set_option(k, opts.get(k, 0))
+        for k in ("forward_kernel", "zip_spectral", "zip_mma", "zip_run2", "zip_lanes", "zip_pipeline", "zip_segment_tokens"):
+            m.set_option(k, opts.get(k, 2 if k == "zip_run2" else 0))
         out = fset.forward_batch(pis, Ts, Es)
         ref = out if ref is None else ref
         assert np.allclose(out, ref, rtol=1e-10), (name, opts, out, ref)
         done.append("%s/%s" % (name, m.last_forward_kernel()))
-for k in ("forward_kernel", "zip_spectral", "zip_mma", "zip_lanes", "zip_pipeline", "zip_segment_tokens"):
+for k in ("forward_kernel", "zip_spectral", "zip_mma", "zip_run2", "zip_lanes", "zip_pipeline", "zip_segment_tokens"):
     m.set_option(k, 0)
 g = np.load(os.path.join(ROOT, "tests", "golden", "model_im_k10_10.npz"))
 fused = m.IsolationMigrationModel(10, 10).batched_log_likelihood(g["theta"][:3], fset)

@@ -542,6 +542,8 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
                 "executed_dmma_tflops": dmma_tflops, "executed_dmma_frac_of_peak": dmma_tflops / peak_dmma,
                 "dmma_passes_per_launch": passes_per_launch, "dmma_per_pass": KT * NT,
                 "passes_per_warp_step": passes_per_launch / max(1.0, steps_exec / 8.0),
+                "frac_note": "frac counts ALGORITHMIC flops only; the tensor pipe itself is busy executed_dmma_frac_of_peak of the time "
+                             "(ncu sm__inst_executed_pipe_tensor_subpipe_dmma agrees: profiles/r02_zip*_mma_ncu.txt)",
                 "executed_note": "every pass is KT x NT DMMAs of 512 flop for the 8 chains of a warp: tiles are padded to 8 x 4 "
                                  "(K=10: 100 of 192 MACs useful) and a pass for a cold entry serves only the chains on that entry",
                 "smem_view_of_the_fma_shapes": smem_view, "compression": compression, "plain_forward_equivalent": fp64_view}

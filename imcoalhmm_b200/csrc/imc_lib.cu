@@ -874,13 +874,16 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         // dictionary that fits is small (K >= 32), judged by the expected DMMA work = tokens x passes per warp-step.
         bool run2 = false;
         if (g_ctx.opt_zip_run2 != 2 && !parts && zip_mma_tile(zip_tile(K)) && g_ctx.opt_zip_mma != 2 && g_ctx.opt_zip_lanes == 0) {
-            if ((rc = seqset_run2_prepare(set))) return rc;
             ZipPlan p1, p2;
             ZipDevice *z1 = nullptr, *z2 = nullptr;
-            if (set->run2_state == 1 && zip_plan(K, S, set->run_merges.size(), &p1, 0, true, true, false) == IMC_OK &&
-                zip_device(set, p1.M, &z1, true, false) == IMC_OK && zip_plan(K, S, set->run2_merges.size(), &p2, 0, true, true, true) == IMC_OK &&
-                zip_device(set, p2.M, &z2, true, true) == IMC_OK)
-                run2 = g_ctx.opt_zip_run2 == 1 || (double)z2->total_tokens * z2->est_passes < 0.93 * (double)z1->total_tokens * z1->est_passes;
+            // only a stream with many cold passes has something to gain: the second encoding is not even prepared otherwise
+            if (zip_plan(K, S, set->run_merges.size(), &p1, 0, true, true, false) == IMC_OK && zip_device(set, p1.M, &z1, true, false) == IMC_OK &&
+                (g_ctx.opt_zip_run2 == 1 || z1->est_passes >= 2.4)) {
+                if ((rc = seqset_run2_prepare(set))) return rc;
+                if (set->run2_state == 1 && zip_plan(K, S, set->run2_merges.size(), &p2, 0, true, true, true) == IMC_OK &&
+                    zip_device(set, p2.M, &z2, true, true) == IMC_OK)
+                    run2 = g_ctx.opt_zip_run2 == 1 || (double)z2->total_tokens * z2->est_passes < 0.93 * (double)z1->total_tokens * z1->est_passes;
+            }
         }
         g_want_run2 = run2;
         const int sstride = zip_spec_stride(K, S, run2);

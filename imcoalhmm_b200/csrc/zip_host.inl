@@ -132,18 +132,20 @@ static int seqset_run2_prepare(imc_seqset* set) {
     const int ns = (int)set->streams.size(), nsym = set->nsym;
     if (nsym < 2 || nsym + 2 > 200 || ns == 0 || set->parts_total > 0) return IMC_OK;
     try {
-        std::vector<std::vector<uint8_t>> syms(ns);
-        if (!parallel_for(ns, [&](int k) { zip_expand(set->merges, set->tok_full[k], nsym, syms[k]); })) throw std::bad_alloc();
+        // every step expands a stream back to its symbols and lets go of them again: never more than one chunk per core in memory
+        std::vector<std::vector<long long>> inruns_k(ns, std::vector<long long>(nsym, 0));
+        if (!parallel_for(ns, [&](int k) {
+                std::vector<uint8_t> sy;
+                zip_expand(set->merges, set->tok_full[k], nsym, sy);
+                for (size_t t = 0; t < sy.size();) {
+                    size_t e = t;
+                    while (e < sy.size() && sy[e] == sy[t]) ++e;
+                    if (sy[t] != set->fold_sym && e - t >= (size_t)RUN2_MIN) inruns_k[k][sy[t]] += (long long)(e - t);
+                    t = e;
+                }
+            })) throw std::bad_alloc();
         std::vector<long long> inruns(nsym, 0);
-        for (int k = 0; k < ns; ++k) {
-            const auto& sy = syms[k];
-            for (size_t t = 0; t < sy.size();) {
-                size_t e = t;
-                while (e < sy.size() && sy[e] == sy[t]) ++e;
-                if (sy[t] != set->fold_sym && e - t >= (size_t)RUN2_MIN) inruns[sy[t]] += (long long)(e - t);
-                t = e;
-            }
-        }
+        for (int k = 0; k < ns; ++k) for (int v = 0; v < nsym; ++v) inruns[v] += inruns_k[k][v];
         const int r2 = (int)(std::max_element(inruns.begin(), inruns.end()) - inruns.begin());
         if (inruns[r2] == 0) return IMC_OK;
         set->run_sym2 = r2;
@@ -156,14 +158,18 @@ static int seqset_run2_prepare(imc_seqset* set) {
             const int stride = std::max(1, ns / 32);
             for (int k = 0; k < ns && budget > 0; k += stride) {
                 int fr; long long r2s;
+                std::vector<uint8_t> sy;
+                zip_expand(set->merges, set->tok_full[k], nsym, sy);
                 sample.emplace_back();
-                run2_tokenize(syms[k].data(), syms[k].size(), nsym, set->fold_sym, r2, &fr, sample.back(), &r2s);
-                budget -= (long long)syms[k].size();
+                run2_tokenize(sy.data(), sy.size(), nsym, set->fold_sym, r2, &fr, sample.back(), &r2s);
+                budget -= (long long)sy.size();
             }
             set->run2_merges = run_learn(sample, nsym + 2, 256, 16);
         }
         if (!parallel_for(ns, [&](int k) {
-                run2_encode(set->run2_merges, syms[k].data(), syms[k].size(), nsym, set->fold_sym, r2, &set->run2_first_run[k],
+                std::vector<uint8_t> sy;
+                zip_expand(set->merges, set->tok_full[k], nsym, sy);
+                run2_encode(set->run2_merges, sy.data(), sy.size(), nsym, set->fold_sym, r2, &set->run2_first_run[k],
                             set->run2_tok_full[k], &set->run2_sites[k]);
             })) throw std::bad_alloc();
     } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while preparing the two-run encoding"); }

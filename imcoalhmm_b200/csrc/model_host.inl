@@ -366,7 +366,9 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
     for (int s : m->interval_space) nmax = std::max(nmax, host_space(s).n);
     const size_t smem_expm = sizeof(double) * 3 * (size_t)nmax * nmax;
     if (nmax <= 16) {       // isolation-type models: the lean instantiation (no tensor-path code, 8 CTAs per SM)
-        model_expm_kernel<true><<<dim3(K, N), 256, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
+        // 64 threads per 15 x 15 (or 4 x 4) exponential: the CTA is a chain of ~16 tiny products with barriers in between, so the
+        // launch is latency-bound and gains from resident CTAs, not from threads per CTA
+        model_expm_kernel<true><<<dim3(K, N), 64, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
                                                                     (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
     } else {
         static size_t expm_attr = 0;

@@ -180,12 +180,12 @@ class ChunkFactory(object):
             self.pool = None
 
 
-def make_chunks(wl, pis, Ts, Es, chunk_ids):
+def make_chunks(wl, pis, Ts, Es, chunk_ids, **sim_args):
     """Kept for tools/: chunks simulated from the given point-0 model."""
     out = []
     for cid in chunk_ids:
         rng = np.random.Generator(np.random.PCG64(SEED0 + int(cid)))
-        out.append(simulate_chunk(rng, pis[0], Ts[0], Es[0], wl["chunk_len"]))
+        out.append(simulate_chunk(rng, pis[0], Ts[0], Es[0], wl["chunk_len"], **sim_args))
     return out
 
 

@@ -20,8 +20,9 @@ def main():
     ap.add_argument("--chunks", type=int, default=0)
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off[:mma 0 auto|1|2 off]]]")
+    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off[:mma 0 auto|1|2 off[:shape[:run2]]]]]")
     ap.add_argument("--plain", action="store_true", help="also time the uncompressed kernel")
+    ap.add_argument("--missing", type=float, default=0.04, help="missing-data coverage of the simulated chunks (bench.py: 0.04)")
     ap.add_argument("--check", type=int, default=2, help="chunks to check against the oracle")
     args = ap.parse_args()
     wl = dict(bench.WORKLOADS[args.workload])
@@ -35,7 +36,7 @@ def main():
     pis, Ts, Es, st = model.build_hidden_markov_models(thetas)
     assert (st == 0).all()
     t0 = time.time()
-    chunks = bench.make_chunks(wl, pis, Ts, Es, range(wl["chunks"]))
+    chunks = bench.make_chunks(wl, pis, Ts, Es, range(wl["chunks"]), missing=args.missing)
     t_sim = time.time() - t0
     t0 = time.time()
     fset = m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in chunks])

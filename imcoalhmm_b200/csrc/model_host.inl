@@ -366,9 +366,9 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
     for (int s : m->interval_space) nmax = std::max(nmax, host_space(s).n);
     const size_t smem_expm = sizeof(double) * 3 * (size_t)nmax * nmax;
     if (nmax <= 16) {       // isolation-type models: the lean instantiation (no tensor-path code, 8 CTAs per SM)
-        // 64 threads per 15 x 15 (or 4 x 4) exponential: the CTA is a chain of ~16 tiny products with barriers in between, so the
-        // launch is latency-bound and gains from resident CTAs, not from threads per CTA
-        model_expm_kernel<true><<<dim3(K, N), 64, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
+        // the CTA is a chain of ~16 tiny products with barriers in between: a batch that fills the machine gains from resident
+        // CTAs (64 threads per 15 x 15 exponential: 98 vs 113 us for 256 points), a single point from threads per product (18 vs 42 us)
+        model_expm_kernel<true><<<dim3(K, N), (long long)K * N >= 1024 ? 64 : 256, smem_expm, st>>>(m->dev, (const double*)m->d_params.p, d_status,
                                                                     (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
     } else {
         static size_t expm_attr = 0;
@@ -380,14 +380,16 @@ static int model_build_dev(imc_model* m, int N, const double* d_theta, double* d
                                                                      (double*)m->d_pbuf.p, (double*)m->d_prebuf.p);
     }
     CUDA_TRY(cudaGetLastError());
-    const size_t smem_chain = sizeof(double) * (2 * MAX_STATES + (size_t)K * K + 2 * (size_t)K * MAX_L + 128);
+    size_t smem_chain = sizeof(double) * (2 * MAX_STATES + (size_t)K * K + 2 * (size_t)K * MAX_L + 128);
+    const int stage = smem_chain + sizeof(double) * (size_t)m->p_stride <= 96 * 1024 ? 1 : 0;     // (two CTAs per SM still fit)
+    if (stage) smem_chain += sizeof(double) * (size_t)m->p_stride;
     static size_t chain_attr = 0;
     if (smem_chain > chain_attr && smem_chain > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(model_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain));
         chain_attr = smem_chain;
     }
     model_chain_kernel<<<N, 128, smem_chain, st>>>(m->dev, (const double*)m->d_params.p, (const double*)m->d_pbuf.p,
-                                                   (const double*)m->d_prebuf.p, d_status, d_pi, d_T);
+                                                   (const double*)m->d_prebuf.p, d_status, d_pi, d_T, stage);
     CUDA_TRY(cudaGetLastError());
     g_launches += 3;
     return IMC_OK;

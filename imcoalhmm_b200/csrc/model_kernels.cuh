@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256) model_expm_kernel(ModelDev m, const doubl
 // u chain, L-block products, joint matrix J -> pi, T   (transitions.py:204-248).  One CTA per point.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const double* params, const double* pbuf,
-                                                          const double* prebuf, int* status, double* pi, double* T) {
+                                                          const double* prebuf, int* status, double* pi, double* T, int stage) {
     extern __shared__ double sm[];
     const int n_pt = blockIdx.x, K = m.K, tid = threadIdx.x, nt = blockDim.x;
     if (status[n_pt] != 0) {   // invalid point: a harmless HMM; its log-likelihood is replaced by -inf afterwards
@@ -415,7 +415,14 @@ __global__ void __launch_bounds__(128) model_chain_kernel(ModelDev m, const doub
     double* upth = J + K * K;                // [K][MAX_L]   up_through_i on L(space(i+1))
     double* esum = upth + K * MAX_L;         // [K][MAX_L]   sum over E(space(j+1)) of P_j[l][e], l in L(space(j))
     double* red = esum + K * MAX_L;          // [nt]
+    // small models (stage != 0): all of the point's interval matrices are copied into shared memory first -- the chains below
+    // are serial and would otherwise wait for L2 at every link
     const double* P = pbuf + (size_t)n_pt * m.p_stride;
+    if (stage) {
+        double* Ps = red + nt;
+        for (long long x = tid; x < m.p_stride; x += nt) Ps[x] = P[x];
+        P = Ps;
+    }
     const double* rep = params + (size_t)n_pt * PointParams::size(K) + PointParams::rep_off(K);
     for (int x = tid; x < K * K; x += nt) J[x] = 0.0;
     // u_0: row `initial` of upto0

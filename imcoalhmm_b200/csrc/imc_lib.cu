@@ -105,6 +105,7 @@ struct Context {
     long long opt_zip_pipeline = 0;    // pieces per chunk in pipelined mode: 0 = auto, 1 = off, >= 2 forced
     long long opt_zip_spectral = 0;    // spectral form of the zip kernel (run tokens): 0 = auto, 1 = always, 2 = never
     long long opt_zip_mma = 0;         // MMA form of the spectral kernel: 0 = auto, 1 = always (tiles >= 8), 2 = never
+    long long opt_zip_align = 0;       // aligned form of the MMA shape (one entry per warp-step, host-built schedules): 0 = auto, 1 = on, 2 = off
     long long opt_zip_mma_shape = 0;   // launch shape of the MMA form: 0 = auto, 1..4 see zip_plan_k
     long long opt_zip_run2 = 0;        // two-run form of the MMA shape: 0 = auto (fewer expected DMMA passes), 1 = always, 2 = never
     long long opt_zip_spectral_force_bad = 0;   // test switch: zip_spectral_kernel declares every point unfit (plain-form pass serves them)
@@ -199,6 +200,8 @@ struct ZipDevice {
     double hot_share = 0.0;
     bool run2 = false;                        // two-run form (nsym + 2 base entries, second power table)
     double est_passes = 1.0;                  // expected MMA passes per warp-step: 1 + sum over cold ids of P(some chain of 8 is on it)
+    bool sched = false;                       // aligned form: per-quad schedules, streams padded with no-op words (zip_align_quad)
+    long long pass_cost = 0;                  // MMA passes of one parameter point over all warp-loads (estimate in lock step, exact when aligned)
     long long total_tokens = 0;
     int max_ntok = 0;
     std::vector<ZipChunk> host_chunks;        // sorted by ntok, descending
@@ -620,6 +623,8 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
 // set->d_chain[n][chunk] for the points served.
 static const int MAX_POINTS_PARTS = 32768;
+constexpr double ZIP_STEP_OVERHEAD = 200.0;        // clocks per warp-step beside the DMMAs (calibrated on configs 2, 3, 5; see profiles/r02_aligned_form.txt)
+static thread_local bool g_want_sched = false;     // aligned form (implies the two-run form) wanted, if the call turns out not to be chain-scarce
 static thread_local bool g_want_run2 = false;      // two-run form wanted for the spectral pass of the current call
 
 static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, const double* d_T, const double* d_E, bool spec,
@@ -646,6 +651,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             plan = mp; z = mz; mma = true;
         }
     }
+    const bool try_sched = mma && z->run2 && g_want_sched && set->parts_total == 0 && g_ctx.opt_zip_segment_tokens <= 0;
     // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
     // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
     //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
@@ -696,6 +702,11 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             }
         }
     }
+    if (try_sched && mma && seglen <= 0) {       // not chain-scarce, not segmented: the aligned streams of the same dictionary
+        ZipDevice* zs = nullptr;
+        if ((rc = zip_device(set, z->M, &zs, true, true, true))) return rc;
+        z = zs;
+    }
     ZipArgs za;
     za.tokens = (const uint8_t*)z->tokens.p;
     za.chunks = (const ZipChunk*)z->chunks.p;
@@ -719,6 +730,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     za.nbase = S + (z->run2 ? 2 : 0);
     za.run2 = z->run2 ? 1 : 0;
     za.mma_passes = nullptr;
+    za.sched = z->sched ? 1 : 0;
     if (mma) {
         if (!g_mma_passes) {
             CUDA_TRY(cudaMalloc((void**)&g_mma_passes, sizeof(unsigned long long)));
@@ -778,7 +790,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
     }
     if (spec || !plist) {
         g_last_kernel = spec ? (split ? (mma ? (z->run2 ? "zip-spectral-mma2-segmented" : "zip-spectral-mma-segmented") : "zip-spectral-segmented")
-                                      : (plan.lanes == 32 ? "zip-spectral-warp" : (mma ? (z->run2 ? "zip-spectral-mma2" : "zip-spectral-mma") : "zip-spectral")))
+                                      : (plan.lanes == 32 ? "zip-spectral-warp" : (mma ? (z->sched ? "zip-spectral-mma2-aligned" : (z->run2 ? "zip-spectral-mma2" : "zip-spectral-mma")) : "zip-spectral")))
                              : (split ? "zip-segmented" : (plan.lanes == 32 ? "zip-warp" : "zip"));
     }
     if ((rc = launch_zip(za, plan, st))) return rc;
@@ -872,7 +884,7 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
         }
         // Two-run form of the MMA shape (the second run symbol -- missing data -- diagonalised as well): worth it where the
         // dictionary that fits is small (K >= 32), judged by the expected DMMA work = tokens x passes per warp-step.
-        bool run2 = false;
+        bool run2 = false, sched = false;
         if (g_ctx.opt_zip_run2 != 2 && !parts && zip_mma_tile(zip_tile(K)) && g_ctx.opt_zip_mma != 2 && g_ctx.opt_zip_lanes == 0) {
             ZipPlan p1, p2;
             ZipDevice *z1 = nullptr, *z2 = nullptr;
@@ -884,8 +896,32 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                     zip_device(set, p2.M, &z2, true, true) == IMC_OK)
                     run2 = g_ctx.opt_zip_run2 == 1 || (double)z2->total_tokens * z2->est_passes < 0.93 * (double)z1->total_tokens * z1->est_passes;
             }
+            // Aligned form: the two-run streams of every warp-load merged into one schedule with a single entry per warp-step; its
+            // pass count is exact, the lock-step ones are estimates (0.9: it pays a little more per pass for the no-op bookkeeping)
+            if (z1 && g_ctx.opt_zip_align != 2 && (g_ctx.opt_zip_align == 1 || ((long long)N * ns >= 1024 && z1->est_passes >= 1.5))) {
+                ZipPlan p3;
+                ZipDevice* z3 = nullptr;
+                if ((rc = seqset_run2_prepare(set))) return rc;
+                if (set->run2_state == 1 && zip_plan(K, S, set->run2_merges.size(), &p3, 0, true, true, true) == IMC_OK &&
+                    zip_device(set, p3.M, &z3, true, true, true) == IMC_OK) {
+                    const ZipDevice* zl = run2 && z2 ? z2 : z1;
+                    // cost in FP64-pipe clocks of a warp: a pass is KT x NT DMMAs of 16 clocks; every warp-step also carries ~ZIP_STEP_OVERHEAD
+                    // clocks of token decoding, table look-ups and rescaling, which lock step pays once for all its passes
+                    const int tile = zip_tile(K);
+                    const double pass = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8);
+                    const double lock = (double)zl->pass_cost / zl->est_passes * (ZIP_STEP_OVERHEAD + zl->est_passes * pass);
+                    const double aligned = (double)z3->pass_cost * (ZIP_STEP_OVERHEAD + pass);
+                    sched = g_ctx.opt_zip_align == 1 || aligned < 0.95 * lock;
+                    if (getenv("IMC_TRACE_PLAN"))
+                        fprintf(stderr, "imc plan: K=%d lock-step steps %.0f x %.2f passes (%s), aligned steps %lld -> cost %.3g vs %.3g: %s\n", K,
+                                (double)zl->pass_cost / zl->est_passes, zl->est_passes, zl->run2 ? "two-run" : "one-run", z3->pass_cost, lock, aligned,
+                                sched ? "aligned" : "lock step");
+                }
+            }
+            if (sched) run2 = true;
         }
         g_want_run2 = run2;
+        g_want_sched = sched;
         const int sstride = zip_spec_stride(K, S, run2);
         if ((rc = set->d_spec.reserve(sizeof(double) * (size_t)N * sstride))) return rc;
         if ((rc = set->d_lists.reserve(sizeof(int) * ((size_t)3 * N + 2)))) return rc;
@@ -1036,6 +1072,7 @@ extern "C" int imc_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "zip_spectral")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_spectral must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_spectral = value; return IMC_OK; }
     if (!strcmp(key, "zip_spectral_force_bad")) { g_ctx.opt_zip_spectral_force_bad = value ? 1 : 0; return IMC_OK; }
     if (!strcmp(key, "zip_mma")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_mma must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_mma = value; return IMC_OK; }
+    if (!strcmp(key, "zip_align")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_align must be 0, 1 or 2"); g_ctx.opt_zip_align = value; return IMC_OK; }
     if (!strcmp(key, "zip_mma_shape")) { if (value < 0 || value > 4) return fail(IMC_ERR_INVALID, "zip_mma_shape must be in [0, 4]"); g_ctx.opt_zip_mma_shape = value; return IMC_OK; }
     if (!strcmp(key, "zip_run2")) { if (value < 0 || value > 2) return fail(IMC_ERR_INVALID, "zip_run2 must be 0 (auto), 1 (always) or 2 (never)"); g_ctx.opt_zip_run2 = value; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { g_ctx.opt_comm_fused = value ? 1 : 0; return IMC_OK; }
@@ -1056,6 +1093,7 @@ extern "C" int imc_get_option(const char* key, int64_t* value_out) {
     if (!strcmp(key, "zip_spectral")) { *value_out = g_ctx.opt_zip_spectral; return IMC_OK; }
     if (!strcmp(key, "zip_spectral_force_bad")) { *value_out = g_ctx.opt_zip_spectral_force_bad; return IMC_OK; }
     if (!strcmp(key, "zip_mma")) { *value_out = g_ctx.opt_zip_mma; return IMC_OK; }
+    if (!strcmp(key, "zip_align")) { *value_out = g_ctx.opt_zip_align; return IMC_OK; }
     if (!strcmp(key, "zip_mma_shape")) { *value_out = g_ctx.opt_zip_mma_shape; return IMC_OK; }
     if (!strcmp(key, "zip_run2")) { *value_out = g_ctx.opt_zip_run2; return IMC_OK; }
     if (!strcmp(key, "comm_fused")) { *value_out = g_ctx.opt_comm_fused; return IMC_OK; }

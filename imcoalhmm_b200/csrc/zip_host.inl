@@ -178,13 +178,56 @@ static int seqset_run2_prepare(imc_seqset* set) {
 }
 
 // token streams over the first M dictionary ids, level-ordered, on the device (cached per M and form)
-static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDevice** out);
-static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false, bool run2 = false) {
-    try { return zip_device_build(set, M, spec, run2, out); }
+static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, bool sched, ZipDevice** out);
+static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false, bool run2 = false, bool sched = false) {
+    try { return zip_device_build(set, M, spec, run2, sched, out); }
     catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory while deriving the token streams"); }
 }
-static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDevice** out) {
-    for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec && z->run2 == run2) { *out = z; return IMC_OK; }
+
+// Aligned form of the MMA shape (sched): the chains of a warp do not march in lock step through their own token streams but
+// follow ONE common schedule per warp-load (quad) -- a supersequence of their entry-id sequences, built here -- in which every
+// warp-step applies a single entry: chains whose next token is that entry take it, the others hold a no-op word.  One MMA pass per
+// warp-step, where lock step spends 1 + (distinct cold entries among the chains).  Schedule: hot steps until `stall` chains wait at
+// a cold entry (or no chain wants the hot one), then one step per waiting cold entry, twice (in the two-run form a chain served by
+// "into the second basis" wants "back" next).  streams[i] = words of chain i, all of one length (a multiple of 8).
+static void zip_align_quad(const std::vector<const std::vector<uint32_t>*>& tok, int hot, int stall,
+                           std::vector<std::vector<uint32_t>>* streams, long long* steps_out) {
+    const int n = (int)tok.size();
+    std::vector<size_t> ptr(n, 0);
+    long long steps = 0;
+    auto next_id = [&](int i) { return ptr[i] < tok[i]->size() ? (int)((*tok[i])[ptr[i]] & 0xffu) : -1; };
+    auto emit = [&](int id) {
+        for (int i = 0; i < n; ++i) {
+            uint32_t w = RUN_NOP_BIT | (uint32_t)id;          // (sitting this step out, but every lane knows the step's entry)
+            if (next_id(i) == id) w = (*tok[i])[ptr[i]++];
+            if (streams) (*streams)[i].push_back(w);
+        }
+        ++steps;
+    };
+    for (;;) {
+        bool left = false;
+        for (int i = 0; i < n; ++i) left = left || next_id(i) >= 0;
+        if (!left) break;
+        for (;;) {
+            int nhot = 0, nstalled = 0;
+            for (int i = 0; i < n; ++i) { const int id = next_id(i); nhot += id == hot; nstalled += id >= 0 && id != hot; }
+            if (nhot == 0 || nstalled >= stall) break;
+            emit(hot);
+        }
+        for (int round = 0; round < 2; ++round) {
+            bool want[256] = {false};
+            for (int i = 0; i < n; ++i) { const int id = next_id(i); if (id >= 0 && id != hot) want[id] = true; }
+            for (int id = 0; id < 256; ++id) if (want[id]) emit(id);
+        }
+    }
+    if (streams)
+        for (int i = 0; i < n; ++i) while ((*streams)[i].size() % 8) (*streams)[i].push_back(RUN_NOP_BIT | 0xffu);
+    if (steps_out) *steps_out = (steps + 7) / 8 * 8;
+}
+
+static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, bool sched, ZipDevice** out) {
+    for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec && z->run2 == run2 && z->sched == sched) { *out = z; return IMC_OK; }
+    if (sched && (!spec || M > 255)) return fail(IMC_ERR_INVALID, "the aligned form needs run tokens and at most 255 dictionary ids");
     const int ns = (int)set->streams.size();
     const ZipMerges& mg = run2 ? set->run2_merges : (spec ? set->run_merges : set->merges);
     const std::vector<std::vector<uint32_t>>& rfull = run2 ? set->run2_tok_full : set->run_tok_full;
@@ -205,6 +248,49 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDev
     std::vector<int> order(ns);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ntok(x) > ntok(y); });
+    int hot_id = 0;
+    double hot_share = 0.0, est_passes = 1.0;
+    long long real_tokens = 0;
+    if (spec) {        // the most frequent entry of the streams: the MMA form keeps its matrix in registers
+        std::vector<long long> hist(256, 0);
+        for (int k = 0; k < ns; ++k) { for (uint32_t t : rtok[k]) hist[t & 0xffu]++; real_tokens += (long long)rtok[k].size(); }
+        hot_id = (int)(std::max_element(hist.begin(), hist.end()) - hist.begin());
+        hot_share = real_tokens > 0 ? (double)hist[hot_id] / (double)real_tokens : 0.0;
+        for (int id = 0; id < 256; ++id)
+            if (id != hot_id && hist[id] > 0) est_passes += 1.0 - std::pow(1.0 - (double)hist[id] / (double)real_tokens, 8.0);
+    }
+    // MMA passes the streams cost, summed over the warp-loads of 8 chains (sorted order): lock step = longest stream of the quad x
+    // expected passes per warp-step; aligned = the steps of the quad's schedule
+    long long pass_cost = 0;
+    for (int i = 0; i < ns; i += 8) pass_cost += (long long)std::llround((double)ntok(order[i]) * est_passes);
+    if (sched) {
+        const int nq = (ns + 7) / 8;
+        auto quad_tokens = [&](int q) {
+            std::vector<const std::vector<uint32_t>*> t;
+            for (int i = q * 8; i < std::min(ns, q * 8 + 8); ++i) t.push_back(&rtok[order[i]]);
+            return t;
+        };
+        int stall = 3;          // the threshold that gives the fewest steps on a sample of quads
+        {
+            long long best = -1;
+            for (int g = 2; g <= 6; ++g) {
+                long long tot = 0;
+                for (int q = 0; q < nq; q += std::max(1, nq / 4)) { long long st; zip_align_quad(quad_tokens(q), hot_id, g, nullptr, &st); tot += st; }
+                if (best < 0 || tot < best) { best = tot; stall = g; }
+            }
+        }
+        std::vector<std::vector<std::vector<uint32_t>>> aligned(nq);
+        if (!parallel_for(nq, [&](int q) {
+                const auto t = quad_tokens(q);
+                aligned[q].resize(t.size());
+                zip_align_quad(t, hot_id, stall, &aligned[q], nullptr);
+            })) return fail(IMC_ERR_NOMEM, "out of host memory while aligning the token streams");
+        pass_cost = 0;
+        for (int q = 0; q < nq; ++q) {
+            pass_cost += aligned[q].empty() ? 0 : (long long)aligned[q][0].size();
+            for (size_t j = 0; j < aligned[q].size(); ++j) rtok[order[q * 8 + j]].swap(aligned[q][j]);      // (run sites below skip the no-op words)
+        }
+    }
     std::vector<ZipChunk> chunks(ns);
     long long off = 0;
     for (int i = 0; i < ns; ++i) {
@@ -216,7 +302,7 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDev
         chunks[i].out_index = k;
         chunks[i].first_run = spec ? (run2 ? set->run2_first_run[k] : set->first_run[k]) : 0;
         long long rs = chunks[i].first_run;
-        if (spec) for (uint32_t t : rtok[k]) if (!(t & RUN_TABLE2_BIT)) rs += (t >> 8) & RUN_MAX;
+        if (spec) for (uint32_t t : rtok[k]) if (!(t & (RUN_TABLE2_BIT | RUN_NOP_BIT))) rs += (t >> 8) & RUN_MAX;
         chunks[i].run_sites = (int)rs;
         chunks[i].run2_sites = run2 ? (int)set->run2_sites[k] : 0;
         chunks[i].pad = 0;
@@ -224,6 +310,7 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDev
         off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
     std::vector<uint8_t> flat((size_t)off, 0);
+    if (sched) { uint32_t* w = reinterpret_cast<uint32_t*>(flat.data()); for (size_t x = 0; x < flat.size() / 4; ++x) w[x] = RUN_NOP_BIT | 0xffu; }
     long long total = 0;
     for (int i = 0; i < ns; ++i) {
         const int k = order[i];
@@ -234,19 +321,17 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, ZipDev
     if (!z) return fail(IMC_ERR_NOMEM, "out of memory");
     z->M = M;
     z->spec = spec;
-    if (spec) {        // the most frequent entry of the streams: the MMA form keeps its matrix in registers
-        std::vector<long long> hist(256, 0);
-        for (int k = 0; k < ns; ++k) for (uint32_t t : rtok[k]) hist[t & 0xffu]++;
-        z->hot_id = (int)(std::max_element(hist.begin(), hist.end()) - hist.begin());
-        z->hot_share = total > 0 ? (double)hist[z->hot_id] / (double)total : 0.0;
-        z->est_passes = 1.0;
-        for (int id = 0; id < 256; ++id)
-            if (id != z->hot_id && hist[id] > 0) z->est_passes += 1.0 - std::pow(1.0 - (double)hist[id] / (double)total, 8.0);
-    }
+    z->hot_id = hot_id;
+    z->hot_share = hot_share;
+    z->est_passes = sched ? 1.0 : est_passes;
+    z->pass_cost = pass_cost;
+    z->sched = sched;
+    if (sched) total = real_tokens;
     z->run2 = run2;
     z->nlevels = (int)zl.level_start.size() - 1;
     z->total_tokens = total;
-    z->max_ntok = ns ? chunks[0].ntok : 0;
+    z->max_ntok = 0;
+    for (const ZipChunk& c : chunks) z->max_ntok = std::max(z->max_ntok, c.ntok);
     z->host_chunks.swap(chunks);      // no copy, cannot throw
     int rc;
     if ((rc = z->tokens.reserve(std::max<size_t>(flat.size(), 64))) || (rc = z->chunks.reserve(sizeof(ZipChunk) * std::max(ns, 1))) ||

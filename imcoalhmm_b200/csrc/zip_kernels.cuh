@@ -39,6 +39,7 @@ constexpr int RUN_LO_ROWS = 1 << RUN_LO_BITS, RUN_LO_MASK = RUN_LO_ROWS - 1;
 constexpr int RUN_ROWS = RUN_LO_ROWS + (1 << RUN_HI_BITS);
 constexpr int RUN_MAX = (1 << (RUN_LO_BITS + RUN_HI_BITS)) - 1;
 constexpr int RUN_HI_MASK = (1 << RUN_HI_BITS) - 1;
+constexpr uint32_t RUN_NOP_BIT = 1u << 21;         // word bit: no token of this chain in this warp-step (aligned form, zip_align_quad)
 constexpr uint32_t RUN_TABLE2_BIT = 1u << 20;      // word bit: the run of this token is of the SECOND run symbol (two-run form)
 
 struct ZipChunk {
@@ -92,6 +93,7 @@ struct ZipArgs {
     int hot_id;                  // MMA form: the most frequent entry of the streams (its matrix lives in registers)
     int nbase;                   // spectral form: base entries read from `spec` (S, or S + 2 in the two-run form: + B^-1, B)
     int run2;                    // two-run form: a second power table (of the second run symbol's eigenvalues) is in use
+    int sched;                        // MMA form: aligned streams (one entry per warp-step, no-op words; zip_align_quad in zip_host.inl)
     unsigned long long* mma_passes;   // MMA form: passes (of KT x NT DMMAs each) executed, for the roofline (one atomic per work unit)
 };
 
@@ -793,7 +795,7 @@ __device__ __forceinline__ long long lds_s64(uint32_t addr) {
 }
 
 // The same work unit in the MMA form (ZipCfgM, spectral form only): 8 chains per warp, state in the D / A fragments.
-template <class C>
+template <class C, bool SCHED>
 __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int unit, const double* dict, const double* sE,
                                                  const double* spi, const long long* dexp, const double* ptab,
                                                  const double (&Bh)[C::KT][C::NT], const typename C::Lane& L) {
@@ -810,7 +812,8 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
     IMC_ASSERT(n >= 0 && n < a.N && quad * C::CPW < a.nchunks);
     const ZipChunk ch = a.chunks[have ? ci : quad * C::CPW];
     const int tok0 = seg * a.seglen;
-    const int nt = have ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
+    // (aligned form: lanes without a chain follow the words of the quad's first chain, as no-ops, to know every step's entry)
+    const int nt = (have || SCHED) ? (a.nseg > 1 ? max(0, min(ch.ntok - tok0, a.seglen)) : ch.ntok) : 0;
     IMC_ASSERT(ch.ntok >= 0 && ch.first_sym < a.S && ch.first_sym >= -a.K && ch.first_run <= RUN_MAX && hot < a.M);
     const uint4* tp = reinterpret_cast<const uint4*>(a.tokens + ch.tok_off + (size_t)tok0 * 4);
     int maxnt = nt;
@@ -868,7 +871,7 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         constexpr bool ALL = decltype(all_tag)::value;
         if (!ALL && !active) wb = 0u;
         const int id = wb & 0xffu;
-        IMC_ASSERT(id < a.M && (wb >> 21) == 0u && (a.run2 || !(wb & RUN_TABLE2_BIT)));
+        IMC_ASSERT(id < a.M && (wb >> 22) == 0u && (a.run2 || !(wb & RUN_TABLE2_BIT)));
         const uint32_t tab = ptab_s + ((wb >> 20) & 1u) * (RUN_ROWS * PT * 8);      // the first or the second run symbol's table
         const uint32_t pa = tab + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = tab + (RUN_LO_ROWS + ((wb >> (8 + RUN_LO_BITS)) & RUN_HI_MASK)) * (PT * 8);
         double2 fa[NT], fb[NT];            // (lambda / lambda_max)^n of this token for the lane's states: independent of the products below
@@ -909,6 +912,42 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
             scale += ex;
         }
     };
+    // aligned form: ONE entry per warp-step, the same for every chain that takes part; the others hold a no-op word that still
+    // names the step's entry (so the choice of the B operand needs no vote), 0xff in the padding behind a stream
+    auto step_aligned = [&](uint32_t wb) {
+        const int ids = wb & 0xffu;
+        if (ids == 0xff) return;                       // warp-uniform: the streams of a quad have one length
+        const bool active = have && !(wb & RUN_NOP_BIT);
+        IMC_ASSERT(ids < a.M && (wb >> 22) == 0u && __all_sync(0xffffffffu, ids == __shfl_sync(0xffffffffu, ids, 0)));
+        // (a no-op word carries no run: rows 0 of the tables)
+        const uint32_t tab = ptab_s + ((wb >> 20) & 1u) * (RUN_ROWS * PT * 8);
+        const uint32_t pa = tab + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = tab + (RUN_LO_ROWS + ((wb >> (8 + RUN_LO_BITS)) & RUN_HI_MASK)) * (PT * 8);
+        double2 fa[NT], fb[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { fa[t] = lds_f64x2(pa + t * 64); fb[t] = lds_f64x2(pb + t * 64); }
+        const long long ex = lds_s64(dexp_s + ids * 8);
+        ++passes;
+        double N[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { N[t][0] = 0.0; N[t][1] = 0.0; }
+        if (ids == hot) {
+#pragma unroll
+            for (int u = 0; u < KT; ++u)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) dmma884(N[t][0], N[t][1], D[u >> 1][u & 1], Bh[u][t]);
+        } else {
+            const uint32_t bc = dict_s + ids * (C::STRIDE_D * 8);
+#pragma unroll
+            for (int u = 0; u < KT; ++u)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) dmma884(N[t][0], N[t][1], D[u >> 1][u & 1], lds_f64(bc + (u * NT + t) * 256));
+        }
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { D[t][0] = N[t][0] * (fa[t].x * fb[t].x); D[t][1] = N[t][1] * (fa[t].y * fb[t].y); }
+            scale += ex;
+        }
+    };
     uint4 cur = make_uint4(0, 0, 0, 0), cur2 = cur;
     if (nt > 0) { cur = tp[0]; cur2 = tp[1]; }
     for (int blk = 0; blk * 8 < maxnt; ++blk) {
@@ -916,7 +955,10 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         if ((blk + 1) * 8 < nt) { nxt = tp[2 * blk + 2]; nxt2 = tp[2 * blk + 3]; }
         const int rem = nt - blk * 8;
         const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, cur2.x, cur2.y, cur2.z, cur2.w};
-        if (__all_sync(0xffffffffu, rem >= 8)) {
+        if (SCHED) {          // streams of a quad have one length, a multiple of 8; lanes without a chain hold no-op words throughout
+#pragma unroll
+            for (int b = 0; b < 8; ++b) step_aligned(rem > 0 ? w[b] : (RUN_NOP_BIT | 0xffu));
+        } else if (__all_sync(0xffffffffu, rem >= 8)) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) step(w[b], true, std::true_type());
         } else {
@@ -1060,7 +1102,8 @@ __global__ void __launch_bounds__(THREADS, MINB) zip_forward_kernel(ZipArgs a) {
                 if (lane == 0) unit = atomicAdd(a.point_next + slot, 1);
                 unit = __shfl_sync(0xffffffffu, unit, 0);
                 if (unit >= nunits) break;
-                zip_run_unit_mma<C>(a, n, unit, dict, sE, spi, dexp, ptab, Bh, L);
+                if (a.sched) zip_run_unit_mma<C, true>(a, n, unit, dict, sE, spi, dexp, ptab, Bh, L);
+                else zip_run_unit_mma<C, false>(a, n, unit, dict, sE, spi, dexp, ptab, Bh, L);
             }
         } else {
             for (; warp < a.active_warps;) {

@@ -56,7 +56,8 @@ for trial in range(trials):
         fk = 1
     spec = int(rng.choice([0, 1, 1, 1, 2]))                  # spectral form: auto, forced (points that do not qualify take the plain form), off
     for k, v in (("forward_kernel", fk), ("zip_lanes", lanes), ("zip_ctas_per_sm", ctas), ("zip_segment_tokens", seg), ("zip_max_entries", cap),
-                 ("zip_pipeline", pipe), ("zip_spectral", spec), ("zip_mma", int(rng.choice([0, 1, 2]))), ("zip_run2", int(rng.choice([0, 1, 2])))):
+                 ("zip_pipeline", pipe), ("zip_spectral", spec), ("zip_mma", int(rng.choice([0, 1, 2]))), ("zip_run2", int(rng.choice([0, 1, 2]))),
+                 ("zip_align", int(rng.choice([0, 1, 1, 2])))):
         m.set_option(k, v)
     got = fset.forward_batch(pis, Ts, Es)
     # the oracle's plain forward divides by the zero scale of an impossible observation and returns NaN where the

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0)
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off[:mma 0 auto|1|2 off[:shape[:run2]]]]]")
+    ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off[:mma 0 auto|1|2 off[:shape[:run2[:align 0 auto|1|2 off]]]]]]")
     ap.add_argument("--plain", action="store_true", help="also time the uncompressed kernel")
     ap.add_argument("--missing", type=float, default=0.04, help="missing-data coverage of the simulated chunks (bench.py: 0.04)")
     ap.add_argument("--check", type=int, default=2, help="chunks to check against the oracle")
@@ -77,6 +77,11 @@ def main():
         m.set_option("zip_mma", mma)
         m.set_option("zip_mma_shape", f[6] if len(f) > 6 else 0)
         m.set_option("zip_run2", f[7] if len(f) > 7 else 0)
+        al = f[8] if len(f) > 8 else 0
+        try:
+            m.set_option("zip_align", al)
+        except m.IMCError:
+            pass                      # an older experiment build (IMC_LIB_PATH)
         m.set_option("forward_kernel", 4)
         m.set_option("zip_lanes", lanes)
         m.set_option("zip_ctas_per_sm", ctas)
@@ -85,7 +90,7 @@ def main():
         m.set_option("zip_ctas_per_sm", ctas)   # zip_info reports the plan in effect
         info = fset.zip_info(K)
         rinfo = fset.run_info(K)
-        out = timed("zip lanes=%d ctas=%d cap=%d pipe=%d spec=%d mma=%d M=%d/%d tok=%d/%d" % (lanes, ctas, cap, pipe, spec, mma, info["ids_used"],
+        out = timed("zip lanes=%d ctas=%d cap=%d pipe=%d spec=%d mma=%d align=%d M=%d/%d tok=%d/%d" % (lanes, ctas, cap, pipe, spec, mma, al, info["ids_used"],
                     rinfo["ids_used"], info["tokens"], rinfo["tokens"]))
         if ref is None:
             ref = out

@@ -534,7 +534,8 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
             KT, NT = (K + 3) // 4, (K + 7) // 8
             dmma_tflops = passes_per_launch * KT * NT * 512.0 / t_kernel / 1e12
             roofline = {
-                "bound": "fp64-tensor", "kernel": kname + " (spectral form, MMA shape)", "achieved": exec_tflops, "peak": peak_dmma,
+                "bound": "fp64-tensor", "kernel": kname + " (spectral form, MMA shape%s)" % (", aligned streams" if "aligned" in kernel else ""),
+                "kernel_form": kernel, "achieved": exec_tflops, "peak": peak_dmma,
                 "unit": "TFLOP/s", "frac": exec_tflops / peak_dmma, "traffic": None, "kernel_ms": 1e3 * t_kernel,
                 "bound_note": "FP64 tensor pipe: achieved = chain-steps x (2 K^2 + K) flop / kernel time; peak = DMMA.8x8x4 rate "
                               "measured in this run (imc_measure_fp64_peak)",
@@ -545,7 +546,8 @@ def measure_workload(g, name, wl, chunk_factory, steps, warmup, forward_kernel=0
                 "frac_note": "frac counts ALGORITHMIC flops only; the tensor pipe itself is busy executed_dmma_frac_of_peak of the time "
                              "(ncu sm__inst_executed_pipe_tensor_subpipe_dmma agrees: profiles/r02_zip*_mma_ncu.txt)",
                 "executed_note": "every pass is KT x NT DMMAs of 512 flop for the 8 chains of a warp: tiles are padded to 8 x 4 "
-                                 "(K=10: 100 of 192 MACs useful) and a pass for a cold entry serves only the chains on that entry",
+                                 "(K=10: 100 of 192 MACs useful) and a pass serves only the chains whose token is its entry "
+                                 "(lock step: hot pass + one per distinct cold entry; aligned: one pass per step of the warp's schedule)",
                 "smem_view_of_the_fma_shapes": smem_view, "compression": compression, "plain_forward_equivalent": fp64_view}
         else:
             roofline = dict(smem_view, kernel=kname + (" (spectral form: run tokens)" if spectral else ""), traffic=None,

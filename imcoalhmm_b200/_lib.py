@@ -86,6 +86,9 @@ _SIGNATURES = {
     "imc_get_option": (ctypes.c_int, [ctypes.c_char_p, c_i64p]),
     "imc_kernel_launches": (ctypes.c_int64, []),
     "imc_mma_passes": (ctypes.c_int, [c_i64p]),
+    "imc_seqset_align_info": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i64p, c_f64p, c_i64p, c_i32p, c_i32p]),
+    "imc_seqset_align_quad": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int64,
+                                             c_i64p, c_i32p]),
     "imc_last_forward_kernel": (ctypes.c_char_p, []),
 }
 

@@ -214,15 +214,65 @@ static void zip_align_quad(const std::vector<const std::vector<uint32_t>*>& tok,
             if (nhot == 0 || nstalled >= stall) break;
             emit(hot);
         }
-        for (int round = 0; round < 2; ++round) {
-            bool want[256] = {false};
-            for (int i = 0; i < n; ++i) { const int id = next_id(i); if (id >= 0 && id != hot) want[id] = true; }
+        // cold slot: one step per waiting cold entry; again for the chains it has moved to another cold entry (in the two-run form
+        // "into the second basis" is followed by "back"), as long as that serves at least two chains per step
+        for (int round = 0; round < 8; ++round) {
+            int want[256] = {0}, waiting = 0, kinds = 0;
+            for (int i = 0; i < n; ++i) { const int id = next_id(i); if (id >= 0 && id != hot) { kinds += want[id]++ == 0; ++waiting; } }
+            if (waiting == 0 || (round >= 2 && waiting < 2 * kinds)) break;
             for (int id = 0; id < 256; ++id) if (want[id]) emit(id);
         }
     }
     if (streams)
         for (int i = 0; i < n; ++i) while ((*streams)[i].size() % 8) (*streams)[i].push_back(RUN_NOP_BIT | 0xffu);
     if (steps_out) *steps_out = (steps + 7) / 8 * 8;
+}
+
+// The two-run token streams of the set over the first M dictionary ids (ids level-ordered like the device dictionary), the
+// order of the streams by length and their histogram figures: what the aligned form is built from (host only, no CUDA).
+struct ZipHostStreams {
+    std::vector<std::vector<uint32_t>> rtok;
+    std::vector<int> order;
+    int hot_id = 0;
+    double hot_share = 0.0, est_passes = 1.0;
+    long long tokens = 0;
+};
+static void zip_host_streams(const ZipMerges& mg, const std::vector<std::vector<uint32_t>>& rfull, int M, const ZipLevels& zl, ZipHostStreams* h) {
+    const int ns = (int)rfull.size();
+    h->rtok.assign(ns, {});
+    if (!parallel_for(ns, [&](int k) {
+            run_expand(mg, rfull[k], M, h->rtok[k]);
+            for (auto& t : h->rtok[k]) t = (t & ~0xffu) | zl.perm[t & 0xffu];
+        })) throw std::bad_alloc();
+    h->order.resize(ns);
+    std::iota(h->order.begin(), h->order.end(), 0);
+    std::stable_sort(h->order.begin(), h->order.end(), [&](int x, int y) { return h->rtok[x].size() > h->rtok[y].size(); });
+    std::vector<long long> hist(256, 0);
+    h->tokens = 0;
+    for (int k = 0; k < ns; ++k) { for (uint32_t t : h->rtok[k]) hist[t & 0xffu]++; h->tokens += (long long)h->rtok[k].size(); }
+    h->hot_id = (int)(std::max_element(hist.begin(), hist.end()) - hist.begin());
+    h->hot_share = h->tokens > 0 ? (double)hist[h->hot_id] / (double)h->tokens : 0.0;
+    h->est_passes = 1.0;
+    for (int id = 0; id < 256; ++id)
+        if (id != h->hot_id && hist[id] > 0) h->est_passes += 1.0 - std::pow(1.0 - (double)hist[id] / (double)h->tokens, 8.0);
+}
+static std::vector<const std::vector<uint32_t>*> zip_quad_tokens(const ZipHostStreams& h, int q) {
+    std::vector<const std::vector<uint32_t>*> t;
+    const int ns = (int)h.order.size();
+    for (int i = q * 8; i < std::min(ns, q * 8 + 8); ++i) t.push_back(&h.rtok[h.order[i]]);
+    return t;
+}
+// the stall threshold that gives the fewest steps on a sample of quads
+static int zip_align_pick_stall(const ZipHostStreams& h) {
+    const int nq = ((int)h.order.size() + 7) / 8;
+    int stall = 3;
+    long long best = -1;
+    for (int g = 2; g <= 6; ++g) {
+        long long tot = 0;
+        for (int q = 0; q < nq; q += std::max(1, nq / 4)) { long long st; zip_align_quad(zip_quad_tokens(h, q), h.hot_id, g, nullptr, &st); tot += st; }
+        if (best < 0 || tot < best) { best = tot; stall = g; }
+    }
+    return stall;
 }
 
 static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, bool sched, ZipDevice** out) {
@@ -598,6 +648,73 @@ extern "C" int imc_seqset_run_tokens(imc_seqset* set, int chunk, int ids, uint32
         if (capacity < (int64_t)tok.size()) return fail(IMC_ERR_INVALID, "capacity %lld < %zu tokens", (long long)capacity, tok.size());
         if (!tok.empty()) memcpy(out, tok.data(), tok.size() * sizeof(uint32_t));
     }
+    return IMC_OK;
+}
+
+// Host-only views of the aligned form for a K-state model (tests, tools/schedule_sim.py): no CUDA call is made.
+static int align_host_streams(imc_seqset* set, int K, ZipHostStreams* h, int* M_out) {
+    if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    int rc = seqset_run2_prepare(set);
+    if (rc) return rc;
+    if (set->run2_state != 1) return fail(IMC_ERR_UNSUPPORTED, "this set has no second run symbol");
+    ZipPlan plan;
+    if ((rc = zip_plan(K, set->nsym, set->run2_merges.size(), &plan, 0, true, true, true))) return rc;
+    try {
+        ZipLevels zl = zip_levels(set->run2_merges, plan.M);
+        zip_host_streams(set->run2_merges, set->run2_tok_full, plan.M, zl, h);
+    } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory"); }
+    if (M_out) *M_out = plan.M;
+    return IMC_OK;
+}
+
+extern "C" int imc_seqset_align_info(imc_seqset* set, int K, int stall, int64_t* lock_steps, double* est_passes, int64_t* aligned_steps,
+                                     int* stall_used, int* hot_id) {
+    ZipHostStreams h;
+    int rc = align_host_streams(set, K, &h, nullptr);
+    if (rc) return rc;
+    try {
+        const int ns = (int)h.order.size(), nq = (ns + 7) / 8;
+        if (stall <= 0) stall = zip_align_pick_stall(h);
+        long long lock = 0;
+        for (int i = 0; i < ns; i += 8) lock += (long long)h.rtok[h.order[i]].size();
+        std::vector<long long> st(nq, 0);
+        if (!parallel_for(nq, [&](int q) { zip_align_quad(zip_quad_tokens(h, q), h.hot_id, stall, nullptr, &st[q]); })) throw std::bad_alloc();
+        long long al = 0;
+        for (long long x : st) al += x;
+        if (lock_steps) *lock_steps = lock;
+        if (est_passes) *est_passes = h.est_passes;
+        if (aligned_steps) *aligned_steps = al;
+        if (stall_used) *stall_used = stall;
+        if (hot_id) *hot_id = h.hot_id;
+    } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory"); }
+    return IMC_OK;
+}
+
+// words of warp-load `quad` as out[nchains][steps]: stall > 0 the aligned streams, stall <= 0 the chains' own token streams,
+// each padded to the longest with the padding word (RUN_NOP_BIT | 0xff)
+extern "C" int imc_seqset_align_quad(imc_seqset* set, int K, int quad, int stall, uint32_t* out, int64_t capacity, int64_t* steps, int* nchains) {
+    if (!steps || !nchains) return fail(IMC_ERR_INVALID, "NULL argument");
+    ZipHostStreams h;
+    int rc = align_host_streams(set, K, &h, nullptr);
+    if (rc) return rc;
+    const int ns = (int)h.order.size();
+    if (quad < 0 || quad * 8 >= ns) return fail(IMC_ERR_INVALID, "quad %d out of range", quad);
+    try {
+        const auto t = zip_quad_tokens(h, quad);
+        std::vector<std::vector<uint32_t>> streams(t.size());
+        if (stall > 0) zip_align_quad(t, h.hot_id, stall, &streams, nullptr);
+        else {
+            size_t mx = 0;
+            for (auto* v : t) mx = std::max(mx, v->size());
+            for (size_t i = 0; i < t.size(); ++i) { streams[i] = *t[i]; streams[i].resize(mx, RUN_NOP_BIT | 0xffu); }
+        }
+        *nchains = (int)t.size();
+        *steps = streams.empty() ? 0 : (int64_t)streams[0].size();
+        if (out) {
+            if (capacity < *steps * *nchains) return fail(IMC_ERR_INVALID, "capacity %lld < %lld words", (long long)capacity, (long long)(*steps * *nchains));
+            for (size_t i = 0; i < streams.size(); ++i) if (*steps) memcpy(out + i * (size_t)*steps, streams[i].data(), (size_t)*steps * sizeof(uint32_t));
+        }
+    } catch (const std::bad_alloc&) { return fail(IMC_ERR_NOMEM, "out of host memory"); }
     return IMC_OK;
 }
 

@@ -182,6 +182,25 @@ class ForwarderSet(object):
         return {"run_sym": sym.value, "ids_available": avail.value, "ids_used": used.value, "tokens": tok.value,
                 "levels": lev.value}
 
+    def align_info(self, K, stall=0):
+        """Aligned form for a K-state model (host only): dict(lock_steps, est_passes, aligned_steps, stall, hot_id)."""
+        lock, al, est = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+        st, hot = ctypes.c_int32(), ctypes.c_int32()
+        check(_lib.load().imc_seqset_align_info(self._handle, int(K), int(stall), ctypes.byref(lock), ctypes.byref(est), ctypes.byref(al),
+                                                ctypes.byref(st), ctypes.byref(hot)))
+        return {"lock_steps": lock.value, "est_passes": est.value, "aligned_steps": al.value, "stall": st.value, "hot_id": hot.value}
+
+    def align_quad(self, K, quad, stall):
+        """uint32[nchains, steps]: the words of warp-load `quad`, aligned (stall > 0) or the chains' own streams (stall <= 0)."""
+        lib = _lib.load()
+        steps, nch = ctypes.c_int64(), ctypes.c_int32()
+        check(lib.imc_seqset_align_quad(self._handle, int(K), int(quad), int(stall), None, 0, ctypes.byref(steps), ctypes.byref(nch)))
+        out = np.zeros((nch.value, steps.value), dtype=np.uint32)
+        if out.size:
+            check(lib.imc_seqset_align_quad(self._handle, int(K), int(quad), int(stall), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                            out.size, ctypes.byref(steps), ctypes.byref(nch)))
+        return out
+
     def run_pairs(self):
         """[P,2] (uint8): row i = (left, right) of run-dictionary id NSYM + i, creation order."""
         n = self.run_info()["ids_available"] - (self.forwarders[0].NSYM if self.forwarders else 0)

@@ -233,6 +233,8 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       diagonalised too, so that a block of m such sites costs two fixed matrices (B^-1, B) and a diagonal
  *                       instead of a product of power-of-two dictionary entries.  0 = auto (where it lowers the expected
  *                       number of DMMA passes: state counts whose dictionary hardly fits, K >= 32), 1 = always, 2 = never.
+ * key "zip_align":      aligned form of the MMA shape (the chains of a warp follow one host-built schedule with a single dictionary
+ *                       entry per warp-step; two-run tokens): 0 = auto (cost model), 1 = wherever it applies, 2 = off.
  * key "zip_mma_shape":  launch shape of the MMA form: 0 = auto, 1 = one CTA of 512 threads per SM (256 for K >= 32),
  *                       2 = two CTAs of 256, 3 = four CTAs of 256 threads with 64 registers (K <= 12), 4 = four CTAs of 128.
  * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).
@@ -252,6 +254,14 @@ int imc_measure_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 int64_t imc_kernel_launches(void);
 /* MMA passes executed by this process so far (each = KT x NT mma.sync.m8n8k4.f64 of 512 flop per warp, KT = ceil(K/4),
  * NT = ceil(K/8)): the executed FP64 tensor work behind bench.py's roofline.  Synchronises the device. */
+/* Aligned form of the MMA kernel (host only, no CUDA call): for a K-state model, the warp-steps of the two-run token streams in
+ * lock step (sum over warp-loads of 8 chains of the longest stream) with the expected passes per step, and the warp-steps (= passes)
+ * of the host-built schedules with one dictionary entry per step.  stall = 0: pick the threshold as the library does. */
+int imc_seqset_align_info(imc_seqset* set, int K, int stall, int64_t* lock_steps, double* est_passes, int64_t* aligned_steps,
+                          int* stall_used, int* hot_id);
+/* The words of warp-load `quad` as out[nchains][steps] (tests): stall > 0 the aligned streams (bit 21 = no token of this chain in this
+ * step, bits 0-7 the step's entry, 0xff in the padding), stall <= 0 the chains' own streams padded with the padding word. */
+int imc_seqset_align_quad(imc_seqset* set, int K, int quad, int stall, uint32_t* out, int64_t capacity, int64_t* steps, int* nchains);
 int imc_mma_passes(int64_t* passes_out);
 /* name of the forward kernel chosen by the last forward call on this thread
  * ("generic", "pair", "dmma", "zip", "zip-segmented", "zip-warp": one warp per chain, chosen for chain-scarce calls;

@@ -103,7 +103,14 @@ def test_full_size_im_model_shard():
     mk = lambda cs: m.ForwarderSet([m.Forwarder.from_symbols(c, 3) for c in cs])
     whole_set = mk(chunks)
     whole = whole_set.forward_batch(pis, Ts, Es)
-    assert m.last_forward_kernel() == "zip-spectral-mma" and np.isfinite(whole).all()
+    assert m.last_forward_kernel() == "zip-spectral-mma2-aligned" and np.isfinite(whole).all()      # the automatic choice at K=20
+    m.set_option("zip_align", 2)
+    try:
+        lock_step = whole_set.forward_batch(pis, Ts, Es)
+        assert m.last_forward_kernel() == "zip-spectral-mma"
+    finally:
+        m.set_option("zip_align", 0)
+    np.testing.assert_allclose(lock_step, whole, rtol=1e-12)
     m.set_option("zip_spectral", 2)
     plain_form = whole_set.forward_batch(pis[:64], Ts[:64], Es[:64])
     assert m.last_forward_kernel() == "zip"

@@ -8,7 +8,7 @@ from conftest import golden_model, example_symbols, random_hmm
 pytestmark = pytest.mark.gpu
 RTOL = 1e-11
 OPTS = ("forward_kernel", "zip_ctas_per_sm", "zip_max_entries", "zip_lanes", "zip_segment_tokens", "zip_pipeline", "zip_mma", "zip_run2",
-        "zip_spectral", "zip_spectral_force_bad")
+        "zip_align", "zip_spectral", "zip_spectral_force_bad")
 
 
 @pytest.fixture(autouse=True)
@@ -89,8 +89,11 @@ def test_reference_models_all_shapes(model):
         shapes += [dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_pipeline=1), dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_pipeline=5),
                    dict(zip_mma=1, zip_run2=1, zip_segment_tokens=256), dict(zip_mma=1, zip_run2=1, zip_segment_tokens=-1, zip_max_entries=5),
                    dict(zip_run2=0)]
+        # the aligned form (one dictionary entry per warp-step, host-built schedules): whole chunks, pieces, a tiny dictionary
+        shapes += [dict(zip_mma=1, zip_align=1, zip_segment_tokens=-1, zip_pipeline=1), dict(zip_mma=1, zip_align=1, zip_segment_tokens=-1, zip_pipeline=5),
+                   dict(zip_mma=1, zip_align=1, zip_segment_tokens=-1, zip_pipeline=32), dict(zip_mma=1, zip_align=1, zip_segment_tokens=-1, zip_max_entries=6)]
     for opts in shapes:
-        for k in OPTS[1:8]:
+        for k in OPTS[1:9]:
             m.set_option(k, opts.get(k, 0))
         got = s.forward_batch(pis, Ts, Es)
         assert m.last_forward_kernel().startswith("zip-spectral"), m.last_forward_kernel()
@@ -98,6 +101,8 @@ def test_reference_models_all_shapes(model):
             assert "mma" in m.last_forward_kernel(), m.last_forward_kernel()
         if opts.get("zip_run2") == 1:
             assert "mma2" in m.last_forward_kernel(), m.last_forward_kernel()
+        if opts.get("zip_align") == 1:
+            assert m.last_forward_kernel() == "zip-spectral-mma2-aligned", m.last_forward_kernel()
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg="%s %s" % (model, opts))
         assert s.spectral_counts() == (len(pis), 0)
         one = s.forward(pis[-1], Ts[-1], Es[-1])
@@ -127,6 +132,15 @@ def test_random_reversible_hmms_every_tile(K):
             np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d mma seg=%d run2=%d" % (K, seg, r2))
             assert "mma" in m.last_forward_kernel() and s.spectral_counts() == (6, 0)
             assert ("mma2" in m.last_forward_kernel()) == (r2 == 1)
+        m.set_option("zip_run2", 0)
+        m.set_option("zip_align", 1)
+        for pipe in (1, 4):         # aligned form: whole streams, pieces
+            m.set_option("zip_segment_tokens", -1)
+            m.set_option("zip_pipeline", pipe)
+            np.testing.assert_allclose(s.forward_batch(pis, Ts, Es), want, rtol=RTOL, err_msg="K=%d aligned pipe=%d" % (K, pipe))
+            assert m.last_forward_kernel() == "zip-spectral-mma2-aligned" and s.spectral_counts() == (6, 0)
+        m.set_option("zip_align", 0)
+        m.set_option("zip_pipeline", 0)
         m.set_option("zip_mma", 0)
         m.set_option("zip_run2", 0)
         m.set_option("zip_segment_tokens", 0)

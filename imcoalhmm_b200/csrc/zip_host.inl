@@ -654,6 +654,7 @@ extern "C" int imc_seqset_run_tokens(imc_seqset* set, int chunk, int ids, uint32
 // Host-only views of the aligned form for a K-state model (tests, tools/schedule_sim.py): no CUDA call is made.
 static int align_host_streams(imc_seqset* set, int K, ZipHostStreams* h, int* M_out) {
     if (!set) return fail(IMC_ERR_INVALID, "NULL set");
+    std::lock_guard<std::recursive_mutex> lock(set->serial.mu);       // the two-run encoding is prepared once per set (host side only: no event)
     int rc = seqset_run2_prepare(set);
     if (rc) return rc;
     if (set->run2_state != 1) return fail(IMC_ERR_UNSUPPORTED, "this set has no second run symbol");

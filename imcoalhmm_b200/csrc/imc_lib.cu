@@ -766,7 +766,10 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
         const double waves = (double)N * nquads / ((double)sms * plan.ctas_per_sm * (plan.threads / 32));
         long long nseg = 1;
         if (g_ctx.opt_zip_pipeline >= 2) nseg = g_ctx.opt_zip_pipeline;
-        else if (g_ctx.opt_zip_pipeline == 0 && waves >= 1.0 && waves < 40.0) nseg = (long long)std::ceil(40.0 / waves);
+        // (also where the warps are not all busy but the POINTS do not divide among the CTAs: 256 points x 8 warp-loads on 148 SMs ran
+        // 3.26 ms as whole chunks, 2.62 ms in pieces -- the CTAs without a point of their own in the last round take pieces)
+        else if (g_ctx.opt_zip_pipeline == 0 && (waves >= 1.0 || N > sms * plan.ctas_per_sm) && waves < 40.0)
+            nseg = (long long)std::ceil(40.0 / std::max(waves, 1.0));
         nseg = std::min<long long>({nseg, 32, z->max_ntok / 256});
         if (nseg >= 2) {
             const int plen = (int)(((z->max_ntok + nseg - 1) / nseg + 15) / 16 * 16);

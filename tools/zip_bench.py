@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--sweep", default="0:0:0", help="comma list of ctas_per_sm:max_entries:lanes[:pipeline pieces[:spectral 0 auto|1|2 off[:mma 0 auto|1|2 off[:shape[:run2[:align 0 auto|1|2 off]]]]]]")
     ap.add_argument("--plain", action="store_true", help="also time the uncompressed kernel")
+    ap.add_argument("--segment", type=int, default=0, help="zip_segment_tokens: 0 auto, -1 whole chunks, > 0 segment length")
     ap.add_argument("--missing", type=float, default=0.04, help="missing-data coverage of the simulated chunks (bench.py: 0.04)")
     ap.add_argument("--check", type=int, default=2, help="chunks to check against the oracle")
     args = ap.parse_args()
@@ -72,6 +73,7 @@ def main():
         pipe = f[3] if len(f) > 3 else 0
         spec = f[4] if len(f) > 4 else 0
         m.set_option("zip_pipeline", pipe)
+        m.set_option("zip_segment_tokens", args.segment)
         m.set_option("zip_spectral", spec)
         mma = f[5] if len(f) > 5 else 0
         m.set_option("zip_mma", mma)

@@ -234,7 +234,8 @@ int imc_statespace_describe(int space, int* n_states, int* n_edges, int* counts,
  *                       instead of a product of power-of-two dictionary entries.  0 = auto (where it lowers the expected
  *                       number of DMMA passes: state counts whose dictionary hardly fits, K >= 32), 1 = always, 2 = never.
  * key "zip_align":      aligned form of the MMA shape (the chains of a warp follow one host-built schedule with a single dictionary
- *                       entry per warp-step; two-run tokens): 0 = auto (cost model), 1 = wherever it applies, 2 = off.
+ *                       entry per warp-step; two-run tokens): 0 = auto (cost model; IMC_TRACE_PLAN=1 in the environment prints its
+ *                       decision to stderr), 1 = wherever it applies, 2 = off.
  * key "zip_mma_shape":  launch shape of the MMA form: 0 = auto, 1 = one CTA of 512 threads per SM (256 for K >= 32),
  *                       2 = two CTAs of 256, 3 = four CTAs of 256 threads with 64 registers (K <= 12), 4 = four CTAs of 128.
  * key "zip_spectral_force_bad": 1 = treat every point as not qualifying (exercises the plain-form pass; tests).

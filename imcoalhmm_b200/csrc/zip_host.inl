@@ -224,7 +224,7 @@ static void zip_align_quad(const std::vector<const std::vector<uint32_t>*>& tok,
         }
     }
     if (streams)
-        for (int i = 0; i < n; ++i) while ((*streams)[i].size() % 8) (*streams)[i].push_back(RUN_NOP_BIT | 0xffu);
+        for (int i = 0; i < n; ++i) while ((*streams)[i].size() % 8) (*streams)[i].push_back(RUN_NOP_BIT | (uint32_t)hot);   // (an idle hot step)
     if (steps_out) *steps_out = (steps + 7) / 8 * 8;
 }
 
@@ -277,7 +277,7 @@ static int zip_align_pick_stall(const ZipHostStreams& h) {
 
 static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, bool sched, ZipDevice** out) {
     for (ZipDevice* z : set->zip_dev) if (z->M == M && z->spec == spec && z->run2 == run2 && z->sched == sched) { *out = z; return IMC_OK; }
-    if (sched && (!spec || M > 255)) return fail(IMC_ERR_INVALID, "the aligned form needs run tokens and at most 255 dictionary ids");
+    if (sched && !spec) return fail(IMC_ERR_INVALID, "the aligned form needs run tokens");
     const int ns = (int)set->streams.size();
     const ZipMerges& mg = run2 ? set->run2_merges : (spec ? set->run_merges : set->merges);
     const std::vector<std::vector<uint32_t>>& rfull = run2 ? set->run2_tok_full : set->run_tok_full;
@@ -360,7 +360,7 @@ static int zip_device_build(imc_seqset* set, int M, bool spec, bool run2, bool s
         off += (long long)((ntok(k) * tsz + align - 1) / align * align + align);
     }
     std::vector<uint8_t> flat((size_t)off, 0);
-    if (sched) { uint32_t* w = reinterpret_cast<uint32_t*>(flat.data()); for (size_t x = 0; x < flat.size() / 4; ++x) w[x] = RUN_NOP_BIT | 0xffu; }
+    if (sched) { uint32_t* w = reinterpret_cast<uint32_t*>(flat.data()); for (size_t x = 0; x < flat.size() / 4; ++x) w[x] = RUN_NOP_BIT | (uint32_t)hot_id; }
     long long total = 0;
     for (int i = 0; i < ns; ++i) {
         const int k = order[i];

@@ -913,18 +913,20 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         }
     };
     // aligned form: ONE entry per warp-step, the same for every chain that takes part; the others hold a no-op word that still
-    // names the step's entry (so the choice of the B operand needs no vote), 0xff in the padding behind a stream
+    // names the step's entry (so the choice of the B operand needs no vote; the padding of a stream names the hot entry)
     auto step_aligned = [&](uint32_t wb) {
         const int ids = wb & 0xffu;
-        if (ids == 0xff) return;                       // warp-uniform: the streams of a quad have one length
         const bool active = have && !(wb & RUN_NOP_BIT);
         IMC_ASSERT(ids < a.M && (wb >> 22) == 0u && __all_sync(0xffffffffu, ids == __shfl_sync(0xffffffffu, ids, 0)));
         // (a no-op word carries no run: rows 0 of the tables)
         const uint32_t tab = ptab_s + ((wb >> 20) & 1u) * (RUN_ROWS * PT * 8);
         const uint32_t pa = tab + ((wb >> 8) & RUN_LO_MASK) * (PT * 8), pb = tab + (RUN_LO_ROWS + ((wb >> (8 + RUN_LO_BITS)) & RUN_HI_MASK)) * (PT * 8);
-        double2 fa[NT], fb[NT];
+        double f[NT][2];                   // (lambda / lambda_max)^n of this token for the lane's states: independent of the products below
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { fa[t] = lds_f64x2(pa + t * 64); fb[t] = lds_f64x2(pb + t * 64); }
+        for (int t = 0; t < NT; ++t) {
+            const double2 fa = lds_f64x2(pa + t * 64), fb = lds_f64x2(pb + t * 64);
+            f[t][0] = fa.x * fb.x; f[t][1] = fa.y * fb.y;
+        }
         const long long ex = lds_s64(dexp_s + ids * 8);
         ++passes;
         double N[NT][2];
@@ -942,11 +944,15 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
 #pragma unroll
                 for (int t = 0; t < NT; ++t) dmma884(N[t][0], N[t][1], D[u >> 1][u & 1], lds_f64(bc + (u * NT + t) * 256));
         }
-        if (active) {
+        // chains that sit this step out keep their state: selects, not a branch (the lanes of a warp differ here, and a divergent
+        // region around eight DMULs costs more than the DMULs)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) { D[t][0] = N[t][0] * (fa[t].x * fb[t].x); D[t][1] = N[t][1] * (fa[t].y * fb[t].y); }
-            scale += ex;
+        for (int t = 0; t < NT; ++t) {
+            const double d0 = N[t][0] * f[t][0], d1 = N[t][1] * f[t][1];
+            D[t][0] = active ? d0 : D[t][0];
+            D[t][1] = active ? d1 : D[t][1];
         }
+        scale += active ? ex : 0ll;
     };
     uint4 cur = make_uint4(0, 0, 0, 0), cur2 = cur;
     if (nt > 0) { cur = tp[0]; cur2 = tp[1]; }
@@ -957,7 +963,7 @@ __device__ __forceinline__ void zip_run_unit_mma(const ZipArgs& a, int n, int un
         const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, cur2.x, cur2.y, cur2.z, cur2.w};
         if (SCHED) {          // streams of a quad have one length, a multiple of 8; lanes without a chain hold no-op words throughout
 #pragma unroll
-            for (int b = 0; b < 8; ++b) step_aligned(rem > 0 ? w[b] : (RUN_NOP_BIT | 0xffu));
+            for (int b = 0; b < 8; ++b) step_aligned(w[b]);
         } else if (__all_sync(0xffffffffu, rem >= 8)) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) step(w[b], true, std::true_type());

@@ -261,7 +261,8 @@ int64_t imc_kernel_launches(void);
 int imc_seqset_align_info(imc_seqset* set, int K, int stall, int64_t* lock_steps, double* est_passes, int64_t* aligned_steps,
                           int* stall_used, int* hot_id);
 /* The words of warp-load `quad` as out[nchains][steps] (tests): stall > 0 the aligned streams (bit 21 = no token of this chain in this
- * step, bits 0-7 the step's entry, 0xff in the padding), stall <= 0 the chains' own streams padded with the padding word. */
+ * step, bits 0-7 the step's entry; the padding to a multiple of 8 steps names the hot entry), stall <= 0 the chains' own streams
+ * padded to the longest with the word (1 << 21) | 0xff. */
 int imc_seqset_align_quad(imc_seqset* set, int K, int quad, int stall, uint32_t* out, int64_t capacity, int64_t* steps, int* nchains);
 int imc_mma_passes(int64_t* passes_out);
 /* name of the forward kernel chosen by the last forward call on this thread

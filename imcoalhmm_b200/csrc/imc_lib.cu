@@ -623,7 +623,7 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
 // set->d_chain[n][chunk] for the points served.
 static const int MAX_POINTS_PARTS = 32768;
-constexpr double ZIP_STEP_OVERHEAD = 200.0;        // clocks per warp-step beside the DMMAs (calibrated on configs 2, 3, 5; see profiles/r02_aligned_form.txt)
+constexpr double ZIP_STEP_OVERHEAD = 73.0;         // clocks per warp-step beside the DMMAs with every warp of the SM busy (see the aligned-form decision)
 static thread_local bool g_want_sched = false;     // aligned form (implies the two-run form) wanted, if the call turns out not to be chain-scarce
 static thread_local bool g_want_run2 = false;      // two-run form wanted for the spectral pass of the current call
 
@@ -908,12 +908,16 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                 if (set->run2_state == 1 && zip_plan(K, S, set->run2_merges.size(), &p3, 0, true, true, true) == IMC_OK &&
                     zip_device(set, p3.M, &z3, true, true, true) == IMC_OK) {
                     const ZipDevice* zl = run2 && z2 ? z2 : z1;
-                    // cost in FP64-pipe clocks of a warp: a pass is KT x NT DMMAs of 16 clocks; every warp-step also carries ~ZIP_STEP_OVERHEAD
-                    // clocks of token decoding, table look-ups and rescaling, which lock step pays once for all its passes
+                    // cost in FP64-pipe clocks of a warp: a pass is KT x NT DMMAs of 16 clocks; every warp-step also carries its own
+                    // token decoding, table look-ups and rescaling, which lock step pays once for all its passes and which hide the
+                    // better the more warps of the SM are busy (calibrated: 73 clocks with all warps busy -- config-4 and config-3
+                    // shards -- 100 with 13 of 16, config 2; profiles/r02_aligned_form.txt)
                     const int tile = zip_tile(K);
                     const double pass = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8);
-                    const double lock = (double)zl->pass_cost / zl->est_passes * (ZIP_STEP_OVERHEAD + zl->est_passes * pass);
-                    const double aligned = (double)z3->pass_cost * (ZIP_STEP_OVERHEAD + pass);
+                    const int wmax = p3.threads / 32, busy = std::min(wmax, (ns + 7) / 8);
+                    const double overhead = ZIP_STEP_OVERHEAD + 9.0 * (wmax - busy) * (16.0 / wmax);
+                    const double lock = (double)zl->pass_cost / zl->est_passes * (overhead + zl->est_passes * pass);
+                    const double aligned = (double)z3->pass_cost * (overhead + pass);
                     sched = g_ctx.opt_zip_align == 1 || aligned < 0.95 * lock;
                     if (getenv("IMC_TRACE_PLAN"))
                         fprintf(stderr, "imc plan: K=%d lock-step steps %.0f x %.2f passes (%s), aligned steps %lld -> cost %.3g vs %.3g: %s\n", K,

@@ -188,8 +188,9 @@ static int zip_device(imc_seqset* set, int M, ZipDevice** out, bool spec = false
 // follow ONE common schedule per warp-load (quad) -- a supersequence of their entry-id sequences, built here -- in which every
 // warp-step applies a single entry: chains whose next token is that entry take it, the others hold a no-op word.  One MMA pass per
 // warp-step, where lock step spends 1 + (distinct cold entries among the chains).  Schedule: hot steps until `stall` chains wait at
-// a cold entry (or no chain wants the hot one), then one step per waiting cold entry, twice (in the two-run form a chain served by
-// "into the second basis" wants "back" next).  streams[i] = words of chain i, all of one length (a multiple of 8).
+// a cold entry (or no chain wants the hot one), then a cold slot: one step per waiting cold entry, and once more for the chains that
+// moved on to another cold entry (in the two-run form a chain served by "into the second basis" wants "back" next); further rounds
+// only while they serve two chains per step.  streams[i] = words of chain i, all of one length (a multiple of 8).
 static void zip_align_quad(const std::vector<const std::vector<uint32_t>*>& tok, int hot, int stall,
                            std::vector<std::vector<uint32_t>>* streams, long long* steps_out) {
     const int n = (int)tok.size();

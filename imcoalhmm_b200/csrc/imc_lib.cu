@@ -646,8 +646,10 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
         ZipPlan mp;
         ZipDevice* mz = nullptr;
         const bool r2 = g_want_run2 && set->run2_state == 1;          // two-run form: decided by forward_local_dev before the preparation kernel
-        if (zip_plan(K, S, r2 ? set->run2_merges.size() : avail, &mp, 0, true, true, r2) == IMC_OK && zip_device(set, mp.M, &mz, true, r2) == IMC_OK &&
-            (g_ctx.opt_zip_mma == 1 || mz->hot_share >= 0.5)) {
+        g_mma_shape_hint = g_want_sched && r2 && set->parts_total == 0 && g_ctx.opt_zip_segment_tokens <= 0 ? 2 : 0;
+        const int planned = zip_plan(K, S, r2 ? set->run2_merges.size() : avail, &mp, 0, true, true, r2);
+        g_mma_shape_hint = 0;
+        if (planned == IMC_OK && zip_device(set, mp.M, &mz, true, r2) == IMC_OK && (g_ctx.opt_zip_mma == 1 || mz->hot_share >= 0.5)) {
             plan = mp; z = mz; mma = true;
         }
     }
@@ -905,8 +907,10 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                 ZipPlan p3;
                 ZipDevice* z3 = nullptr;
                 if ((rc = seqset_run2_prepare(set))) return rc;
-                if (set->run2_state == 1 && zip_plan(K, S, set->run2_merges.size(), &p3, 0, true, true, true) == IMC_OK &&
-                    zip_device(set, p3.M, &z3, true, true, true) == IMC_OK) {
+                g_mma_shape_hint = 2;
+                const int planned3 = set->run2_state == 1 ? zip_plan(K, S, set->run2_merges.size(), &p3, 0, true, true, true) : IMC_ERR_UNSUPPORTED;
+                g_mma_shape_hint = 0;
+                if (planned3 == IMC_OK && zip_device(set, p3.M, &z3, true, true, true) == IMC_OK) {
                     const ZipDevice* zl = run2 && z2 ? z2 : z1;
                     // cost in FP64-pipe clocks of a warp: a pass is KT x NT DMMAs of 16 clocks; every warp-step also carries its own
                     // token decoding, table look-ups and rescaling, which lock step pays once for all its passes and which hide the
@@ -914,10 +918,12 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                     // shards -- 100 with 13 of 16, config 2; profiles/r02_aligned_form.txt)
                     const int tile = zip_tile(K);
                     const double pass = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8);
-                    const int wmax = p3.threads / 32, busy = std::min(wmax, (ns + 7) / 8);
-                    const double overhead = ZIP_STEP_OVERHEAD + 9.0 * (wmax - busy) * (16.0 / wmax);
-                    const double lock = (double)zl->pass_cost / zl->est_passes * (overhead + zl->est_passes * pass);
-                    const double aligned = (double)z3->pass_cost * (overhead + pass);
+                    auto overhead = [&](const ZipPlan& p) {       // per warp-step, by the warps of the SM that the plan keeps busy
+                        const int wcta = p.threads / 32, wmax = wcta * p.ctas_per_sm, busy = p.ctas_per_sm * std::min(wcta, (ns + 7) / 8);
+                        return ZIP_STEP_OVERHEAD + 9.0 * (wmax - busy) * (16.0 / wmax);
+                    };
+                    const double lock = (double)zl->pass_cost / zl->est_passes * (overhead(run2 && z2 ? p2 : p1) + zl->est_passes * pass);
+                    const double aligned = (double)z3->pass_cost * (overhead(p3) + pass);
                     sched = g_ctx.opt_zip_align == 1 || aligned < 0.95 * lock;
                     if (getenv("IMC_TRACE_PLAN"))
                         fprintf(stderr, "imc plan: K=%d lock-step steps %.0f x %.2f passes (%s), aligned steps %lld -> cost %.3g vs %.3g: %s\n", K,

@@ -37,6 +37,7 @@ static int zip_default_lanes(int K) { return (K >= 8 && K <= 24 && K != 10) ? 4 
 // MMA form (ZipCfgM): spectral form, tiles >= 8 states
 static bool zip_mma_tile(int K) { return K >= 8; }
 static thread_local int g_plan_chunks = 0;     // chunks of the set being planned for (0 = unknown), set by zip_pass
+static thread_local int g_mma_shape_hint = 0;           // launch shape zip_plan uses for the MMA form when the option says auto (set while planning the aligned form)
 static unsigned long long* g_mma_passes = nullptr;      // device counter (ZipArgs::mma_passes)
 
 template <int K, bool SPEC>
@@ -53,7 +54,10 @@ static ZipPlan zip_plan_k(int S, int avail_ids, int want_ctas, int want_lanes, b
             using C = ZipCfgM<K>;
             int shape = (int)g_ctx.opt_zip_mma_shape;
             // a point offers ceil(chunks / 8) independent warp-loads at a time: CTAs with more warps than that would idle
-            if (shape == 0) shape = 1;       // measured on B200 (c2: 3.52 vs 3.70 ms, K=20: 12.4 vs 13.2 ms with two CTAs of 256)
+            // lock step: one CTA (c2: 3.52 vs 3.70 ms, K=20: 12.4 vs 13.2 ms with two CTAs of 256).  Aligned form (g_mma_shape_hint): two
+            // CTAs -- its dictionary is small, two points in flight fill the warps a single point leaves idle and hide each other's
+            // dictionary builds (c2: 3.15 vs 3.48 ms; 128 / 192 chunks: 3.64 / 5.20 vs 3.90 / 5.57; K=20, 100 chunks: 15.8 vs 17.4 ms)
+            if (shape == 0) shape = g_mma_shape_hint ? g_mma_shape_hint : 1;
             if (K > 24) shape = 1;
             if (K > 12 && shape == 3) shape = 2;
             p.mma = true;

@@ -42,8 +42,15 @@ def test_full_size_properties(full_c2):
     info = whole_set.zip_info(10)
     assert info["tokens"] * 100 < whole_set.total_sites            # > 100x compression on this alignment
     whole = whole_set.forward_batch(pis, Ts, Es)
-    assert m.last_forward_kernel() == "zip-spectral-mma" and np.isfinite(whole).all()      # the automatic choice on this alignment
+    assert m.last_forward_kernel() == "zip-spectral-mma2-aligned" and np.isfinite(whole).all()     # the automatic choice on this alignment
     assert whole_set.spectral_counts() == (256, 0)
+    m.set_option("zip_align", 2)                                   # the lock-step one-run form on the same streams
+    try:
+        lock_step = whole_set.forward_batch(pis, Ts, Es)
+        assert m.last_forward_kernel() == "zip-spectral-mma"
+    finally:
+        m.set_option("zip_align", 0)
+    np.testing.assert_allclose(lock_step, whole, rtol=1e-12)
     assert whole_set.run_info(10)["tokens"] * 250 < whole_set.total_sites  # > 250 sites per mat-vec
     # the FMA shape of the spectral form, then the plain form (pair dictionary, no eigenbasis), on the same 1e8 sites
     m.set_option("zip_mma", 2)

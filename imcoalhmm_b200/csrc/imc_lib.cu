@@ -623,7 +623,7 @@ static int launch_chain_reduce(const double* chain, int ns, int N, double* d_out
 // spec: spectral form over run tokens (points of the ok list), else the plain form (pass 1 scratch).  Results land in
 // set->d_chain[n][chunk] for the points served.
 static const int MAX_POINTS_PARTS = 32768;
-constexpr double ZIP_STEP_OVERHEAD = 73.0;         // clocks per warp-step beside the DMMAs with every warp of the SM busy (see the aligned-form decision)
+constexpr double ZIP_STEP_LATENCY = 120.0;         // clocks of a lone warp's step beside twice its FP64 pipe time (see the aligned-form decision)
 static thread_local bool g_want_sched = false;     // aligned form (implies the two-run form) wanted, if the call turns out not to be chain-scarce
 static thread_local bool g_want_run2 = false;      // two-run form wanted for the spectral pass of the current call
 
@@ -654,6 +654,8 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
         }
     }
     const bool try_sched = mma && z->run2 && g_want_sched && set->parts_total == 0 && g_ctx.opt_zip_segment_tokens <= 0;
+    ZipDevice* zs = nullptr;           // the aligned streams of the same dictionary
+    if (try_sched && (rc = zip_device(set, z->M, &zs, true, true, true))) return rc;
     // ---- chain-scarce call (few chunks x few points)?  Three ways to run it, chosen by a cost model in SM clocks whose
     // constants come from the round-1 measurements (profiles/r01_latency_single_point.txt):
     //   (a) as it is: every chain walks its whole chunk; a lone chain advances one step per ~lat clocks
@@ -684,19 +686,29 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             double best = cost_seg(z->max_ntok);          // (a)
             long long best_seg = -1;
             int best_lanes = plan.lanes;
+            if (zs) {
+                // (a') whole chunks in the aligned form: ~330 clocks per step of a lone warp (8 chunks x 256 points: 1.00 ms where
+                // the warp-per-chain shape took 1.63; 16 chunks: 1.27 vs 2.47 ms), one set of DMMAs per step when the SMs fill up
+                const int tile = zip_tile(K);
+                const double P = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8) + 8.0 * ((tile + 7) / 8);
+                best = std::min(best, std::max((ZIP_STEP_LATENCY + 2.0 * P) * zs->max_ntok, 1.3 * (double)zs->pass_cost * N * P / 0.8 / (4.0 * sms)));
+            }
             if (seglen == 0) {
                 for (long long sl = 64; sl < z->max_ntok; sl *= 2) {        // (c)
                     const double t = cost_seg(sl);
                     if (t < 0.8 * best) { best = t; best_seg = sl; }
                 }
             }
-            if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0 && g_ctx.opt_zip_mma != 1) {   // (b)
+            // (the warp-per-chain shape is for a handful of chains; a batch large enough for the aligned form -- >= 1024 chains -- is
+            // not: 8 / 16 chunks x 256 points took 1.63 / 2.47 ms there, 1.00 / 1.27 ms aligned)
+            if (g_ctx.opt_zip_lanes == 0 && zip_tile(K) >= 10 && seglen <= 0 && g_ctx.opt_zip_mma != 1 && !zs) {   // (b)
                 const long long warps = (long long)sms * (zip_tile(K) <= 24 ? 16 : 8);
                 const double rounds = std::ceil((double)((long long)N * ns) / (double)warps);
                 const double t = rounds * z->max_ntok * lat32;
                 if (t < best) { best = t; best_seg = -1; best_lanes = 32; }
             }
             if (seglen == 0) seglen = best_seg;
+            if (best_seg > 0 || best_lanes != plan.lanes) zs = nullptr;          // segments or the warp shape won: lock-step forms
             if (best_lanes != plan.lanes) {
                 if ((rc = zip_plan(K, S, avail, &plan, best_lanes, spec))) return rc;
                 if ((rc = zip_device(set, plan.M, &z, spec))) return rc;
@@ -704,11 +716,7 @@ static int zip_pass(imc_seqset* set, int N, int K, int S, const double* d_pi, co
             }
         }
     }
-    if (try_sched && mma && seglen <= 0) {       // not chain-scarce, not segmented: the aligned streams of the same dictionary
-        ZipDevice* zs = nullptr;
-        if ((rc = zip_device(set, z->M, &zs, true, true, true))) return rc;
-        z = zs;
-    }
+    if (zs && mma && seglen <= 0) z = zs;        // not segmented, not the warp shape: the aligned streams
     ZipArgs za;
     za.tokens = (const uint8_t*)z->tokens.p;
     za.chunks = (const ZipChunk*)z->chunks.p;
@@ -912,18 +920,20 @@ static int forward_local_dev(imc_seqset* set, int N, int K, int S, const double*
                 g_mma_shape_hint = 0;
                 if (planned3 == IMC_OK && zip_device(set, p3.M, &z3, true, true, true) == IMC_OK) {
                     const ZipDevice* zl = run2 && z2 ? z2 : z1;
-                    // cost in FP64-pipe clocks of a warp: a pass is KT x NT DMMAs of 16 clocks; every warp-step also carries its own
-                    // token decoding, table look-ups and rescaling, which lock step pays once for all its passes and which hide the
-                    // better the more warps of the SM are busy (calibrated: 73 clocks with all warps busy -- config-4 and config-3
-                    // shards -- 100 with 13 of 16, config 2; profiles/r02_aligned_form.txt)
-                    const int tile = zip_tile(K);
-                    const double pass = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8);
-                    auto overhead = [&](const ZipPlan& p) {       // per warp-step, by the warps of the SM that the plan keeps busy
-                        const int wcta = p.threads / 32, wmax = wcta * p.ctas_per_sm, busy = p.ctas_per_sm * std::min(wcta, (ns + 7) / 8);
-                        return ZIP_STEP_OVERHEAD + 9.0 * (wmax - busy) * (16.0 / wmax);
+                    // Clocks per parameter point and SM.  A warp-step holds the FP64 pipe of its sub-partition for P clocks (its passes
+                    // of KT x NT DMMAs of 16 clocks, the DMULs of the table factors) and takes a lone warp ~120 + 2 P clocks (measured
+                    // at K=10: 570 in lock step, ~330 aligned); with W warps of the SM busy a round of one step each takes
+                    // max(latency, W / 4 x P / 0.8), and a point is steps x warp-loads / W rounds.  Reproduces configs 2-5 and the
+                    // few-chunk cases of profiles/r02_aligned_form.txt within 15 %; the aligned form has to win by 5 %.
+                    const int tile = zip_tile(K), nq = (ns + 7) / 8;
+                    const double pass = 16.0 * ((tile + 3) / 4) * ((tile + 7) / 8), dmul = 8.0 * ((tile + 7) / 8);
+                    auto point_cost = [&](const ZipPlan& p, double quad_steps, double passes) {
+                        const int W = p.ctas_per_sm * std::min(p.threads / 32, nq);
+                        const double P = passes * pass + dmul;
+                        return quad_steps * std::max(ZIP_STEP_LATENCY + 2.0 * P, W / 4.0 * P / 0.8) / W;
                     };
-                    const double lock = (double)zl->pass_cost / zl->est_passes * (overhead(run2 && z2 ? p2 : p1) + zl->est_passes * pass);
-                    const double aligned = (double)z3->pass_cost * (overhead(p3) + pass);
+                    const double lock = point_cost(run2 && z2 ? p2 : p1, (double)zl->pass_cost / zl->est_passes, zl->est_passes);
+                    const double aligned = point_cost(p3, (double)z3->pass_cost, 1.0);
                     sched = g_ctx.opt_zip_align == 1 || aligned < 0.95 * lock;
                     if (getenv("IMC_TRACE_PLAN"))
                         fprintf(stderr, "imc plan: K=%d lock-step steps %.0f x %.2f passes (%s), aligned steps %lld -> cost %.3g vs %.3g: %s\n", K,
